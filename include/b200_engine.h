@@ -1,0 +1,94 @@
+/*
+ * b200_engine.h — the thin C-ABI layer between the darknet-compatible host code (plain C) and the
+ * hand-written sm_100a CUDA kernels, plus the ADDITIVE batched entry points (SURVEY.md §8b "Batch
+ * semantics").  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Everything here is exported from libdarknet.so next to the reference-compatible symbols declared
+ * in darknet.h.  Functions that touch the device fail loudly (message on stderr + abort()) when no
+ * CUDA device / driver is available: there is NO CPU fallback anywhere in the product path.
+ */
+#ifndef B200_ENGINE_H
+#define B200_ENGINE_H
+#include "darknet.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- precision of the activation path ---------------------------------------------------------- */
+#define B200_PREC_BF16 0   /* NHWC bf16 activations, tcgen05 implicit-GEMM convs, fp32 accumulate (default) */
+#define B200_PREC_FP32 1   /* NHWC fp32 activations, CUDA-core fp32 convs: the rtol 1e-4 parity mode        */
+void b200_set_default_precision(int prec);     /* applies to networks parsed afterwards (env B200_PRECISION=fp32|bf16 too) */
+int  b200_get_precision(const network *net);
+
+/* conv kernel selection for the bf16 path: 0 = auto (tcgen05 wherever the shape allows), 1 = force CUDA-core kernel */
+void b200_set_conv_backend(network *net, int backend);
+
+/* When 0, network_predict() leaves head-layer outputs on the device (no D2H of l.output / net->output);
+ * the batched detection entry points below never need the host copy.  Default 1 = reference behaviour
+ * (network.c:505, yolo_layer.c:359-362: heads are valid host fp32 NCHW after every predict). */
+void b200_set_head_sync(network *net, int on);
+
+/* ---- opaque engine, one per network -------------------------------------------------------------- */
+typedef struct b200_engine b200_engine;
+b200_engine *b200_engine_of(const network *net);
+
+/* host code → device, called by parse_network_cfg / load_weights / free_network */
+b200_engine *b200_engine_create(network *net, int precision);   /* plans buffers from the layer array      */
+void b200_engine_destroy(b200_engine *e);
+void b200_engine_upload_weights(b200_engine *e, network *net);    /* BN folding + repack (+ bf16 cast) + H2D */
+
+/* forward_network replacement (network.c:188-211).  `input` is HOST fp32 NCHW, batch*inputs floats. */
+void b200_engine_forward(b200_engine *e, network *net, const float *input);
+/* same, but the input is ALREADY resident on the device (fp32 NCHW): the timed region of bench.py's `value` */
+void b200_engine_forward_resident(b200_engine *e, network *net);
+float *b200_engine_input_device(b200_engine *e);                  /* device fp32 NCHW staging buffer          */
+void b200_engine_sync(b200_engine *e);
+
+/* weights arena: one contiguous device allocation holding every folded/repacked parameter, so that
+ * multi-GPU replicas are initialised with ONE NCCL broadcast. */
+void *b200_weights_arena(network *net, size_t *bytes);
+
+/* ---- test / inspection hooks (teacher-forced per-layer parity) ----------------------------------- */
+/* copies layer i's device output into host fp32 NCHW (darknet layout); `out` needs batch*outputs floats */
+void b200_fetch_layer_output(network *net, int i, float *out);
+/* overwrites layer i's device output from host fp32 NCHW */
+void b200_set_layer_output(network *net, int i, const float *in);
+/* runs layers [start, end) on the device using whatever currently sits in their input buffers */
+void b200_run_layers(network *net, int start, int end);
+/* name of the kernel family that executes layer i ("conv_tc", "conv_simt", "conv_stem", "maxpool", ...) */
+const char *b200_layer_kernel(network *net, int i);
+/* number of kernels launched by this library since process start (bench.py's gpu_launches) */
+unsigned long long b200_launch_count(void);
+
+/* ---- additive batched box extraction + NMS ------------------------------------------------------- */
+/* get_network_boxes for batch item b (the reference only ever reads item 0: yolo_layer.c:281,326). */
+detection *get_network_boxes_batch(network *net, int b, int w, int h, float thresh, float hier,
+                                   int *map, int relative, int *num);
+
+/* compact record produced by the fused device path: one per surviving (box, class) pair */
+typedef struct {
+    int   image;        /* batch index                      */
+    int   cls;          /* class id                         */
+    int   box_id;       /* global anchor index inside the image: concatenated heads, cell-major anchor-minor like get_*_detections */
+    float prob;         /* objectness * class prob (post NMS, > thresh) */
+    float objectness;
+    box   bbox;         /* corrected exactly like correct_yolo_boxes / correct_region_boxes */
+} b200_det;
+
+/* network_predict + get_network_boxes + do_nms_sort for EVERY image of the batch, entirely on the device:
+ * decode with warp-ballot compaction, class-wise bitmask NMS, and only the kept records cross PCIe.
+ * `input` host fp32 NCHW (NULL = use the resident device input).  Returns the number of records written
+ * to `out` (at most max_out); counts[b] (may be NULL) receives the per-image candidate count before NMS. */
+int b200_detect_batch(network *net, const float *input, int w, int h, float thresh, float nms_thresh,
+                      int relative, b200_det *out, int max_out, int *counts);
+
+/* device NMS on caller-provided host boxes (the kernel behind do_nms_sort); exposed for parity tests:
+ * boxes[n*4] (x,y,w,h), probs[n*classes] row-major, modified in place exactly like box.c:58-89 zeroes prob[k]. */
+void b200_nms_sort_arrays(const float *boxes, float *probs, int n, int classes, float thresh);
+void b200_nms_obj_arrays(const float *boxes, float *objectness, int n, float thresh, unsigned char *suppressed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

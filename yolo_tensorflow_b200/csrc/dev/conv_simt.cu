@@ -1,0 +1,173 @@
+// conv_simt.cu — CUDA-core convolutions.
+//
+//  * conv_stem_kernel: the network's first layer (C_in <= 4).  Reads the caller's fp32 NCHW image directly,
+//    so the NCHW->NHWC / fp32->bf16 boundary conversion costs no extra pass, and writes NHWC.
+//  * conv_simt_kernel: generic implicit GEMM (64 pixels x 64 filters x 16 K per step, fp32 accumulate).
+//    It is the arithmetic of the fp32-exact mode (B200_PREC_FP32, rtol 1e-4 against the reference) and the
+//    fallback of the bf16 mode for shapes the tcgen05 kernel does not take.
+//
+// Both restate forward_convolutional_layer (convolutional_layer.c:445-485): out[m][n] = sum_k W[m][k]*col[k][n]
+// with zero padding (im2col.c:3-12), then the inference batch-norm as a per-filter scale/shift
+// ((x-mean)/(sqrt(var)+1e-6)*gamma+beta, blas.c:147-158, batchnorm_layer.c:150-154) or the plain bias, then the
+// activation.  K is walked in (ky,kx,c) order here instead of the reference's (c,ky,kx): the weights are
+// repacked to match at load time, only the fp32 summation order differs.
+#include "kernels.h"
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(256)
+conv_stem_kernel(const float *__restrict__ in, int N, int H, int W, int C, T *__restrict__ out, int OH, int OW, int ldo,
+                 int Cout, int size, int stride, int pad, const T *__restrict__ wt, const float *__restrict__ scale,
+                 const float *__restrict__ shift, int act)
+{
+    extern __shared__ float ws[];                    // [K][Cout] fp32
+    const int K = size * size * C;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+        int k = i / Cout, co = i % Cout;
+        ws[i] = Elem<T>::load(wt + (size_t)co * K + k);
+    }
+    __syncthreads();
+    const long long total = (long long)N * OH * OW;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+        const float *img = in + (size_t)n * C * H * W;
+        for (int c0 = 0; c0 < Cout; c0 += 32) {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            for (int ky = 0; ky < size; ++ky) {
+                int y = oy * stride + ky - pad;
+                if (y < 0 || y >= H) continue;
+                for (int kx = 0; kx < size; ++kx) {
+                    int x = ox * stride + kx - pad;
+                    if (x < 0 || x >= W) continue;
+                    for (int c = 0; c < C; ++c) {
+                        float v = __ldg(img + ((size_t)c * H + y) * W + x);
+                        const float *wrow = ws + ((ky * size + kx) * C + c) * Cout + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = fmaf(v, wrow[j], acc[j]);   // reads past Cout stay inside ws? guarded below
+                    }
+                }
+            }
+            T *dst = out + (size_t)pix * ldo + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int co = c0 + j;
+                if (co < Cout) Elem<T>::store(dst + j, apply_act<EXACT>(fmaf(acc[j], scale[co], shift[co]), act));
+            }
+        }
+    }
+}
+
+void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
+{
+    int K = p.size * p.size * c;
+    // ws is read 32 filters at a time: pad the allocation so the tail chunk stays in bounds
+    size_t smem = ((size_t)K * out.c + 32) * sizeof(float);
+    long long pixels = (long long)n * out.h * out.w;
+    int grid = (int)((pixels + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (out.dtype == DT_F32) {
+        B200_CHECK(cudaFuncSetAttribute(conv_stem_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_stem_kernel<float, true><<<grid, 256, smem, s>>>(in_nchw, n, h, w, c, (float *)out.p, out.h, out.w, out.ld, out.c,
+                                                                  p.size, p.stride, p.pad, (const float *)p.w, p.scale, p.shift, p.act);
+    } else {
+        B200_CHECK(cudaFuncSetAttribute(conv_stem_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_stem_kernel<bf16, false><<<grid, 256, smem, s>>>(in_nchw, n, h, w, c, (bf16 *)out.p, out.h, out.w, out.ld, out.c,
+                                                                  p.size, p.stride, p.pad, (const bf16 *)p.w, p.scale, p.shift, p.act);
+    }
+    B200_LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic implicit GEMM: block tile 64 pixels x 64 filters, K step 16, 256 threads, 4x4 outputs per thread
+// ---------------------------------------------------------------------------------------------------
+#define SB_M 64
+#define SB_N 64
+#define SB_K 16
+
+template <typename T, typename TO, bool EXACT>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const T *__restrict__ in, int N, int H, int W, int C, int ldi, TO *__restrict__ out, int OH, int OW, int ldo,
+                 int Cout, int size, int stride, int pad, const T *__restrict__ wt, const float *__restrict__ scale,
+                 const float *__restrict__ shift, int act)
+{
+    __shared__ float As[SB_K][SB_M + 4];
+    __shared__ float Bs[SB_K][SB_N + 4];
+    const int K = size * size * C;
+    const long long M = (long long)N * OH * OW;
+    const long long m0 = (long long)blockIdx.x * SB_M;
+    const int n0 = blockIdx.y * SB_N;
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;          // tx -> filters, ty -> pixels
+
+    // loader roles: thread loads A[pixel = tid/4][k = (tid%4)*4 .. +4) and B[filter = tid/4][same k range]
+    const int lrow = tid / 4, lk = (tid % 4) * 4;
+    const long long apix = m0 + lrow;
+    int aox = 0, aoy = 0, an = 0;
+    const bool apix_ok = apix < M;
+    if (apix_ok) { aox = (int)(apix % OW); aoy = (int)((apix / OW) % OH); an = (int)(apix / ((long long)OW * OH)); }
+    const int bco = n0 + lrow;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += SB_K) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + lk + j;
+            float a = 0.f, b = 0.f;
+            if (k < K) {
+                int tap = k / C, c = k - tap * C;
+                int ky = tap / size, kx = tap - ky * size;
+                int y = aoy * stride + ky - pad, x = aox * stride + kx - pad;
+                if (apix_ok && y >= 0 && y < H && x >= 0 && x < W)
+                    a = Elem<T>::load(in + (((size_t)an * H + y) * W + x) * ldi + c);
+                if (bco < Cout) b = Elem<T>::load(wt + (size_t)bco * K + k);
+            }
+            As[lk + j][lrow] = a;
+            Bs[lk + j][lrow] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SB_K; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        long long pix = m0 + ty * 4 + i;
+        if (pix >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = n0 + tx * 4 + j;
+            if (co < Cout) Elem<TO>::store(out + pix * ldo + co, apply_act<EXACT>(fmaf(acc[i][j], scale[co], shift[co]), act));
+        }
+    }
+}
+
+void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s)
+{
+    long long M = (long long)out.n * out.h * out.w;
+    dim3 grid(div_up(M, SB_M), div_up(out.c, SB_N));
+#define SIMT_ARGS(TI, TO) (const TI *)in.p, in.n, in.h, in.w, in.c, in.ld, (TO *)out.p, out.h, out.w, out.ld, out.c, p.size, p.stride, \
+                          p.pad, (const TI *)p.w, p.scale, p.shift, p.act
+    if (in.dtype == DT_F32 && out.dtype == DT_F32) conv_simt_kernel<float, float, true><<<grid, 256, 0, s>>>(SIMT_ARGS(float, float));
+    else if (in.dtype == DT_BF16 && out.dtype == DT_BF16) conv_simt_kernel<bf16, bf16, false><<<grid, 256, 0, s>>>(SIMT_ARGS(bf16, bf16));
+    else if (in.dtype == DT_BF16 && out.dtype == DT_F32) conv_simt_kernel<bf16, float, false><<<grid, 256, 0, s>>>(SIMT_ARGS(bf16, float));
+    else { fprintf(stderr, "b200-darknet: conv_simt: unsupported dtype pair\n"); abort(); }
+#undef SIMT_ARGS
+    B200_LAUNCHED();
+}

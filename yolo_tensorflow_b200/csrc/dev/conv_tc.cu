@@ -1,0 +1,467 @@
+// conv_tc.cu — the fused implicit-GEMM convolution on 5th-generation tensor cores (sm_100a only).
+//
+// What it replaces: forward_convolutional_layer's im2col_cpu + gemm_nn + batch-norm + activate_array
+// (convolutional_layer.c:445-485, im2col.c:16-39, gemm.c:74-89, batchnorm_layer.c:150-154) as ONE kernel:
+//
+//   D[pixel, filter] = sum over (ky,kx,c) of  X[n, oy*s+ky-pad, ox*s+kx-pad, c] * W[filter, ky, kx, c]
+//   out = act(D * scale[filter] + shift[filter])            (folded inference BN / bias, leaky, cast)
+//
+//   * GEMM M = output pixels (128 per tile = the 128 TMEM lanes), N = filters (<= 256 per tile), K = taps x C_in.
+//   * A operand: never materialised.  For every filter tap the TMA engine gathers a [pixels x BLOCK_K channels]
+//     box of the NHWC activation straight into 128B/64B/32B-swizzled shared memory; image borders are the TMA
+//     out-of-bounds zero fill (= im2col's zero padding), stride-2 layers read one of four parity-phase views of
+//     the tensor.  1x1 layers use a dense 2-D [pixels][C] view, 3x3 layers a 4-D (C,W,H,N) view with a
+//     rectangular (TW x TH x TN) pixel tile chosen per layer to fill the 128 rows.
+//   * B operand: weights repacked [C_out][ky][kx][C_in] (K-major), 2-D TMA box [BLOCK_N x BLOCK_K].
+//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one elected thread, accumulators in TMEM,
+//     double-buffered (2 x BLOCK_N columns) so the epilogue of tile t overlaps the mainloop of tile t+1.
+//   * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
+//     (tcgen05.ld -> scale/shift/leaky -> bf16 or fp32 -> 16-byte global stores, NHWC with row pitch ldo so a
+//     layer can write into a channel slice of a concat buffer).
+//   * Persistent: grid = min(tiles, #SM); tiles are walked filter-tile-fastest so co-running CTAs share A in L2.
+//
+// Roofline: tensor pipe.  FLOPs per launch = 2 * pixels * C_out * K (darknet's own BFLOPs formula,
+// convolutional_layer.c:325).
+#include "kernels.h"
+#include <cuda.h>
+#include <string>
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------------
+struct alignas(64) ConvTcMaps {
+    CUtensorMap a[4];        // mode 0: a[0] dense [pixels][C]; mode 1: a[py*2+px] parity-phase views (stride 1 uses a[0])
+    CUtensorMap b;           // weights [cout_pad][K]
+};
+
+struct ConvTcArgs {
+    int mode;                // 0 = dense rows (1x1), 1 = spatial tiles
+    int batch, OH, OW, cout_pad, ldo;
+    int size, stride, pad, cin_blocks;
+    int TW, TH, TN, tiles_x, tiles_y;
+    int m_tiles, n_tiles, block_n, num_kblocks, stages;
+    int a_rows;              // rows the A box really carries (<= 128)
+    int b_stage_bytes;       // 1024-aligned
+    int tmem_cols;
+    int act;
+    long long npix;
+    const float *scale, *shift;
+    void *out;
+};
+
+static constexpr int kTcThreads = 192;
+
+// shared-memory descriptor for a K-major operand tile whose rows are BLOCK_K*2 bytes (= the swizzle span)
+template <int BLOCK_K> __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    constexpr uint64_t layout = BLOCK_K == 64 ? 2 : (BLOCK_K == 32 ? 4 : 6);      // SWIZZLE_128B / 64B / 32B
+    constexpr uint64_t sbo = (8 * BLOCK_K * 2) >> 4;                                // 8 rows
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int BLOCK_K, typename OutT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = 128 * BLOCK_K * 2;
+    const int stages = args.stages;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)stages * A_BYTES;
+    uint8_t *aux = sB + (size_t)stages * args.b_stage_bytes;
+    uint64_t *full = (uint64_t *)aux;                 // [stages]
+    uint64_t *empty = full + 8;                       // [stages]
+    uint64_t *tfull = empty + 8;                      // [2]
+    uint64_t *tempty = tfull + 2;                     // [2]
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    float *s_scale = (float *)(aux + 256);            // [2][256]
+    float *s_shift = s_scale + 512;                   // [2][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = args.m_tiles * args.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(args.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)(args.a_rows * BLOCK_K * 2 + args.block_n * BLOCK_K * 2);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % args.n_tiles, m_tile = tile / args.n_tiles;
+                int ox0 = 0, oy0 = 0, n0 = 0;
+                if (args.mode == 1) {
+                    int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
+                    ox0 = tx * args.TW; oy0 = ty * args.TH; n0 = tn * args.TN;
+                }
+                for (int kb = 0; kb < args.num_kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], tx_bytes);
+                    const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
+                    void *dstA = sA + (size_t)stage * A_BYTES;
+                    if (args.mode == 0) {
+                        tma_load_2d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, m_tile * 128);
+                    } else {
+                        const int ky = tap / args.size, kx = tap - ky * args.size;
+                        int dy = ky - args.pad, dx = kx - args.pad;
+                        if (args.stride == 1) {
+                            tma_load_4d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, ox0 + dx, oy0 + dy, n0);
+                        } else {                  // stride 2: input x = 2*ox + dx  ->  phase dx&1, offset floor(dx/2)
+                            int px = dx & 1, py = dy & 1;
+                            int xoff = (dx - px) / 2, yoff = (dy - py) / 2;
+                            tma_load_4d(&maps.a[py * 2 + px], dstA, &full[stage], cb * BLOCK_K, ox0 + xoff, oy0 + yoff, n0);
+                        }
+                    }
+                    tma_load_2d(&maps.b, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.block_n >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * args.block_n);
+                for (int kb = 0; kb < args.num_kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc<BLOCK_K>(smem_u32(sA + (size_t)stage * A_BYTES));
+                    const uint64_t bdesc = make_desc<BLOCK_K>(smem_u32(sB + (size_t)stage * args.b_stage_bytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty[stage]);                 // frees the smem slot once these MMAs have read it
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[acc]);                       // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================== epilogue (warps 2..5) ============================
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may touch
+        const int row = quarter * 32 + lane;
+        const int ep_tid = threadIdx.x - 64;
+        int acc = 0; uint32_t acc_phase = 0;
+        constexpr int VEC = 16 / (int)sizeof(OutT);           // elements per 16-byte store
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % args.n_tiles, m_tile = tile / args.n_tiles;
+            const int col0 = n_tile * args.block_n;
+            for (int c = ep_tid; c < args.block_n; c += 128) {
+                int co = col0 + c;
+                s_scale[acc * 256 + c] = co < args.cout_pad ? args.scale[co] : 0.f;
+                s_shift[acc * 256 + c] = co < args.cout_pad ? args.shift[co] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // which output pixel does this TMEM lane hold?
+            long long pix = -1;
+            if (args.mode == 0) {
+                long long p = (long long)m_tile * 128 + row;
+                if (p < args.npix) pix = p;
+            } else {
+                int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
+                int rx = row % args.TW, ry = (row / args.TW) % args.TH, rn = row / (args.TW * args.TH);
+                int ox = tx * args.TW + rx, oy = ty * args.TH + ry, n = tn * args.TN + rn;
+                if (row < args.a_rows && ox < args.OW && oy < args.OH && n < args.batch) pix = ((long long)n * args.OH + oy) * args.OW + ox;
+            }
+            OutT *orow = pix >= 0 ? (OutT *)args.out + pix * args.ldo + col0 : nullptr;
+
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
+            const float *sc = s_scale + acc * 256, *sh = s_shift + acc * 256;
+            for (int c0 = 0; c0 < args.block_n; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c0, r);
+                tmem_ld_wait();
+                if (orow) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float y = fmaf(__uint_as_float(r[j]), sc[c0 + j], sh[c0 + j]);
+                        if (args.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
+                        else if (args.act == ACT_RELU) y = y > 0.f ? y : 0.f;
+                        else if (args.act == ACT_LOGISTIC) y = 1.f / (1.f + __expf(-y));
+                        v[j] = y;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += VEC)
+                        if (col0 + c0 + j < args.cout_pad) store_vec<OutT>(orow + c0 + j, v + j);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(args.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side: tensor maps + plan
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        B200_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { fprintf(stderr, "b200-darknet: cuTensorMapEncodeTiled unavailable\n"); abort(); }
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int block_k)
+{
+    return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+static void encode(CUtensorMap *map, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+                   const cuuint32_t *box, int block_k)
+{
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides_bytes, box, ones,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "b200-darknet: cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu box %u %u\n", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        abort();
+    }
+}
+
+struct ConvTcPlan {
+    ConvTcMaps maps;
+    ConvTcArgs args;
+    int block_k, out_dtype, grid;
+    size_t smem_bytes;
+    double flops;
+    std::string desc;
+};
+
+template <int BLOCK_K, typename OutT> static void launch_variant(ConvTcPlan *p, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_K, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    conv_tc_kernel<BLOCK_K, OutT><<<p->grid, kTcThreads, p->smem_bytes, s>>>(p->maps, p->args);
+}
+
+void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
+{
+    if (p->out_dtype == DT_BF16) {
+        if (p->block_k == 64) launch_variant<64, bf16>(p, s);
+        else if (p->block_k == 32) launch_variant<32, bf16>(p, s);
+        else launch_variant<16, bf16>(p, s);
+    } else {
+        if (p->block_k == 64) launch_variant<64, float>(p, s);
+        else if (p->block_k == 32) launch_variant<32, float>(p, s);
+        else launch_variant<16, float>(p, s);
+    }
+    B200_LAUNCHED();
+}
+
+void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
+const char *conv_tc_plan_desc(ConvTcPlan *p) { return p->desc.c_str(); }
+
+ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual)
+{
+    if (residual) return nullptr;                               // (residual fusion: later round)
+    if (in.dtype != DT_BF16) return nullptr;
+    if (getenv("B200_DISABLE_TC")) return nullptr;
+    const int C = in.c;
+    int block_k = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 0));
+    if (!block_k) return nullptr;
+    if (cp.stride != 1 && cp.stride != 2) return nullptr;
+    if (in.ld % 8 != 0 || ((uintptr_t)in.p & 15) || ((uintptr_t)out.p & 15)) return nullptr;
+    if ((out.ld * dt_size(out.dtype)) % 16 != 0 || out.ld < cp.cout_pad) return nullptr;
+    if (cp.cout_pad % 16 != 0) return nullptr;
+
+    ConvTcPlan *p = new ConvTcPlan();
+    memset(&p->maps, 0, sizeof p->maps);
+    ConvTcArgs &a = p->args;
+    memset(&a, 0, sizeof a);
+    p->block_k = block_k;
+    p->out_dtype = out.dtype;
+    const int K = cp.size * cp.size * C;
+    a.batch = in.n; a.OH = out.h; a.OW = out.w; a.cout_pad = cp.cout_pad; a.ldo = out.ld;
+    a.size = cp.size; a.stride = cp.stride; a.pad = cp.pad; a.cin_blocks = C / block_k;
+    a.num_kblocks = cp.size * cp.size * a.cin_blocks;
+    a.act = cp.act; a.scale = cp.scale; a.shift = cp.shift; a.out = out.p;
+    a.npix = (long long)in.n * out.h * out.w;
+    a.block_n = cp.cout_pad < 256 ? cp.cout_pad : 256;
+    a.n_tiles = (cp.cout_pad + a.block_n - 1) / a.block_n;
+    const size_t esz = 2;
+
+    // ---- A views ----
+    if (cp.size == 1 && cp.stride == 1 && cp.pad == 0) {
+        a.mode = 0;
+        a.a_rows = 128;
+        a.m_tiles = (int)((a.npix + 127) / 128);
+        cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)a.npix};
+        cuuint64_t strides[1] = {(cuuint64_t)in.ld * esz};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, 128};
+        encode(&p->maps.a[0], in.p, 2, dims, strides, box, block_k);
+    } else {
+        a.mode = 1;
+        // pick the rectangular pixel tile (TW x TH x TN <= 128 rows) that wastes the fewest MMA rows
+        double best = -1; int bw = 1, bh = 1, bn = 1;
+        for (int tw = 1; tw <= out.w && tw <= 128; ++tw)
+            for (int th = 1; th <= out.h && tw * th <= 128; ++th) {
+                int tn_max = 128 / (tw * th);
+                if (tn_max > in.n) tn_max = in.n;
+                for (int tn = 1; tn <= tn_max; ++tn) {
+                    double tiles = (double)div_up(out.w, tw) * div_up(out.h, th) * div_up(in.n, tn);
+                    double eff = (double)out.w * out.h * in.n / (tiles * 128.0);
+                    // prefer wide tiles on ties: longer contiguous runs per TMA box row
+                    double score = eff + 1e-6 * tw + 1e-9 * th;
+                    if (score > best) { best = score; bw = tw; bh = th; bn = tn; }
+                }
+            }
+        a.TW = bw; a.TH = bh; a.TN = bn;
+        a.tiles_x = div_up(out.w, bw); a.tiles_y = div_up(out.h, bh);
+        a.m_tiles = a.tiles_x * a.tiles_y * div_up(in.n, bn);
+        a.a_rows = bw * bh * bn;
+        cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+        if (cp.stride == 1) {
+            cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+            cuuint64_t strides[3] = {(cuuint64_t)in.ld * esz, (cuuint64_t)in.w * in.ld * esz, (cuuint64_t)in.h * in.w * in.ld * esz};
+            encode(&p->maps.a[0], in.p, 4, dims, strides, box, block_k);
+        } else {
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    int pw = (in.w - px + 1) / 2, ph = (in.h - py + 1) / 2;
+                    if (pw < 1) pw = 1;
+                    if (ph < 1) ph = 1;
+                    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)pw, (cuuint64_t)ph, (cuuint64_t)in.n};
+                    cuuint64_t strides[3] = {(cuuint64_t)2 * in.ld * esz, (cuuint64_t)2 * in.w * in.ld * esz, (cuuint64_t)in.h * in.w * in.ld * esz};
+                    void *base = (unsigned char *)in.p + ((size_t)py * in.w + px) * in.ld * esz;
+                    encode(&p->maps.a[py * 2 + px], base, 4, dims, strides, box, block_k);
+                }
+        }
+    }
+    // ---- B view ----
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cp.cout_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)K * esz};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)a.block_n};
+        encode(&p->maps.b, (void *)cp.w, 2, dims, strides, box, block_k);
+    }
+    // ---- smem / tmem budget ----
+    const int a_bytes = 128 * block_k * 2;
+    a.b_stage_bytes = (a.block_n * block_k * 2 + 1023) / 1024 * 1024;
+    const int aux_bytes = 256 + 2 * 512 * 4;
+    int stages = (227 * 1024 - 1024 - aux_bytes) / (a_bytes + a.b_stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages > a.num_kblocks && a.num_kblocks >= 2) stages = a.num_kblocks;
+    if (stages < 2) { delete p; return nullptr; }
+    a.stages = stages;
+    p->smem_bytes = (size_t)stages * (a_bytes + a.b_stage_bytes) + aux_bytes + 1024;
+    int cols = 2 * a.block_n;
+    a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+    int tiles = a.m_tiles * a.n_tiles;
+    p->grid = tiles < 148 ? tiles : 148;
+    p->flops = 2.0 * (double)a.npix * out.c * K;
+    char buf[256];
+    snprintf(buf, sizeof buf, "conv_tc mode%d k%d n%d tile %dx%dx%d rows %d m_tiles %d n_tiles %d stages %d smem %zu grid %d",
+             a.mode, block_k, a.block_n, a.TW, a.TH, a.TN, a.a_rows, a.m_tiles, a.n_tiles, stages, p->smem_bytes, p->grid);
+    p->desc = buf;
+    return p;
+}

@@ -1,0 +1,735 @@
+// engine.cu — the device engine behind the darknet C API: planning, memory, weight repacking, the forward
+// loop (forward_network, network.c:188-211, re-expressed as a stream of sm_100a kernels), layer inspection hooks,
+// and the device side of get_network_boxes / do_nms_sort.
+//
+// Data layout in HBM:
+//   * activations  NHWC, bf16 (default) or fp32 (B200_PREC_FP32); a TView carries (n,h,w,c,ld) so a producer can
+//                  write into a channel slice of a consumer's concat buffer;
+//   * head outputs darknet layout, fp32: per image [anchor][entry][h*w] (what drivers read through l.output);
+//   * parameters   one contiguous arena: per conv [Cout_pad][ky][kx][Cin] in the activation dtype + fp32
+//                  scale/shift (inference batch-norm folded to one multiply-add per output);
+//   * candidates   SoA per image: box[cap][4], objectness[cap], prob[cap][classes], id[cap], count.
+#include "kernels.h"
+#include "b200_engine.h"
+#include <vector>
+#include <string>
+#include <cmath>
+#include <cstring>
+
+struct DevLayer {
+    LAYER_TYPE type;
+    TView out;                 // NHWC output view (n = planned batch capacity)
+    bool owns_out;
+    float *head_out;           // YOLO / REGION / DETECTION / CONNECTED: fp32 [batch][outputs]
+    // parameters (inside the arena)
+    void *w;
+    float *scale, *shift, *lbias;
+    size_t w_off, scale_off, shift_off, lbias_off, w_bytes;
+    int cout_pad;
+    ConvTcPlan *tc;
+    bool stem;
+    std::string kernel;
+};
+
+struct b200_engine {
+    int precision, act_dtype;
+    int n, cap;                // layers, batch capacity
+    int device;
+    int conv_backend, head_sync;
+    cudaStream_t stream;
+    std::vector<DevLayer> L;
+    float *d_input;            // fp32 NCHW network input [cap][inputs]
+    TView in_view;             // NHWC copy of the input (only when layer 0 is not a stem conv)
+    unsigned char *arena;      // parameters
+    size_t arena_bytes;
+    float *xfer;               // fp32 scratch for fetch/set (max layer size)
+    size_t xfer_floats;
+    // decode / nms
+    std::vector<HeadDesc> heads;
+    HeadDesc *d_heads;
+    int boxes_per_image, classes;
+    CandBuffers cand;          // device
+    int cand_slots;
+    NmsScratch nms_scratch;
+    DetRecord *d_records; int records_cap; int *d_record_count;
+    // host staging for one image's candidates
+    float *h_box, *h_obj, *h_prob; int *h_id; int h_cap;
+};
+
+static void *dev_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    B200_CHECK(cudaMalloc(&p, bytes ? bytes : 16));
+    return p;
+}
+
+static void require_device(int device)
+{
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        fprintf(stderr, "b200-darknet: no CUDA device available (%s). This engine has no CPU fallback.\n",
+                err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+        abort();
+    }
+    B200_CHECK(cudaSetDevice(device < count ? device : 0));
+}
+
+static bool g_cuda_ready = false;
+static bool cuda_usable()
+{
+    int count = 0;
+    return cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
+}
+
+extern "C" void cuda_set_device(int n)
+{
+    gpu_index = n;
+    if (cuda_usable()) B200_CHECK(cudaSetDevice(n));
+}
+
+extern "C" unsigned long long b200_launch_count(void) { return g_b200_launches; }
+
+static TView view_of(const DevLayer &d, int batch)
+{
+    TView v = d.out;
+    v.n = batch;
+    return v;
+}
+
+static int act_id(ACTIVATION a)
+{
+    switch (a) {
+    case LEAKY: return ACT_LEAKY;
+    case LINEAR: return ACT_LINEAR;
+    case LOGISTIC: return ACT_LOGISTIC;
+    case RELU: return ACT_RELU;
+    default:
+        fprintf(stderr, "b200-darknet: activation %d is outside the YOLO inference path\n", (int)a);
+        abort();
+    }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ----------------------------------------------------------------------------------------------------
+// planning
+// ----------------------------------------------------------------------------------------------------
+static std::vector<std::vector<int>> consumers_of(const network *net)
+{
+    std::vector<std::vector<int>> c(net->n);
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        if (l.type == ROUTE) {
+            for (int j = 0; j < l.n; ++j) c[l.input_layers[j]].push_back(i);
+        } else {
+            if (i > 0) c[i - 1].push_back(i);
+            if (l.type == SHORTCUT) c[l.index].push_back(i);
+        }
+    }
+    return c;
+}
+
+static void build_engine_device_state(b200_engine *e, network *net)
+{
+    require_device(net->gpu_index);
+    B200_CHECK(cudaGetDevice(&e->device));
+    B200_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const int esize = (int)dt_size(e->act_dtype);
+    auto cons = consumers_of(net);
+
+    e->d_input = (float *)dev_alloc((size_t)e->cap * net->inputs * sizeof(float));
+    size_t max_floats = (size_t)e->cap * net->inputs;
+
+    // ---- output views ------------------------------------------------------------------------------
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        DevLayer &d = e->L[i];
+        d.type = l.type;
+        size_t floats = (size_t)e->cap * l.outputs;
+        if (floats > max_floats) max_floats = floats;
+        int dtype = e->act_dtype;
+        if (l.type == CONVOLUTIONAL && e->precision == B200_PREC_BF16 && i + 1 < net->n && cons[i].size() == 1 &&
+            (net->layers[i + 1].type == YOLO || net->layers[i + 1].type == REGION))
+            dtype = DT_F32;                        // head logits stay fp32: no quantisation before the decode
+        switch (l.type) {
+        case CONVOLUTIONAL: {
+            // row pitch padded to 16 filters (255 -> 256): keeps every pixel row 16-byte aligned for vector stores
+            int ld = (int)align_up(l.out_c, 16);
+            d.out = TView{dev_alloc((size_t)e->cap * l.out_h * l.out_w * ld * dt_size(dtype)), e->cap, l.out_h, l.out_w, l.out_c, ld, dtype};
+            d.owns_out = true;
+            break;
+        }
+        case MAXPOOL: case UPSAMPLE: case SHORTCUT: case REORG: case LOCAL:
+            d.out = TView{dev_alloc(floats * dt_size(dtype)), e->cap, l.out_h, l.out_w, l.out_c, l.out_c, dtype};
+            d.owns_out = true;
+            break;
+        case ROUTE:
+            if (l.out_c == 0) { fprintf(stderr, "b200-darknet: route %d joins layers of different spatial size\n", i); abort(); }
+            if (l.n == 1) { d.out = e->L[l.input_layers[0]].out; d.owns_out = false; }
+            else {
+                int dt0 = e->L[l.input_layers[0]].out.dtype;
+                d.out = TView{dev_alloc(floats * dt_size(dt0)), e->cap, l.out_h, l.out_w, l.out_c, l.out_c, dt0};
+                d.owns_out = true;
+            }
+            break;
+        case DROPOUT:
+            d.out = e->L[i - 1].out; d.owns_out = false;
+            d.head_out = e->L[i - 1].head_out;
+            break;
+        case CONNECTED: case YOLO: case REGION: case DETECTION:
+            d.head_out = (float *)dev_alloc(floats * sizeof(float));
+            d.out = TView{d.head_out, e->cap, 1, 1, l.outputs, l.outputs, DT_F32};
+            d.owns_out = false;
+            break;
+        default:
+            fprintf(stderr, "b200-darknet: layer %d has a type outside the inference path\n", i);
+            abort();
+        }
+    }
+    e->xfer_floats = max_floats;
+    e->xfer = (float *)dev_alloc(max_floats * sizeof(float));
+
+    // ---- first layer input -------------------------------------------------------------------------------
+    const layer &l0 = net->layers[0];
+    e->L[0].stem = (l0.type == CONVOLUTIONAL && l0.c <= 4);
+    if (!e->L[0].stem) {
+        if (!(net->h && net->w && net->c)) { fprintf(stderr, "b200-darknet: network input must be an image\n"); abort(); }
+        e->in_view = TView{dev_alloc((size_t)e->cap * net->inputs * esize), e->cap, net->h, net->w, net->c, net->c, e->act_dtype};
+    }
+
+    // ---- parameter arena -----------------------------------------------------------------------------------
+    size_t off = 0;
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        DevLayer &d = e->L[i];
+        if (l.type == CONVOLUTIONAL) {
+            d.cout_pad = (int)align_up(l.n, 16);
+            d.w_bytes = (size_t)d.cout_pad * l.size * l.size * l.c * esize;
+            d.w_off = off; off = align_up(off + d.w_bytes, 256);
+            d.scale_off = off; off = align_up(off + d.cout_pad * sizeof(float), 256);
+            d.shift_off = off; off = align_up(off + d.cout_pad * sizeof(float), 256);
+        } else if (l.type == LOCAL) {
+            d.w_bytes = (size_t)l.nweights * esize;
+            d.w_off = off; off = align_up(off + d.w_bytes, 256);
+            d.lbias_off = off; off = align_up(off + (size_t)l.outputs * sizeof(float), 256);
+        } else if (l.type == CONNECTED) {
+            d.w_bytes = (size_t)l.inputs * l.outputs * esize;
+            d.w_off = off; off = align_up(off + d.w_bytes, 256);
+            d.scale_off = off; off = align_up(off + (size_t)l.outputs * sizeof(float), 256);
+            d.shift_off = off; off = align_up(off + (size_t)l.outputs * sizeof(float), 256);
+        }
+    }
+    e->arena_bytes = off;
+    e->arena = (unsigned char *)dev_alloc(off);
+    B200_CHECK(cudaMemset(e->arena, 0, off ? off : 16));
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        DevLayer &d = e->L[i];
+        if (l.type == CONVOLUTIONAL || l.type == LOCAL || l.type == CONNECTED) d.w = e->arena + d.w_off;
+        if (l.type == CONVOLUTIONAL || l.type == CONNECTED) { d.scale = (float *)(e->arena + d.scale_off); d.shift = (float *)(e->arena + d.shift_off); }
+        if (l.type == LOCAL) d.lbias = (float *)(e->arena + d.lbias_off);
+    }
+
+    // ---- kernel selection ------------------------------------------------------------------------------------
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        DevLayer &d = e->L[i];
+        switch (l.type) {
+        case CONVOLUTIONAL: {
+            if (l.size == 1 && (l.stride != 1 || l.pad != 0)) {
+                // reference quirk (convolutional_layer.c:468-469): 1x1 convs skip im2col and ignore stride/pad
+                fprintf(stderr, "b200-darknet: 1x1 convolution with stride/pad is not supported (layer %d)\n", i);
+                abort();
+            }
+            d.kernel = d.stem ? "conv_stem" : "conv_simt";
+            if (!d.stem && e->precision == B200_PREC_BF16) {
+                ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
+                d.tc = conv_tc_plan_create(e->L[i - 1].out, d.out, p, nullptr);
+                if (d.tc) d.kernel = "conv_tc";
+            }
+            break;
+        }
+        case MAXPOOL: d.kernel = "maxpool"; break;
+        case UPSAMPLE: d.kernel = "upsample"; break;
+        case SHORTCUT: d.kernel = "shortcut"; break;
+        case REORG: d.kernel = "reorg"; break;
+        case ROUTE: d.kernel = l.n == 1 ? "alias" : "route_copy"; break;
+        case DROPOUT: d.kernel = "alias"; break;
+        case LOCAL: d.kernel = "local"; break;
+        case CONNECTED: d.kernel = "connected"; break;
+        case YOLO: d.kernel = "yolo_forward"; break;
+        case REGION: d.kernel = "region_forward"; break;
+        case DETECTION: d.kernel = "detection_forward"; break;
+        default: break;
+        }
+    }
+
+    // ---- heads for decode ---------------------------------------------------------------------------------------
+    int base = 0;
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        if (l.type != YOLO && l.type != REGION && l.type != DETECTION) continue;
+        HeadDesc h;
+        memset(&h, 0, sizeof h);
+        h.type = l.type; h.w = l.w; h.h = l.h; h.n = l.n; h.classes = l.classes; h.coords = l.coords;
+        h.outputs = l.outputs; h.side = l.side; h.sqrt_ = l.sqrt;
+        h.out = e->L[i].head_out;
+        if (l.n > 16) { fprintf(stderr, "b200-darknet: more than 16 anchors per head\n"); abort(); }
+        for (int a = 0; a < l.n && l.type != DETECTION; ++a) {
+            int src = l.type == YOLO ? l.mask[a] : a;
+            h.anchors[2 * a] = l.biases[2 * src];
+            h.anchors[2 * a + 1] = l.biases[2 * src + 1];
+        }
+        h.box_base = base;
+        base += l.w * l.h * l.n;
+        e->heads.push_back(h);
+        e->classes = l.classes;                  // network.c:528 takes classes from the LAST layer
+    }
+    e->boxes_per_image = base;
+    if (!e->heads.empty()) {
+        e->d_heads = (HeadDesc *)dev_alloc(e->heads.size() * sizeof(HeadDesc));
+        B200_CHECK(cudaMemcpy(e->d_heads, e->heads.data(), e->heads.size() * sizeof(HeadDesc), cudaMemcpyHostToDevice));
+    }
+    g_cuda_ready = true;
+}
+
+extern "C" b200_engine *b200_engine_create(network *net, int precision)
+{
+    b200_engine *e = new b200_engine();
+    e->precision = precision;
+    e->act_dtype = precision == B200_PREC_FP32 ? DT_F32 : DT_BF16;
+    e->n = net->n;
+    e->cap = net->batch;
+    e->conv_backend = 0;
+    e->head_sync = 1;
+    e->L.resize(net->n);
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.owns_out = false; }
+    e->stream = nullptr; e->d_input = nullptr; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
+    e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
+    memset(&e->cand, 0, sizeof e->cand); e->cand_slots = 0;
+    memset(&e->nms_scratch, 0, sizeof e->nms_scratch);
+    e->d_records = nullptr; e->records_cap = 0; e->d_record_count = nullptr;
+    e->h_box = e->h_obj = e->h_prob = nullptr; e->h_id = nullptr; e->h_cap = 0;
+    e->boxes_per_image = 0; e->classes = 0;
+    // Parsing a cfg (layer table, shapes) works on a machine without a GPU; anything that computes does not.
+    if (cuda_usable()) build_engine_device_state(e, net);
+    else e->device = -1;
+    return e;
+}
+
+static void need_device(const b200_engine *e, const char *what)
+{
+    if (e->device < 0) {
+        fprintf(stderr, "b200-darknet: %s needs a CUDA device; none was available when the network was parsed. "
+                        "There is no CPU fallback.\n", what);
+        abort();
+    }
+    B200_CHECK(cudaSetDevice(e->device));
+}
+
+extern "C" void b200_engine_destroy(b200_engine *e)
+{
+    if (!e) return;
+    if (e->device >= 0) {
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->stream);
+        for (auto &d : e->L) {
+            if (d.tc) conv_tc_plan_destroy(d.tc);
+            if (d.owns_out) cudaFree(d.out.p);
+            if (d.head_out && d.type != DROPOUT) cudaFree(d.head_out);
+        }
+        cudaFree(e->d_input); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
+        cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
+        cudaFree(e->nms_scratch.mask); cudaFree(e->d_records); cudaFree(e->d_record_count);
+        cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
+        cudaStreamDestroy(e->stream);
+    }
+    delete e;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// weights: fold the inference batch-norm, repack OIHW -> O(ky,kx,I), cast, upload
+// ----------------------------------------------------------------------------------------------------
+static void put_elem(unsigned char *dst, size_t idx, float v, int dtype)
+{
+    if (dtype == DT_F32) ((float *)dst)[idx] = v;
+    else ((bf16 *)dst)[idx] = __float2bfloat16_rn(v);
+}
+
+static void fold_bn(const layer &l, int count, float *scale, float *shift)
+{
+    for (int f = 0; f < count; ++f) {
+        if (l.batch_normalize) {
+            // (x - mean)/(sqrt(var) + .000001f) * gamma + beta      (blas.c:154, batchnorm_layer.c:150-154)
+            double s = (double)l.scales[f] / (sqrt((double)l.rolling_variance[f]) + (double).000001f);
+            scale[f] = (float)s;
+            shift[f] = (float)((double)l.biases[f] - (double)l.rolling_mean[f] * s);
+        } else {
+            scale[f] = 1.f;
+            shift[f] = l.biases[f];
+        }
+    }
+}
+
+extern "C" void b200_engine_upload_weights(b200_engine *e, network *net)
+{
+    need_device(e, "load_weights");
+    std::vector<unsigned char> host(e->arena_bytes, 0);
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        DevLayer &d = e->L[i];
+        if (l.type == CONVOLUTIONAL) {
+            const int K = l.size * l.size * l.c;
+            unsigned char *w = host.data() + d.w_off;
+            for (int o = 0; o < l.n; ++o)
+                for (int c = 0; c < l.c; ++c)
+                    for (int ky = 0; ky < l.size; ++ky)
+                        for (int kx = 0; kx < l.size; ++kx) {
+                            float v = l.weights[(((size_t)o * l.c + c) * l.size + ky) * l.size + kx];
+                            put_elem(w, (size_t)o * K + (size_t)(ky * l.size + kx) * l.c + c, v, e->act_dtype);
+                        }
+            fold_bn(l, l.n, (float *)(host.data() + d.scale_off), (float *)(host.data() + d.shift_off));
+        } else if (l.type == LOCAL) {
+            const int locations = l.out_h * l.out_w, K = l.size * l.size * l.c;
+            unsigned char *w = host.data() + d.w_off;
+            for (int loc = 0; loc < locations; ++loc)
+                for (int o = 0; o < l.n; ++o)
+                    for (int c = 0; c < l.c; ++c)
+                        for (int t = 0; t < l.size * l.size; ++t) {
+                            float v = l.weights[((size_t)loc * l.n + o) * K + (size_t)c * l.size * l.size + t];
+                            put_elem(w, ((size_t)loc * l.n + o) * K + (size_t)t * l.c + c, v, e->act_dtype);
+                        }
+            memcpy(host.data() + d.lbias_off, l.biases, (size_t)l.outputs * sizeof(float));
+        } else if (l.type == CONNECTED) {
+            // the producer's CHW flattening becomes HWC on the device: permute the weight columns accordingly
+            const layer &prev = net->layers[i - 1];
+            int pc = prev.out_c, ph = prev.out_h, pw = prev.out_w;
+            bool image_in = pc > 0 && ph * pw > 1 && pc * ph * pw == l.inputs;
+            unsigned char *w = host.data() + d.w_off;
+            for (int o = 0; o < l.outputs; ++o)
+                for (int k = 0; k < l.inputs; ++k) {
+                    size_t dst = k;
+                    if (image_in) { int c = k / (ph * pw), hw = k % (ph * pw); dst = (size_t)hw * pc + c; }
+                    put_elem(w, (size_t)o * l.inputs + dst, l.weights[(size_t)o * l.inputs + k], e->act_dtype);
+                }
+            fold_bn(l, l.outputs, (float *)(host.data() + d.scale_off), (float *)(host.data() + d.shift_off));
+        }
+    }
+    B200_CHECK(cudaMemcpyAsync(e->arena, host.data(), e->arena_bytes, cudaMemcpyHostToDevice, e->stream));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" void *b200_weights_arena(network *net, size_t *bytes)
+{
+    b200_engine *e = b200_engine_of(net);
+    if (bytes) *bytes = e->arena_bytes;
+    return e->arena;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// forward
+// ----------------------------------------------------------------------------------------------------
+static void run_layer(b200_engine *e, network *net, int i, int batch)
+{
+    const layer &l = net->layers[i];
+    DevLayer &d = e->L[i];
+    cudaStream_t s = e->stream;
+    TView in = i > 0 ? view_of(e->L[i - 1], batch) : (d.stem ? TView{nullptr, 0, 0, 0, 0, 0, 0} : [&] { TView v = e->in_view; v.n = batch; return v; }());
+    TView out = view_of(d, batch);
+    switch (l.type) {
+    case CONVOLUTIONAL: {
+        ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
+        if (d.stem) launch_conv_stem(e->d_input, batch, l.h, l.w, l.c, out, p, s);
+        else if (d.tc && e->conv_backend == 0) launch_conv_tc(d.tc, s);
+        else launch_conv_simt(in, out, p, s);
+        break;
+    }
+    case MAXPOOL: launch_maxpool(in, out, l.size, l.stride, l.pad, s); break;
+    case UPSAMPLE: launch_upsample(in, out, l.stride, l.scale, s); break;
+    case SHORTCUT: launch_shortcut(in, view_of(e->L[l.index], batch), out, l.alpha, l.beta, act_id(l.activation), s); break;
+    case REORG:
+        if (l.reverse) { fprintf(stderr, "b200-darknet: reorg reverse=1 is outside the YOLO inference path\n"); abort(); }
+        launch_reorg(in, out, l.stride, s);
+        break;
+    case ROUTE:
+        if (l.n > 1) {
+            int coff = 0;
+            for (int j = 0; j < l.n; ++j) {
+                TView src = view_of(e->L[l.input_layers[j]], batch);
+                TView dst = out;
+                dst.p = (unsigned char *)out.p + (size_t)coff * dt_size(out.dtype);
+                dst.c = src.c;
+                launch_copy_channels(src, dst, s);
+                coff += src.c;
+            }
+        }
+        break;
+    case DROPOUT: break;
+    case LOCAL: launch_local(in, out, d.w, d.lbias, l.size, l.stride, l.pad, act_id(l.activation), s); break;
+    case CONNECTED: {
+        const DevLayer &pd = e->L[i - 1];
+        if (pd.out.ld != pd.out.c) { fprintf(stderr, "b200-darknet: connected input must be dense\n"); abort(); }
+        launch_connected(pd.out.p, pd.out.dtype, batch, l.inputs, l.outputs, d.w, e->act_dtype, d.scale, d.shift,
+                         act_id(l.activation), d.head_out, s);
+        break;
+    }
+    case YOLO: launch_yolo_forward(in, d.head_out, l.n, l.classes, s); break;
+    case REGION: launch_region_forward(in, d.head_out, l.n, l.classes, l.coords, l.softmax, s); break;
+    case DETECTION: launch_detection_forward(e->L[i - 1].head_out, d.head_out, batch, l.outputs, l.side, l.classes, l.softmax, s); break;
+    default: break;
+    }
+}
+
+static int logical_batch(const b200_engine *e, const network *net)
+{
+    if (net->batch > e->cap) {
+        fprintf(stderr, "b200-darknet: batch %d exceeds the cfg batch %d the buffers were planned for\n", net->batch, e->cap);
+        abort();
+    }
+    return net->batch;
+}
+
+static void forward_layers(b200_engine *e, network *net, int start, int end)
+{
+    int batch = logical_batch(e, net);
+    if (start == 0 && !e->L[0].stem) {
+        TView v = e->in_view; v.n = batch;
+        launch_nchw_f32_to_view(e->d_input, v, e->stream);
+    }
+    for (int i = start; i < end; ++i) run_layer(e, net, i, batch);
+}
+
+static void sync_heads_to_host(b200_engine *e, network *net)
+{
+    int batch = logical_batch(e, net);
+    int last = net->n - 1;
+    while (last > 0 && net->layers[last].type == COST) --last;
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        bool head = l.type == YOLO || l.type == REGION || l.type == DETECTION;
+        if (!head && i != last) continue;
+        if (e->L[i].head_out) {
+            B200_CHECK(cudaMemcpyAsync(l.output, e->L[i].head_out, (size_t)batch * l.outputs * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        } else {
+            launch_view_to_nchw_f32(view_of(e->L[i], batch), e->xfer, e->stream);
+            B200_CHECK(cudaMemcpyAsync(l.output, e->xfer, (size_t)batch * l.outputs * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        }
+    }
+}
+
+extern "C" void b200_engine_forward(b200_engine *e, network *net, const float *input)
+{
+    need_device(e, "network_predict");
+    int batch = logical_batch(e, net);
+    B200_CHECK(cudaMemcpyAsync(e->d_input, input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    forward_layers(e, net, 0, net->n);
+    if (e->head_sync) sync_heads_to_host(e, net);
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" void b200_engine_forward_resident(b200_engine *e, network *net)
+{
+    need_device(e, "network_predict");
+    forward_layers(e, net, 0, net->n);
+}
+
+extern "C" float *b200_engine_input_device(b200_engine *e) { return e->d_input; }
+extern "C" void b200_engine_sync(b200_engine *e) { need_device(e, "sync"); B200_CHECK(cudaStreamSynchronize(e->stream)); }
+
+extern "C" int b200_get_precision(const network *net) { return b200_engine_of(net)->precision; }
+extern "C" void b200_set_conv_backend(network *net, int backend) { b200_engine_of(net)->conv_backend = backend; }
+extern "C" void b200_set_head_sync(network *net, int on) { b200_engine_of(net)->head_sync = on; }
+
+// ----------------------------------------------------------------------------------------------------
+// inspection hooks
+// ----------------------------------------------------------------------------------------------------
+extern "C" void b200_fetch_layer_output(network *net, int i, float *out)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_fetch_layer_output");
+    int batch = logical_batch(e, net);
+    size_t bytes = (size_t)batch * net->layers[i].outputs * sizeof(float);
+    if (e->L[i].head_out) {
+        B200_CHECK(cudaMemcpyAsync(out, e->L[i].head_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        launch_view_to_nchw_f32(view_of(e->L[i], batch), e->xfer, e->stream);
+        B200_CHECK(cudaMemcpyAsync(out, e->xfer, bytes, cudaMemcpyDeviceToHost, e->stream));
+    }
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" void b200_set_layer_output(network *net, int i, const float *in)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_set_layer_output");
+    int batch = logical_batch(e, net);
+    size_t bytes = (size_t)batch * net->layers[i].outputs * sizeof(float);
+    if (e->L[i].head_out) {
+        B200_CHECK(cudaMemcpyAsync(e->L[i].head_out, in, bytes, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        B200_CHECK(cudaMemcpyAsync(e->xfer, in, bytes, cudaMemcpyHostToDevice, e->stream));
+        launch_nchw_f32_to_view(e->xfer, view_of(e->L[i], batch), e->stream);
+    }
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" void b200_run_layers(network *net, int start, int end)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_run_layers");
+    if (start < 0) start = 0;
+    if (end > net->n) end = net->n;
+    if (start == 0) {   // the caller placed the image in net->input (host) — stage it like network_predict does
+        int batch = logical_batch(e, net);
+        B200_CHECK(cudaMemcpyAsync(e->d_input, net->input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    forward_layers(e, net, start, end);
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" const char *b200_layer_kernel(network *net, int i)
+{
+    b200_engine *e = b200_engine_of(net);
+    if (e->L[i].tc && e->conv_backend != 0) return "conv_simt";
+    return e->L[i].kernel.c_str();
+}
+
+// ----------------------------------------------------------------------------------------------------
+// boxes + NMS
+// ----------------------------------------------------------------------------------------------------
+static void ensure_candidates(b200_engine *e, int slots)
+{
+    if (e->cand_slots >= slots) return;
+    cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
+    int cap = e->boxes_per_image, cls = e->classes;
+    e->cand.cap = cap; e->cand.classes = cls;
+    e->cand.box = (float *)dev_alloc((size_t)slots * cap * 4 * sizeof(float));
+    e->cand.obj = (float *)dev_alloc((size_t)slots * cap * sizeof(float));
+    e->cand.prob = (float *)dev_alloc((size_t)slots * cap * cls * sizeof(float));
+    e->cand.id = (int *)dev_alloc((size_t)slots * cap * sizeof(int));
+    e->cand.count = (int *)dev_alloc((size_t)slots * sizeof(int));
+    e->cand_slots = slots;
+    if (e->h_cap < cap) {
+        cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
+        B200_CHECK(cudaMallocHost((void **)&e->h_box, (size_t)cap * 4 * sizeof(float)));
+        B200_CHECK(cudaMallocHost((void **)&e->h_obj, (size_t)cap * sizeof(float)));
+        B200_CHECK(cudaMallocHost((void **)&e->h_prob, (size_t)cap * cls * sizeof(float)));
+        B200_CHECK(cudaMallocHost((void **)&e->h_id, (size_t)cap * sizeof(int)));
+        e->h_cap = cap;
+    }
+}
+
+// internal C ABI used by host/boxes.c ------------------------------------------------------------------------
+extern "C" int b200_engine_count_boxes(b200_engine *e, network *net, int image, float thresh)
+{
+    need_device(e, "num_detections");
+    if (e->heads.empty()) return 0;
+    ensure_candidates(e, 1);
+    launch_count_yolo(e->d_heads, (int)e->heads.size(), image, thresh, e->cand.count, e->stream);
+    int n = 0;
+    B200_CHECK(cudaMemcpyAsync(&n, e->cand.count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    return n;
+}
+
+extern "C" int b200_engine_decode_image(b200_engine *e, network *net, int image, int w, int h, float thresh, int relative,
+                                        const float **box, const float **obj, const float **prob, const int **id)
+{
+    need_device(e, "get_network_boxes");
+    if (e->heads.empty()) return 0;
+    ensure_candidates(e, 1);
+    launch_decode(e->d_heads, (int)e->heads.size(), image, 1, net->w, net->h, w, h, thresh, relative, 0, e->cand, e->stream);
+    int n = 0;
+    B200_CHECK(cudaMemcpyAsync(&n, e->cand.count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    if (n > 0) {
+        B200_CHECK(cudaMemcpyAsync(e->h_box, e->cand.box, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        B200_CHECK(cudaMemcpyAsync(e->h_obj, e->cand.obj, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        B200_CHECK(cudaMemcpyAsync(e->h_prob, e->cand.prob, (size_t)n * e->classes * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        B200_CHECK(cudaMemcpyAsync(e->h_id, e->cand.id, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        B200_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    *box = e->h_box; *obj = e->h_obj; *prob = e->h_prob; *id = e->h_id;
+    return n;
+}
+
+extern "C" int b200_engine_classes(b200_engine *e) { return e->classes; }
+
+extern "C" int b200_detect_batch(network *net, const float *input, int w, int h, float thresh, float nms_thresh,
+                                 int relative, b200_det *out, int max_out, int *counts)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_detect_batch");
+    int batch = logical_batch(e, net);
+    if (input) B200_CHECK(cudaMemcpyAsync(e->d_input, input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    forward_layers(e, net, 0, net->n);
+    if (e->heads.empty()) { B200_CHECK(cudaStreamSynchronize(e->stream)); return 0; }
+    ensure_candidates(e, e->cap);
+    if (e->records_cap < max_out) {
+        cudaFree(e->d_records);
+        e->d_records = (DetRecord *)dev_alloc((size_t)max_out * sizeof(DetRecord));
+        e->records_cap = max_out;
+    }
+    if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
+    launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, e->cand, e->stream);
+    launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
+                    e->boxes_per_image, &e->nms_scratch, e->stream);
+    B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));
+    launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
+                   e->d_records, max_out, e->d_record_count, e->stream);
+    int n = 0;
+    B200_CHECK(cudaMemcpyAsync(&n, e->d_record_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (counts) B200_CHECK(cudaMemcpyAsync(counts, e->cand.count, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    if (n > max_out) n = max_out;
+    static_assert(sizeof(DetRecord) == sizeof(b200_det), "record layouts must match");
+    if (n > 0) {
+        B200_CHECK(cudaMemcpyAsync(out, e->d_records, (size_t)n * sizeof(DetRecord), cudaMemcpyDeviceToHost, e->stream));
+        B200_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    return n;
+}
+
+// device NMS on caller-provided host arrays (the kernel behind do_nms_sort / do_nms_obj)
+static cudaStream_t g_nms_stream = nullptr;
+static NmsScratch g_nms_scratch = {nullptr, 0, 0};
+
+static void nms_prepare()
+{
+    if (!cuda_usable()) {
+        fprintf(stderr, "b200-darknet: do_nms_sort/do_nms_obj need a CUDA device. There is no CPU fallback.\n");
+        abort();
+    }
+    if (!g_nms_stream) B200_CHECK(cudaStreamCreateWithFlags(&g_nms_stream, cudaStreamNonBlocking));
+}
+
+extern "C" void b200_nms_sort_arrays(const float *boxes, float *probs, int n, int classes, float thresh)
+{
+    if (n <= 0 || classes <= 0) return;
+    nms_prepare();
+    float *d_box = (float *)dev_alloc((size_t)n * 4 * sizeof(float));
+    float *d_prob = (float *)dev_alloc((size_t)n * classes * sizeof(float));
+    B200_CHECK(cudaMemcpyAsync(d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
+    B200_CHECK(cudaMemcpyAsync(d_prob, probs, (size_t)n * classes * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
+    launch_nms_sort(d_box, d_prob, nullptr, nullptr, 1, n, classes, thresh, n, &g_nms_scratch, g_nms_stream);
+    B200_CHECK(cudaMemcpyAsync(probs, d_prob, (size_t)n * classes * sizeof(float), cudaMemcpyDeviceToHost, g_nms_stream));
+    B200_CHECK(cudaStreamSynchronize(g_nms_stream));
+    cudaFree(d_box); cudaFree(d_prob);
+}
+
+extern "C" void b200_nms_obj_arrays(const float *boxes, float *objectness, int n, float thresh, unsigned char *suppressed)
+{
+    if (n <= 0) return;
+    nms_prepare();
+    float *d_box = (float *)dev_alloc((size_t)n * 4 * sizeof(float));
+    float *d_obj = (float *)dev_alloc((size_t)n * sizeof(float));
+    std::vector<float> before(objectness, objectness + n);
+    B200_CHECK(cudaMemcpyAsync(d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
+    B200_CHECK(cudaMemcpyAsync(d_obj, objectness, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
+    launch_nms_obj(d_box, d_obj, nullptr, nullptr, 1, n, 1, thresh, n, &g_nms_scratch, g_nms_stream);
+    B200_CHECK(cudaMemcpyAsync(objectness, d_obj, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g_nms_stream));
+    B200_CHECK(cudaStreamSynchronize(g_nms_stream));
+    if (suppressed) for (int i = 0; i < n; ++i) suppressed[i] = (before[i] != 0.f && objectness[i] == 0.f) ? 1 : 0;
+    cudaFree(d_box); cudaFree(d_obj);
+}

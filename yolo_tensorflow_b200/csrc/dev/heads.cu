@@ -1,0 +1,135 @@
+// heads.cu — forward_yolo_layer / forward_region_layer / forward_detection_layer (inference part) on device.
+//
+// Input: the linear head convolution's NHWC logits.  Output: the layer's `l.output` in DARKNET layout
+// (fp32, per image [anchor][entry][h*w], entry_index() of yolo_layer.c:125-130 / region_layer.c:151-156),
+// with the reference's activations applied: LOGISTIC in double precision on x,y and obj(+classes)
+// (yolo_layer.c:137-146, region_layer.c:163-172, activations.h:32), raw w,h, and the strided class softmax
+// of the region layer (region_layer.c:182-185 -> blas.c:305-332).  The NHWC->NCHW transpose is fused into
+// the same pass, so logits are read once and activations written once: 2 x outputs x 4 bytes of HBM traffic.
+#include "kernels.h"
+#include <cfloat>
+
+static const int kThreads = 256;
+
+__device__ __forceinline__ float logistic_ref(float x) { return (float)(1. / (1. + exp(-(double)x))); }
+
+// 32x32 shared-memory transpose tiles: per (image, anchor) the [HW][entries] NHWC slab becomes the
+// [entries][HW] darknet slab, so both the logits read (entry fastest) and the activation write (cell fastest)
+// are coalesced; the logistic is applied on the way through.
+template <typename T>
+__global__ void yolo_forward_kernel(const T *__restrict__ in, float *__restrict__ out, int HW, int ld, int anchors, int entries)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z / anchors, a = blockIdx.z % anchors;
+    const int p0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
+    const T *src = in + (size_t)n * HW * ld + a * entries;
+    float *dst = out + ((size_t)n * anchors + a) * entries * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, e = e0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < HW && e < entries) ? Elem<T>::load(src + (size_t)p * ld + e) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int e = e0 + i, p = p0 + threadIdx.x;
+        if (e < entries && p < HW) {
+            float v = tile[threadIdx.x][i];
+            if (e != 2 && e != 3) v = logistic_ref(v);
+            dst[(size_t)e * HW + p] = v;
+        }
+    }
+}
+
+void launch_yolo_forward(TView in, float *out, int anchors, int classes, cudaStream_t s)
+{
+    int HW = in.h * in.w, entries = classes + 5;
+    dim3 grid(div_up(HW, 32), div_up(entries, 32), in.n * anchors), block(32, 8);
+    if (in.dtype == DT_F32) yolo_forward_kernel<float><<<grid, block, 0, s>>>((const float *)in.p, out, HW, in.ld, anchors, entries);
+    else yolo_forward_kernel<bf16><<<grid, block, 0, s>>>((const bf16 *)in.p, out, HW, in.ld, anchors, entries);
+    B200_LAUNCHED();
+}
+
+// region: thread per (image, anchor, cell); walks the entries of its box so the softmax needs no communication
+template <typename T>
+__global__ void region_forward_kernel(const T *__restrict__ in, float *__restrict__ out, int N, int HW, int ld,
+                                      int anchors, int classes, int coords, int softmax)
+{
+    const int entries = coords + 1 + classes;
+    const long long total = (long long)N * anchors * HW;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int loc = (int)(t % HW);
+        int a = (int)((t / HW) % anchors);
+        int n = (int)(t / ((long long)HW * anchors));
+        const T *src = in + ((size_t)n * HW + loc) * ld + a * entries;
+        float *dst = out + ((size_t)n * anchors + a) * entries * HW + loc;
+        dst[0 * HW] = logistic_ref(Elem<T>::load(src + 0));
+        dst[1 * HW] = logistic_ref(Elem<T>::load(src + 1));
+        for (int e = 2; e < coords; ++e) dst[(size_t)e * HW] = Elem<T>::load(src + e);
+        dst[(size_t)coords * HW] = logistic_ref(Elem<T>::load(src + coords));
+        if (!softmax) {
+            for (int j = 0; j < classes; ++j) dst[(size_t)(coords + 1 + j) * HW] = logistic_ref(Elem<T>::load(src + coords + 1 + j));
+        } else {
+            // blas.c:305-321 softmax(input, n, temp=1, stride, output)
+            float largest = -FLT_MAX;
+            for (int j = 0; j < classes; ++j) { float v = Elem<T>::load(src + coords + 1 + j); if (v > largest) largest = v; }
+            float sum = 0;
+            for (int j = 0; j < classes; ++j) {
+                float v = Elem<T>::load(src + coords + 1 + j);
+                float e = (float)exp((double)(v / 1.f - largest / 1.f));
+                sum += e;
+                dst[(size_t)(coords + 1 + j) * HW] = e;
+            }
+            for (int j = 0; j < classes; ++j) dst[(size_t)(coords + 1 + j) * HW] /= sum;
+        }
+    }
+}
+
+void launch_region_forward(TView in, float *out, int anchors, int classes, int coords, int softmax, cudaStream_t s)
+{
+    int HW = in.h * in.w;
+    long long total = (long long)in.n * anchors * HW;
+    int grid = (int)((total + kThreads - 1) / kThreads);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (in.dtype == DT_F32) region_forward_kernel<float><<<grid, kThreads, 0, s>>>((const float *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, softmax);
+    else region_forward_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16 *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, softmax);
+    B200_LAUNCHED();
+}
+
+// detection (YOLOv1): plain copy of the connected layer's fp32 output, optional per-cell class softmax
+__global__ void detection_forward_kernel(const float *__restrict__ in, float *__restrict__ out, int batch, int outputs,
+                                         int side, int classes, int softmax)
+{
+    const long long total = (long long)batch * outputs;
+    if (!softmax) {      // pass 0: copy
+        for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) out[t] = in[t];
+        return;
+    }
+    // pass 1 (separate launch): per-cell class softmax, one thread per (image, cell)
+    const long long cells = (long long)batch * side * side;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < cells; t += (long long)gridDim.x * blockDim.x) {
+        int b = (int)(t / (side * side)), i = (int)(t % (side * side));
+        const float *src = in + (size_t)b * outputs + i * classes;
+        float *dst = out + (size_t)b * outputs + i * classes;
+        float largest = -FLT_MAX;
+        for (int j = 0; j < classes; ++j) if (src[j] > largest) largest = src[j];
+        float sum = 0;
+        for (int j = 0; j < classes; ++j) { float e = (float)exp((double)(src[j] - largest)); sum += e; dst[j] = e; }
+        for (int j = 0; j < classes; ++j) dst[j] /= sum;
+    }
+}
+
+void launch_detection_forward(const float *in, float *out, int batch, int outputs, int side, int classes, int softmax, cudaStream_t s)
+{
+    long long total = (long long)batch * outputs;
+    int grid = (int)((total + kThreads - 1) / kThreads);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (softmax) {
+        // two dependent passes over the same buffer: run the softmax pass as its own launch to stay race-free
+        detection_forward_kernel<<<grid, kThreads, 0, s>>>(in, out, batch, outputs, side, classes, 0);
+        B200_LAUNCHED();
+        detection_forward_kernel<<<grid, kThreads, 0, s>>>(in, out, batch, outputs, side, classes, 1);
+        B200_LAUNCHED();
+    } else {
+        detection_forward_kernel<<<grid, kThreads, 0, s>>>(in, out, batch, outputs, side, classes, 0);
+        B200_LAUNCHED();
+    }
+}

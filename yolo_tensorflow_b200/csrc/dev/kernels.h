@@ -1,0 +1,88 @@
+// kernels.h — launchers of the hand-written sm_100a kernels (internal C++ interface of dev/*.cu).
+#pragma once
+#include "common.cuh"
+
+#define DT_BF16 0
+#define DT_F32 1
+
+// NHWC activation view: element (n,y,x,ch) lives at p[((n*h + y)*w + x)*ld + ch]; ld >= c lets a layer
+// write straight into a channel slice of a concat buffer (route fusion).
+struct TView {
+    void *p;
+    int n, h, w, c;
+    int ld;
+    int dtype;
+};
+static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---- layout transforms (engine.cu I/O, tests) ----------------------------------------------------
+void launch_nchw_f32_to_view(const float *src, TView dst, cudaStream_t s);   // host layout -> device layout
+void launch_view_to_nchw_f32(TView src, float *dst, cudaStream_t s);         // device layout -> host layout
+
+// ---- bandwidth-bound layers (layers.cu) ------------------------------------------------------------
+void launch_maxpool(TView in, TView out, int size, int stride, int pad, cudaStream_t s);
+void launch_upsample(TView in, TView out, int stride, float scale, cudaStream_t s);
+void launch_shortcut(TView in, TView add, TView out, float alpha, float beta, int act, cudaStream_t s);
+void launch_copy_channels(TView in, TView out, cudaStream_t s);               // out view already offset to its slice
+void launch_reorg(TView in, TView out, int stride, cudaStream_t s);
+
+// ---- convolution family ------------------------------------------------------------------------------
+struct ConvParams {
+    int size, stride, pad, act;
+    const void *w;          // repacked weights [Cout_pad][size*size*Cin] (K order ky,kx,c), same dtype as activations
+    const float *scale;     // per-output-channel multiplier (folded batch-norm), fp32
+    const float *shift;     // per-output-channel addend (folded batch-norm / bias), fp32
+    int cout_pad;           // rows in w (multiple of 16 for the tcgen05 path)
+};
+// first-layer kernel: reads the fp32 NCHW network input directly (fuses the layout/precision conversion)
+void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);
+// CUDA-core implicit-GEMM (fp32 accumulate); the fp32-exact path and the fallback for odd shapes
+void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
+// tcgen05/TMEM/TMA implicit-GEMM (bf16 in, fp32 accumulate).  Plans live in conv_tc.cu.
+struct ConvTcPlan;
+ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams p, const TView *residual);   // nullptr if shape unsupported
+void conv_tc_plan_destroy(ConvTcPlan *plan);
+void launch_conv_tc(ConvTcPlan *plan, cudaStream_t s);
+const char *conv_tc_plan_desc(ConvTcPlan *plan);
+
+// YOLOv1 dense layers (dense.cu)
+void launch_local(TView in, TView out, const void *w, const float *bias, int size, int stride, int pad, int act, cudaStream_t s);
+void launch_connected(const void *in, int in_dtype, int batch, int inputs, int outputs, const void *w, int w_dtype,
+                      const float *scale, const float *shift, int act, float *out, cudaStream_t s);
+
+// ---- heads (heads.cu): NHWC logits -> darknet-layout fp32 l.output with the layer's activations ------
+void launch_yolo_forward(TView in, float *out, int anchors, int classes, cudaStream_t s);
+void launch_region_forward(TView in, float *out, int anchors, int classes, int coords, int softmax, cudaStream_t s);
+void launch_detection_forward(const float *in, float *out, int batch, int outputs, int side, int classes, int softmax, cudaStream_t s);
+
+// ---- decode + NMS (decode.cu, nms.cu) --------------------------------------------------------------
+struct HeadDesc {            // one per YOLO/REGION/DETECTION layer, device-resident copy lives in the engine
+    int type;                // LAYER_TYPE value
+    int w, h, n, classes, coords, outputs, side, sqrt_;
+    const float *out;        // darknet-layout fp32 activations [batch][outputs]
+    float anchors[2 * 16];   // (w,h) pairs already selected through mask[]
+    int box_base;            // first global box id of this head inside an image
+};
+struct CandBuffers {
+    float *box;        // [batch][cap][4]
+    float *obj;        // [batch][cap]
+    float *prob;       // [batch][cap][classes]
+    int   *id;         // [batch][cap] global box id
+    int   *count;      // [batch]
+    int cap, classes;
+};
+// mode 0 = reference get_network_boxes semantics (yolo: obj>thresh only; region/detection: every box)
+// mode 1 = compact: additionally drops boxes whose objectness is 0 (what do_nms_sort's partition discards)
+void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
+                   int imw, int imh, float thresh, int relative, int mode, CandBuffers cb, cudaStream_t s);
+void launch_count_yolo(const HeadDesc *heads_dev, int nheads, int image, float thresh, int *count_dev, cudaStream_t s);
+
+struct NmsScratch { unsigned *mask; size_t words_per_cta; int ctas; };
+void launch_nms_sort(const float *box, float *prob, const float *obj, const int *count, int images, int cap,
+                     int classes, float thresh, int max_count, NmsScratch *scratch, cudaStream_t s);
+void launch_nms_obj(const float *box, float *obj, float *prob, const int *count, int images, int cap, int classes,
+                    float thresh, int max_count, NmsScratch *scratch, cudaStream_t s);
+// gathers surviving (box,class) pairs into compact records; returns via counter
+struct DetRecord { int image, cls, box_id; float prob, objectness, x, y, w, h; };
+void launch_collect(const float *box, const float *prob, const float *obj, const int *id, const int *count, int images,
+                    int cap, int classes, DetRecord *out, int max_out, int *out_count, cudaStream_t s);

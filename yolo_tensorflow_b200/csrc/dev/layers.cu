@@ -1,0 +1,333 @@
+// layers.cu — the HBM-bandwidth-bound layers of the YOLO inference path as coalesced, 128-bit vectorised
+// NHWC kernels: maxpool, upsample, shortcut, route (channel-slice copy), reorg, and the NCHW<->NHWC
+// boundary transforms.  Reference semantics: maxpool_layer.c:79-114, blas.c:334-349 (upsample_cpu),
+// blas.c:68-92 + shortcut_layer.c:62-67, route_layer.c:74-87, blas.c:9-30 + reorg_layer.c:107-109.
+//
+// Grid sizing: every kernel is a grid-stride loop launched with a multiple of the SM count (148) so a
+// launch is an integral number of waves whatever the tensor size.
+#include "kernels.h"
+#include <cfloat>
+
+unsigned long long g_b200_launches = 0;
+
+static const int kThreads = 256;
+static inline int grid_for(long long work_items)
+{
+    long long blocks = (work_items + kThreads - 1) / kThreads;
+    const long long wave = 148 * 8;              // 8 resident CTAs of 256 threads per SM
+    if (blocks > wave) blocks = wave * ((blocks + wave - 1) / wave > 4 ? 4 : (blocks + wave - 1) / wave);
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NCHW fp32 (darknet host layout) <-> NHWC T (device layout).  Tiled through shared memory so that both
+// the global read and the global write are coalesced.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, T *__restrict__ dst, int C, int HW, int ld)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float *s = src + (size_t)n * C * HW;
+    T *d = dst + (size_t)n * HW * ld;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) Elem<T>::store(d + (size_t)p * ld + c, tile[threadIdx.x][i]);
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict__ dst, int C, int HW, int ld)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const T *s = src + (size_t)n * HW * ld;
+    float *d = dst + (size_t)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < HW && c < C) ? Elem<T>::load(s + (size_t)p * ld + c) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) d[(size_t)c * HW + p] = tile[threadIdx.x][i];
+    }
+}
+
+void launch_nchw_f32_to_view(const float *src, TView dst, cudaStream_t s)
+{
+    int HW = dst.h * dst.w;
+    dim3 grid(div_up(HW, 32), div_up(dst.c, 32), dst.n), block(32, 8);
+    if (dst.dtype == DT_F32) nchw_to_nhwc_kernel<float><<<grid, block, 0, s>>>(src, (float *)dst.p, dst.c, HW, dst.ld);
+    else nchw_to_nhwc_kernel<bf16><<<grid, block, 0, s>>>(src, (bf16 *)dst.p, dst.c, HW, dst.ld);
+    B200_LAUNCHED();
+}
+
+void launch_view_to_nchw_f32(TView src, float *dst, cudaStream_t s)
+{
+    int HW = src.h * src.w;
+    dim3 grid(div_up(HW, 32), div_up(src.c, 32), src.n), block(32, 8);
+    if (src.dtype == DT_F32) nhwc_to_nchw_kernel<float><<<grid, block, 0, s>>>((const float *)src.p, dst, src.c, HW, src.ld);
+    else nhwc_to_nchw_kernel<bf16><<<grid, block, 0, s>>>((const bf16 *)src.p, dst, src.c, HW, src.ld);
+    B200_LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// maxpool: one thread per (output pixel, 16-byte channel vector).  Window starts at -pad, out-of-bounds
+// taps are skipped (they are -FLT_MAX in the reference and can never win: every window holds >= 1 valid tap).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void maxpool_kernel(const T *__restrict__ in, T *__restrict__ out, int N, int H, int W, int C, int ldi,
+                               int OH, int OW, int ldo, int size, int stride, int pad)
+{
+    const int cv = C / VEC;
+    const long long total = (long long)N * OH * OW * cv;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(t % cv);
+        long long pix = t / cv;
+        int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+        float best[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) best[i] = -FLT_MAX;
+        for (int ky = 0; ky < size; ++ky) {
+            int y = oy * stride + ky - pad;
+            if (y < 0 || y >= H) continue;
+            for (int kx = 0; kx < size; ++kx) {
+                int x = ox * stride + kx - pad;
+                if (x < 0 || x >= W) continue;
+                float val[VEC];
+                const T *src = in + (((size_t)n * H + y) * W + x) * ldi + v * VEC;
+                if (VEC == 1) val[0] = Elem<T>::load(src);
+                else load_vec<T>(src, val);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) best[i] = val[i] > best[i] ? val[i] : best[i];
+            }
+        }
+        T *dst = out + (size_t)pix * ldo + v * VEC;
+        if (VEC == 1) Elem<T>::store(dst, best[0]);
+        else store_vec<T>(dst, best);
+    }
+}
+
+template <typename T>
+static void maxpool_dispatch(TView in, TView out, int size, int stride, int pad, cudaStream_t s)
+{
+    constexpr int V = Elem<T>::VEC;
+    bool vec_ok = (in.c % V == 0) && (in.ld % V == 0) && (out.ld % V == 0) &&
+                  ((uintptr_t)in.p % 16 == 0) && ((uintptr_t)out.p % 16 == 0);
+    long long pixels = (long long)out.n * out.h * out.w;
+    if (vec_ok) {
+        maxpool_kernel<T, V><<<grid_for(pixels * (in.c / V)), kThreads, 0, s>>>(
+            (const T *)in.p, (T *)out.p, in.n, in.h, in.w, in.c, in.ld, out.h, out.w, out.ld, size, stride, pad);
+    } else {
+        maxpool_kernel<T, 1><<<grid_for(pixels * in.c), kThreads, 0, s>>>(
+            (const T *)in.p, (T *)out.p, in.n, in.h, in.w, in.c, in.ld, out.h, out.w, out.ld, size, stride, pad);
+    }
+    B200_LAUNCHED();
+}
+
+void launch_maxpool(TView in, TView out, int size, int stride, int pad, cudaStream_t s)
+{
+    if (in.dtype == DT_F32) maxpool_dispatch<float>(in, out, size, stride, pad, s);
+    else maxpool_dispatch<bf16>(in, out, size, stride, pad, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// upsample (nearest, x stride, times scale): one thread per (output pixel, channel vector)
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void upsample_kernel(const T *__restrict__ in, T *__restrict__ out, int N, int H, int W, int C, int ldi,
+                                int ldo, int stride, float scale)
+{
+    const int cv = C / VEC, OW = W * stride, OH = H * stride;
+    const long long total = (long long)N * OH * OW * cv;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(t % cv);
+        long long pix = t / cv;
+        int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+        const T *src = in + (((size_t)n * H + oy / stride) * W + ox / stride) * ldi + v * VEC;
+        T *dst = out + (size_t)pix * ldo + v * VEC;
+        float val[VEC];
+        if (VEC == 1) val[0] = Elem<T>::load(src); else load_vec<T>(src, val);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) val[i] = scale * val[i];
+        if (VEC == 1) Elem<T>::store(dst, val[0]); else store_vec<T>(dst, val);
+    }
+}
+
+template <typename T>
+static void upsample_dispatch(TView in, TView out, int stride, float scale, cudaStream_t s)
+{
+    constexpr int V = Elem<T>::VEC;
+    bool vec_ok = (in.c % V == 0) && (in.ld % V == 0) && (out.ld % V == 0) &&
+                  ((uintptr_t)in.p % 16 == 0) && ((uintptr_t)out.p % 16 == 0);
+    long long pixels = (long long)out.n * out.h * out.w;
+    if (vec_ok)
+        upsample_kernel<T, V><<<grid_for(pixels * (in.c / V)), kThreads, 0, s>>>((const T *)in.p, (T *)out.p, in.n, in.h, in.w, in.c, in.ld, out.ld, stride, scale);
+    else
+        upsample_kernel<T, 1><<<grid_for(pixels * in.c), kThreads, 0, s>>>((const T *)in.p, (T *)out.p, in.n, in.h, in.w, in.c, in.ld, out.ld, stride, scale);
+    B200_LAUNCHED();
+}
+
+void launch_upsample(TView in, TView out, int stride, float scale, cudaStream_t s)
+{
+    if (in.dtype == DT_F32) upsample_dispatch<float>(in, out, stride, scale, s);
+    else upsample_dispatch<bf16>(in, out, stride, scale, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shortcut: out = act(alpha*in + beta*add) on the overlapping region, act(in) elsewhere.
+// Fast path (identical shapes, the only case in YOLOv3) is a pure 128-bit streaming kernel; the general
+// path reproduces shortcut_cpu's stride/sample indexing for mismatched shapes.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC, bool EXACT>
+__global__ void shortcut_same_kernel(const T *__restrict__ in, const T *__restrict__ add, T *__restrict__ out, long long pixels,
+                                     int C, int ldi, int lda, int ldo, float alpha, float beta, int act)
+{
+    const int cv = C / VEC;
+    const long long total = pixels * cv;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(t % cv);
+        long long pix = t / cv;
+        float a[VEC], b[VEC];
+        if (VEC == 1) { a[0] = Elem<T>::load(in + pix * ldi + v); b[0] = Elem<T>::load(add + pix * lda + v); }
+        else { load_vec<T>(in + pix * ldi + v * VEC, a); load_vec<T>(add + pix * lda + v * VEC, b); }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) a[i] = apply_act<EXACT>(__fadd_rn(__fmul_rn(alpha, a[i]), __fmul_rn(beta, b[i])), act);
+        if (VEC == 1) Elem<T>::store(out + pix * ldo + v, a[0]);
+        else store_vec<T>(out + pix * ldo + v * VEC, a);
+    }
+}
+
+template <typename T, bool EXACT>
+__global__ void shortcut_general_kernel(const T *__restrict__ in, const T *__restrict__ add, T *__restrict__ out, int N,
+                                        int w1, int h1, int c1, int lda, int w2, int h2, int c2, int ldi, int ldo,
+                                        float alpha, float beta, int act)
+{
+    // (w1,h1,c1) = added tensor, (w2,h2,c2) = tensor flowing through; see blas.c:68-92
+    int stride = w1 / w2, sample = w2 / w1;
+    if (stride < 1) stride = 1;
+    if (sample < 1) sample = 1;
+    const int minw = w1 < w2 ? w1 : w2, minh = h1 < h2 ? h1 : h2, minc = c1 < c2 ? c1 : c2;
+    const long long total = (long long)N * h2 * w2 * c2;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(t % c2);
+        long long pix = t / c2;
+        int x = (int)(pix % w2), y = (int)((pix / w2) % h2), n = (int)(pix / ((long long)w2 * h2));
+        float v = Elem<T>::load(in + pix * ldi + k);
+        if (k < minc && x % sample == 0 && y % sample == 0 && x / sample < minw && y / sample < minh) {
+            int i = x / sample, j = y / sample;
+            float a = Elem<T>::load(add + (((size_t)n * h1 + j * stride) * w1 + i * stride) * lda + k);
+            v = __fadd_rn(__fmul_rn(alpha, v), __fmul_rn(beta, a));
+        }
+        Elem<T>::store(out + pix * ldo + k, apply_act<EXACT>(v, act));
+    }
+}
+
+template <typename T, bool EXACT>
+static void shortcut_dispatch(TView in, TView add, TView out, float alpha, float beta, int act, cudaStream_t s)
+{
+    constexpr int V = Elem<T>::VEC;
+    long long pixels = (long long)out.n * out.h * out.w;
+    bool same = add.w == out.w && add.h == out.h && add.c == out.c;
+    if (same) {
+        bool vec_ok = (out.c % V == 0) && (in.ld % V == 0) && (add.ld % V == 0) && (out.ld % V == 0) &&
+                      ((uintptr_t)in.p % 16 == 0) && ((uintptr_t)add.p % 16 == 0) && ((uintptr_t)out.p % 16 == 0);
+        if (vec_ok)
+            shortcut_same_kernel<T, V, EXACT><<<grid_for(pixels * (out.c / V)), kThreads, 0, s>>>(
+                (const T *)in.p, (const T *)add.p, (T *)out.p, pixels, out.c, in.ld, add.ld, out.ld, alpha, beta, act);
+        else
+            shortcut_same_kernel<T, 1, EXACT><<<grid_for(pixels * out.c), kThreads, 0, s>>>(
+                (const T *)in.p, (const T *)add.p, (T *)out.p, pixels, out.c, in.ld, add.ld, out.ld, alpha, beta, act);
+    } else {
+        shortcut_general_kernel<T, EXACT><<<grid_for(pixels * out.c), kThreads, 0, s>>>(
+            (const T *)in.p, (const T *)add.p, (T *)out.p, out.n, add.w, add.h, add.c, add.ld, out.w, out.h, out.c,
+            in.ld, out.ld, alpha, beta, act);
+    }
+    B200_LAUNCHED();
+}
+
+void launch_shortcut(TView in, TView add, TView out, float alpha, float beta, int act, cudaStream_t s)
+{
+    if (in.dtype == DT_F32) shortcut_dispatch<float, true>(in, add, out, alpha, beta, act, s);
+    else shortcut_dispatch<bf16, false>(in, add, out, alpha, beta, act, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// route: copy one input into its channel slice of the concat buffer (16-byte vectors when aligned)
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void copy_channels_kernel(const T *__restrict__ in, T *__restrict__ out, long long pixels, int C, int ldi, int ldo)
+{
+    const int cv = C / VEC;
+    const long long total = pixels * cv;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(t % cv);
+        long long pix = t / cv;
+        if (VEC == 1) out[pix * ldo + v] = in[pix * ldi + v];
+        else *reinterpret_cast<uint4 *>(out + pix * ldo + v * VEC) = *reinterpret_cast<const uint4 *>(in + pix * ldi + v * VEC);
+    }
+}
+
+template <typename T>
+static void copy_dispatch(TView in, TView out, cudaStream_t s)
+{
+    constexpr int V = Elem<T>::VEC;
+    long long pixels = (long long)in.n * in.h * in.w;
+    bool vec_ok = (in.c % V == 0) && (in.ld % V == 0) && (out.ld % V == 0) &&
+                  ((uintptr_t)in.p % 16 == 0) && ((uintptr_t)out.p % 16 == 0);
+    if (vec_ok) copy_channels_kernel<T, V><<<grid_for(pixels * (in.c / V)), kThreads, 0, s>>>((const T *)in.p, (T *)out.p, pixels, in.c, in.ld, out.ld);
+    else copy_channels_kernel<T, 1><<<grid_for(pixels * in.c), kThreads, 0, s>>>((const T *)in.p, (T *)out.p, pixels, in.c, in.ld, out.ld);
+    B200_LAUNCHED();
+}
+
+void launch_copy_channels(TView in, TView out, cudaStream_t s)
+{
+    if (in.dtype != out.dtype) { fprintf(stderr, "b200-darknet: route dtype mismatch\n"); abort(); }
+    if (in.dtype == DT_F32) copy_dispatch<float>(in, out, s);
+    else copy_dispatch<bf16>(in, out, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reorg (YOLOv2 passthrough).  The reference calls reorg_cpu(..., forward=0): with (w,h,c) the INPUT dims,
+// flat NCHW position p of the output takes flat NCHW position q(p) of the input, where p is decomposed as
+// (k,j,i) over [c][h][w] and q = w2 + w*s*(h2 + h*s*c2) with c2 = k % (c/s^2), off = k / (c/s^2),
+// w2 = i*s + off % s, h2 = j*s + off / s.  This is a permutation but NOT space_to_depth; it is reproduced
+// index for index.  One thread per output element, output-channel fastest so writes coalesce in NHWC.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void reorg_kernel(const T *__restrict__ in, T *__restrict__ out, int N, int h, int w, int c, int ldi,
+                             int oh, int ow, int oc, int ldo, int s)
+{
+    const long long total = (long long)N * oh * ow * oc;
+    const int small_c = c / (s * s);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int co = (int)(t % oc);
+        long long pix = t / oc;
+        int xo = (int)(pix % ow), yo = (int)((pix / ow) % oh), n = (int)(pix / ((long long)ow * oh));
+        int p = xo + ow * (yo + oh * co);                       // flat NCHW offset in the output image
+        int i = p % w, j = (p / w) % h, k = p / (w * h);        // same offset seen through the INPUT shape
+        int c2 = k % small_c, off = k / small_c;
+        int w2 = i * s + off % s, h2 = j * s + off / s;
+        int q = w2 + w * s * (h2 + h * s * c2);                 // flat NCHW offset in the input image
+        int xi = q % w, yi = (q / w) % h, ci = q / (w * h);
+        out[pix * ldo + co] = in[(((size_t)n * h + yi) * w + xi) * ldi + ci];
+    }
+}
+
+void launch_reorg(TView in, TView out, int stride, cudaStream_t s)
+{
+    long long total = (long long)out.n * out.h * out.w * out.c;
+    if (in.dtype == DT_F32)
+        reorg_kernel<float><<<grid_for(total), kThreads, 0, s>>>((const float *)in.p, (float *)out.p, in.n, in.h, in.w, in.c, in.ld, out.h, out.w, out.c, out.ld, stride);
+    else
+        reorg_kernel<bf16><<<grid_for(total), kThreads, 0, s>>>((const bf16 *)in.p, (bf16 *)out.p, in.n, in.h, in.w, in.c, in.ld, out.h, out.w, out.c, out.ld, stride);
+    B200_LAUNCHED();
+}

@@ -1,0 +1,297 @@
+// nms.cu — class-wise non-maximum suppression (do_nms_sort, box.c:58-89) and do_nms_obj (box.c:21-55) on device.
+//
+// Reference algorithm, per class k: order the live detections by prob[k] descending (qsort with nms_comparator,
+// box.c:6-19), then greedily, for each i with prob[k] != 0, zero prob[k] of every later j whose
+// box_iou(i,j) > thresh (strict, fp32, box.c:152-182).  Classes are independent (class k only reads/writes
+// prob[k] and the boxes), so every (image, class) pair is one unit of work for one CTA:
+//   1. ordered gather of the detections with prob[k] != 0 (warp-ballot compaction keeps the original order),
+//   2. rank sort, descending, ties broken by original index (a stable order; the reference's qsort leaves tie
+//      order unspecified, and entries with prob 0 can never suppress or be suppressed so they are not sorted),
+//   3. bitmask-IoU: bit j of row i says "i suppresses j" (j > i), 32 IoUs per thread per word, rows kept in
+//      shared memory when the class has <= NMS_SMEM_M survivors and in a per-CTA HBM slab otherwise,
+//   4. one warp scans the rows in order, OR-ing the row of every still-alive box into the removed set,
+//   5. removed boxes get prob[k] = 0.
+// The IoU uses explicit round-to-nearest intrinsics in the reference's operation order so no FMA contraction can
+// change a comparison: keep-lists are bit-exact against the CPU path when fed the same boxes.
+#include "kernels.h"
+
+#define NMS_THREADS 256
+#define NMS_SMEM_M 512                       // survivors per class whose IoU bit-matrix lives in shared memory
+
+__device__ __forceinline__ float overlap_ref(float x1, float w1, float x2, float w2)
+{
+    float l1 = __fsub_rn(x1, __fdiv_rn(w1, 2.f)), l2 = __fsub_rn(x2, __fdiv_rn(w2, 2.f));
+    float left = l1 > l2 ? l1 : l2;
+    float r1 = __fadd_rn(x1, __fdiv_rn(w1, 2.f)), r2 = __fadd_rn(x2, __fdiv_rn(w2, 2.f));
+    float right = r1 < r2 ? r1 : r2;
+    return __fsub_rn(right, left);
+}
+
+__device__ __forceinline__ float iou_ref(float4 a, float4 b)      // (x,y,w,h) centre + size
+{
+    float w = overlap_ref(a.x, a.z, b.x, b.z);
+    float h = overlap_ref(a.y, a.w, b.y, b.w);
+    float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+// layout of the per-unit work area (either dynamic shared memory or the CTA's HBM slab)
+struct NmsWork {
+    float *score;      // [m] gathered scores, original order
+    int *src;          // [m] original detection index, original order
+    int *order;        // [m] original detection index, sorted order
+    float4 *sbox;      // [m] boxes, sorted order
+    unsigned *mask;    // [m][words]
+};
+
+__device__ __forceinline__ size_t work_bytes(int m)
+{
+    size_t words = (m + 31) / 32;
+    return (size_t)m * (4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
+}
+
+__device__ __forceinline__ NmsWork carve(unsigned char *base, int m)
+{
+    NmsWork w;
+    size_t off = 0;
+    w.sbox = (float4 *)(base + off); off += (size_t)m * 16;
+    w.score = (float *)(base + off); off += (size_t)m * 4;
+    w.src = (int *)(base + off); off += (size_t)m * 4;
+    w.order = (int *)(base + off); off += (size_t)m * 4;
+    off = (off + 15) & ~(size_t)15;
+    w.mask = (unsigned *)(base + off);
+    return w;
+}
+
+// score(i) = base[i*stride + k]; live(i) = obj[i] != 0 (NULL obj => all live)
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float *__restrict__ obj,
+           const int *__restrict__ count, int images, int cap, int classes, int score_stride, float thresh,
+           unsigned char *__restrict__ slab, size_t slab_bytes, unsigned char *__restrict__ suppressed_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int warp_totals[NMS_THREADS / 32];
+    __shared__ int s_m;
+    // removed bitset for up to 32768 candidates lives at the front of dynamic smem (4 KB)
+    unsigned *removed = (unsigned *)smem;
+    unsigned char *smem_work = smem + 4096;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int unit = blockIdx.x; unit < images * classes; unit += gridDim.x) {
+        const int img = unit / classes, k = unit % classes;
+        const int n = count ? count[img] : cap;
+        const float *ubox = box + (size_t)img * cap * 4;
+        float *uscore = score + (size_t)img * cap * score_stride + k;
+        const float *uobj = obj ? obj + (size_t)img * cap : nullptr;
+
+        // ---- pass A: count survivors (decides where the work area lives)
+        int m = 0;
+        for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
+            int i = i0 + threadIdx.x;
+            bool f = i < n && uscore[(size_t)i * score_stride] != 0.f && (!uobj || uobj[i] != 0.f);
+            unsigned b = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) warp_totals[warp] = __popc(b);
+            __syncthreads();
+            for (int w = 0; w < NMS_THREADS / 32; ++w) m += warp_totals[w];
+            __syncthreads();
+        }
+        if (m <= 1) continue;                                   // nothing can be suppressed
+        unsigned char *base = (m <= NMS_SMEM_M) ? smem_work : slab + (size_t)blockIdx.x * slab_bytes;
+        if (m > NMS_SMEM_M && work_bytes(m) > slab_bytes) {     // cannot happen: host sizes the slab from max_count
+            if (threadIdx.x == 0) printf("b200-darknet: nms slab too small (m=%d)\n", m);
+            __trap();
+        }
+        NmsWork wk = carve(base, m);
+        const int words = (m + 31) / 32;
+
+        // ---- pass B: ordered gather
+        int written = 0;
+        for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
+            int i = i0 + threadIdx.x;
+            float sc = i < n ? uscore[(size_t)i * score_stride] : 0.f;
+            bool f = i < n && sc != 0.f && (!uobj || uobj[i] != 0.f);
+            unsigned b = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) warp_totals[warp] = __popc(b);
+            __syncthreads();
+            int before = 0, tot = 0;
+            for (int w = 0; w < NMS_THREADS / 32; ++w) { int c = warp_totals[w]; if (w < warp) before += c; tot += c; }
+            if (f) { int d = written + before + __popc(b & ((1u << lane) - 1)); wk.score[d] = sc; wk.src[d] = i; }
+            written += tot;
+            __syncthreads();
+        }
+
+        // ---- rank sort (descending score, ties by original order)
+        for (int i = threadIdx.x; i < m; i += NMS_THREADS) {
+            float si = wk.score[i];
+            int rank = 0;
+            for (int j = 0; j < m; ++j) {
+                float sj = wk.score[j];
+                rank += (sj > si) || (sj == si && j < i);
+            }
+            int d = wk.src[i];
+            wk.order[rank] = d;
+            wk.sbox[rank] = *reinterpret_cast<const float4 *>(ubox + (size_t)d * 4);
+        }
+        for (int w = threadIdx.x; w < words; w += NMS_THREADS) removed[w] = 0u;
+        __syncthreads();
+
+        // ---- IoU bit-matrix: word (i, wj) covers j in [32*wj, 32*wj+32), only j > i matters
+        for (long long t = threadIdx.x; t < (long long)m * words; t += NMS_THREADS) {
+            int i = (int)(t / words), wj = (int)(t % words);
+            unsigned bits = 0u;
+            if (wj * 32 + 31 > i) {
+                float4 a = wk.sbox[i];
+                int j0 = wj * 32;
+#pragma unroll 4
+                for (int b = 0; b < 32; ++b) {
+                    int j = j0 + b;
+                    if (j > i && j < m && iou_ref(a, wk.sbox[j]) > thresh) bits |= 1u << b;
+                }
+            }
+            wk.mask[(size_t)i * words + wj] = bits;
+        }
+        __syncthreads();
+
+        // ---- greedy scan by warp 0
+        if (warp == 0) {
+            for (int i = 0; i < m; ++i) {
+                unsigned r = removed[i >> 5];
+                if (!((r >> (i & 31)) & 1u)) {
+                    for (int w = (i >> 5) + lane; w < words; w += 32) removed[w] |= wk.mask[(size_t)i * words + w];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+
+        // ---- write back
+        for (int i = threadIdx.x; i < m; i += NMS_THREADS) {
+            if ((removed[i >> 5] >> (i & 31)) & 1u) {
+                int d = wk.order[i];
+                uscore[(size_t)d * score_stride] = 0.f;
+                if (suppressed_out) suppressed_out[(size_t)img * cap + d] = 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t host_work_bytes(int m)
+{
+    size_t words = (m + 31) / 32;
+    return (size_t)m * (4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
+}
+
+static void ensure_scratch(NmsScratch *sc, int max_count, int ctas)
+{
+    size_t need = max_count > NMS_SMEM_M ? (host_work_bytes(max_count) + 255) / 256 * 256 : 0;
+    if (need * ctas > sc->words_per_cta * (size_t)sc->ctas || (need && !sc->mask)) {
+        if (sc->mask) B200_CHECK(cudaFree(sc->mask));
+        B200_CHECK(cudaMalloc((void **)&sc->mask, need * ctas));
+    }
+    sc->words_per_cta = need;   // bytes per CTA (name kept for the header)
+    sc->ctas = ctas;
+}
+
+static void run_nms(const float *box, float *score, const float *obj, const int *count, int images, int cap, int classes,
+                    int stride, float thresh, int max_count, NmsScratch *scratch, unsigned char *supp, cudaStream_t s)
+{
+    if (max_count > 32768) { fprintf(stderr, "b200-darknet: nms supports at most 32768 candidates per image\n"); abort(); }
+    int units = images * classes;
+    int ctas = units < 148 * 2 ? units : 148 * 2;
+    if (ctas < 1) return;
+    ensure_scratch(scratch, max_count, ctas);
+    size_t smem = 4096 + host_work_bytes(NMS_SMEM_M);
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    nms_kernel<<<ctas, NMS_THREADS, smem, s>>>(box, score, obj, count, images, cap, classes, stride, thresh,
+                                               (unsigned char *)scratch->mask, scratch->words_per_cta, supp);
+    B200_LAUNCHED();
+}
+
+void launch_nms_sort(const float *box, float *prob, const float *obj, const int *count, int images, int cap,
+                     int classes, float thresh, int max_count, NmsScratch *scratch, cudaStream_t s)
+{
+    run_nms(box, prob, obj, count, images, cap, classes, classes, thresh, max_count, scratch, nullptr, s);
+}
+
+// do_nms_obj: one class-agnostic pass ordered by objectness; a suppressed detection loses objectness and all probs
+__global__ void zero_suppressed_kernel(const unsigned char *__restrict__ supp, float *__restrict__ prob,
+                                       const int *__restrict__ count, int images, int cap, int classes)
+{
+    long long total = (long long)images * cap * classes;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long d = t / classes;
+        int img = (int)(d / cap), i = (int)(d % cap);
+        if (i < (count ? count[img] : cap) && supp[d]) prob[t] = 0.f;
+    }
+}
+
+void launch_nms_obj(const float *box, float *obj, float *prob, const int *count, int images, int cap, int classes,
+                    float thresh, int max_count, NmsScratch *scratch, cudaStream_t s)
+{
+    unsigned char *supp = nullptr;
+    B200_CHECK(cudaMallocAsync((void **)&supp, (size_t)images * cap, s));
+    B200_CHECK(cudaMemsetAsync(supp, 0, (size_t)images * cap, s));
+    run_nms(box, obj, nullptr, count, images, cap, 1, 1, thresh, max_count, scratch, supp, s);
+    if (prob) {
+        long long total = (long long)images * cap * classes;
+        int grid = (int)((total + 255) / 256);
+        if (grid > 148 * 8) grid = 148 * 8;
+        zero_suppressed_kernel<<<grid, 256, 0, s>>>(supp, prob, count, images, cap, classes);
+        B200_LAUNCHED();
+    }
+    B200_CHECK(cudaFreeAsync(supp, s));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// collect: surviving (detection, class) pairs -> compact records (one atomic slot per warp-ballot group)
+// ---------------------------------------------------------------------------------------------------
+__global__ void collect_kernel(const float *__restrict__ box, const float *__restrict__ prob, const float *__restrict__ obj,
+                               const int *__restrict__ id, const int *__restrict__ count, int images, int cap, int classes,
+                               DetRecord *__restrict__ out, int max_out, int *__restrict__ out_count)
+{
+    const long long total = (long long)images * cap * classes;
+    const int lane = threadIdx.x & 31;
+    for (long long t0 = blockIdx.x * (long long)blockDim.x; t0 < total; t0 += (long long)gridDim.x * blockDim.x) {
+        long long t = t0 + threadIdx.x;
+        bool f = false;
+        int img = 0, i = 0, k = 0;
+        float p = 0.f;
+        if (t < total) {
+            k = (int)(t % classes);
+            long long d = t / classes;
+            img = (int)(d / cap); i = (int)(d % cap);
+            if (i < count[img] && obj[d] != 0.f) { p = prob[t]; f = p != 0.f; }
+        }
+        unsigned b = __ballot_sync(0xffffffffu, f);
+        int base = 0;
+        if (lane == 0 && b) base = atomicAdd(out_count, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (f) {
+            int slot = base + __popc(b & ((1u << lane) - 1));
+            if (slot < max_out) {
+                size_t d = (size_t)img * cap + i;
+                DetRecord r;
+                r.image = img; r.cls = k; r.box_id = id[d]; r.prob = p; r.objectness = obj[d];
+                r.x = box[d * 4 + 0]; r.y = box[d * 4 + 1]; r.w = box[d * 4 + 2]; r.h = box[d * 4 + 3];
+                out[slot] = r;
+            }
+        }
+    }
+}
+
+void launch_collect(const float *box, const float *prob, const float *obj, const int *id, const int *count, int images,
+                    int cap, int classes, DetRecord *out, int max_out, int *out_count, cudaStream_t s)
+{
+    long long total = (long long)images * cap * classes;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    collect_kernel<<<grid, 256, 0, s>>>(box, prob, obj, id, count, images, cap, classes, out, max_out, out_count);
+    B200_LAUNCHED();
+}
