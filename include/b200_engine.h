@@ -61,6 +61,12 @@ const char *b200_layer_kernel(network *net, int i);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
 
+/* accessors for FFI callers: 20 ints = type, batch, inputs, outputs, h, w, c, out_h, out_w, out_c, n, size, stride, pad,
+ * classes, coords, batch_normalize, activation, nweights, index */
+int b200_network_layers(const network *net);
+int b200_layer_info(const network *net, int i, int *out);
+float *b200_layer_output_host(const network *net, int i);
+
 /* ---- additive batched box extraction + NMS ------------------------------------------------------- */
 /* get_network_boxes for batch item b (the reference only ever reads item 0: yolo_layer.c:281,326). */
 detection *get_network_boxes_batch(network *net, int b, int w, int h, float thresh, float hier,

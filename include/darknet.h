@@ -156,6 +156,11 @@ void   free_image(image m);
 image  resize_image(image im, int w, int h);                                /* image.c:1347 */
 image  letterbox_image(image im, int w, int h);                             /* image.c:960  */
 float  box_iou(box a, box b);                                               /* box.c:179    */
+image  load_image_color(char *filename, int w, int h);                      /* image.c:1482 (binary PPM/PGM only here) */
+void   rgbgr_image(image im);
+metadata get_metadata(char *file);                                          /* option_list.c:35 */
+void   free_ptrs(void **ptrs, int n);
+void   reset_rnn(network *net);
 
 #ifdef __cplusplus
 }

@@ -242,3 +242,19 @@ void free_network(network *net)
     free(net->steps); free(net->scales);
     free(net);
 }
+
+/* ---- small accessors for foreign-function callers that do not want to mirror the 1160-byte layer struct ---- */
+int b200_network_layers(const network *net) { return net->n; }
+
+int b200_layer_info(const network *net, int i, int *out)
+{
+    if (i < 0 || i >= net->n) return -1;
+    const layer *l = &net->layers[i];
+    int v[20] = { (int)l->type, l->batch, l->inputs, l->outputs, l->h, l->w, l->c, l->out_h, l->out_w, l->out_c,
+                  l->n, l->size, l->stride, l->pad, l->classes, l->coords, l->batch_normalize, (int)l->activation,
+                  l->nweights, l->index };
+    memcpy(out, v, sizeof v);
+    return 20;
+}
+
+float *b200_layer_output_host(const network *net, int i) { return (i < 0 || i >= net->n) ? NULL : net->layers[i].output; }

@@ -1,0 +1,221 @@
+"""ctypes binding of libdarknet.so — same names, argument meaning and struct layouts as the reference
+wrapper (Darknet2Tensorflow/darknet-master/python/darknet.py:20-143), so code written against it keeps
+working, plus the additive batched entry points of include/b200_engine.h.
+
+Importing this module fails loudly when the native library has not been built: there is no Python or
+CPU fallback for any compute call.
+"""
+import os
+from ctypes import (CDLL, POINTER, RTLD_GLOBAL, Structure, c_char_p, c_float, c_int, c_size_t, c_ubyte,
+                    c_ulonglong, c_void_p, byref, pointer)
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("B200_DARKNET_LIB", os.path.join(_HERE, "lib", "libdarknet.so"))
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "or `make -C yolo_tensorflow_b200/csrc` (no CPU fallback exists)")
+
+
+class BOX(Structure):
+    _fields_ = [("x", c_float), ("y", c_float), ("w", c_float), ("h", c_float)]
+
+
+class DETECTION(Structure):
+    _fields_ = [("bbox", BOX), ("classes", c_int), ("prob", POINTER(c_float)), ("mask", POINTER(c_float)),
+                ("objectness", c_float), ("sort_class", c_int)]
+
+
+class IMAGE(Structure):
+    _fields_ = [("w", c_int), ("h", c_int), ("c", c_int), ("data", POINTER(c_float))]
+
+
+class METADATA(Structure):
+    _fields_ = [("classes", c_int), ("names", POINTER(c_char_p))]
+
+
+class B200_DET(Structure):
+    """include/b200_engine.h b200_det: one surviving (box, class) pair of the fused device path."""
+    _fields_ = [("image", c_int), ("cls", c_int), ("box_id", c_int), ("prob", c_float), ("objectness", c_float),
+                ("bbox", BOX)]
+
+
+lib = CDLL(LIB_PATH, RTLD_GLOBAL)
+
+# ---- reference surface (python/darknet.py:48-115) --------------------------------------------------
+lib.network_width.argtypes = [c_void_p]; lib.network_width.restype = c_int
+lib.network_height.argtypes = [c_void_p]; lib.network_height.restype = c_int
+predict = lib.network_predict
+predict.argtypes = [c_void_p, POINTER(c_float)]; predict.restype = POINTER(c_float)
+network_predict = predict
+set_gpu = lib.cuda_set_device; set_gpu.argtypes = [c_int]
+make_image = lib.make_image; make_image.argtypes = [c_int, c_int, c_int]; make_image.restype = IMAGE
+get_network_boxes = lib.get_network_boxes
+get_network_boxes.argtypes = [c_void_p, c_int, c_int, c_float, c_float, POINTER(c_int), c_int, POINTER(c_int)]
+get_network_boxes.restype = POINTER(DETECTION)
+make_network_boxes = lib.make_network_boxes
+make_network_boxes.argtypes = [c_void_p, c_float, POINTER(c_int)]; make_network_boxes.restype = POINTER(DETECTION)
+free_detections = lib.free_detections; free_detections.argtypes = [POINTER(DETECTION), c_int]
+free_ptrs = lib.free_ptrs; free_ptrs.argtypes = [POINTER(c_void_p), c_int]
+reset_rnn = lib.reset_rnn; reset_rnn.argtypes = [c_void_p]
+load_net = lib.load_network; load_net.argtypes = [c_char_p, c_char_p, c_int]; load_net.restype = c_void_p
+parse_network_cfg = lib.parse_network_cfg; parse_network_cfg.argtypes = [c_char_p]; parse_network_cfg.restype = c_void_p
+load_weights = lib.load_weights; load_weights.argtypes = [c_void_p, c_char_p]
+free_network = lib.free_network; free_network.argtypes = [c_void_p]
+set_batch_network = lib.set_batch_network; set_batch_network.argtypes = [c_void_p, c_int]
+do_nms_obj = lib.do_nms_obj; do_nms_obj.argtypes = [POINTER(DETECTION), c_int, c_int, c_float]
+do_nms_sort = lib.do_nms_sort; do_nms_sort.argtypes = [POINTER(DETECTION), c_int, c_int, c_float]
+free_image = lib.free_image; free_image.argtypes = [IMAGE]
+letterbox_image = lib.letterbox_image; letterbox_image.argtypes = [IMAGE, c_int, c_int]; letterbox_image.restype = IMAGE
+resize_image = lib.resize_image; resize_image.argtypes = [IMAGE, c_int, c_int]; resize_image.restype = IMAGE
+load_meta = lib.get_metadata; lib.get_metadata.argtypes = [c_char_p]; lib.get_metadata.restype = METADATA
+load_image = lib.load_image_color; load_image.argtypes = [c_char_p, c_int, c_int]; load_image.restype = IMAGE
+rgbgr_image = lib.rgbgr_image; rgbgr_image.argtypes = [IMAGE]
+predict_image = lib.network_predict_image; predict_image.argtypes = [c_void_p, IMAGE]; predict_image.restype = POINTER(c_float)
+
+# ---- additive surface (include/b200_engine.h) --------------------------------------------------------
+PREC_BF16, PREC_FP32 = 0, 1
+lib.b200_set_default_precision.argtypes = [c_int]
+lib.b200_get_precision.argtypes = [c_void_p]; lib.b200_get_precision.restype = c_int
+lib.b200_set_conv_backend.argtypes = [c_void_p, c_int]
+lib.b200_set_head_sync.argtypes = [c_void_p, c_int]
+lib.b200_fetch_layer_output.argtypes = [c_void_p, c_int, POINTER(c_float)]
+lib.b200_set_layer_output.argtypes = [c_void_p, c_int, POINTER(c_float)]
+lib.b200_run_layers.argtypes = [c_void_p, c_int, c_int]
+lib.b200_layer_kernel.argtypes = [c_void_p, c_int]; lib.b200_layer_kernel.restype = c_char_p
+lib.b200_launch_count.restype = c_ulonglong
+lib.b200_network_layers.argtypes = [c_void_p]; lib.b200_network_layers.restype = c_int
+lib.b200_layer_info.argtypes = [c_void_p, c_int, POINTER(c_int)]; lib.b200_layer_info.restype = c_int
+lib.b200_layer_output_host.argtypes = [c_void_p, c_int]; lib.b200_layer_output_host.restype = POINTER(c_float)
+lib.b200_weights_arena.argtypes = [c_void_p, POINTER(c_size_t)]; lib.b200_weights_arena.restype = c_void_p
+lib.b200_engine_of.argtypes = [c_void_p]; lib.b200_engine_of.restype = c_void_p
+lib.b200_engine_forward_resident.argtypes = [c_void_p, c_void_p]
+lib.b200_engine_input_device.argtypes = [c_void_p]; lib.b200_engine_input_device.restype = c_void_p
+lib.b200_engine_sync.argtypes = [c_void_p]
+lib.get_network_boxes_batch.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_float, POINTER(c_int), c_int, POINTER(c_int)]
+lib.get_network_boxes_batch.restype = POINTER(DETECTION)
+lib.b200_detect_batch.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(B200_DET), c_int, POINTER(c_int)]
+lib.b200_detect_batch.restype = c_int
+lib.b200_nms_sort_arrays.argtypes = [POINTER(c_float), POINTER(c_float), c_int, c_int, c_float]
+lib.b200_nms_obj_arrays.argtypes = [POINTER(c_float), POINTER(c_float), c_int, c_float, POINTER(c_ubyte)]
+
+LAYER_INFO_FIELDS = ("type", "batch", "inputs", "outputs", "h", "w", "c", "out_h", "out_w", "out_c", "n", "size",
+                     "stride", "pad", "classes", "coords", "batch_normalize", "activation", "nweights", "index")
+LAYER_TYPES = ("CONVOLUTIONAL DECONVOLUTIONAL CONNECTED MAXPOOL SOFTMAX DETECTION DROPOUT CROP ROUTE COST NORMALIZATION "
+               "AVGPOOL LOCAL SHORTCUT ACTIVE RNN GRU LSTM CRNN BATCHNORM NETWORK XNOR REGION YOLO REORG UPSAMPLE "
+               "LOGXENT L2NORM BLANK").split()
+
+
+def _fptr(a):
+    return a.ctypes.data_as(POINTER(c_float))
+
+
+class Network:
+    """Convenience owner of a `network*` (what the reference wrapper passes around as c_void_p)."""
+
+    def __init__(self, cfg, weights=None, precision=None):
+        if precision is not None:
+            lib.b200_set_default_precision(int(precision))
+        self.ptr = parse_network_cfg(str(cfg).encode())
+        if precision is not None:
+            lib.b200_set_default_precision(-1)
+        if weights:
+            load_weights(self.ptr, str(weights).encode())
+        self.n = lib.b200_network_layers(self.ptr)
+        self.w, self.h = lib.network_width(self.ptr), lib.network_height(self.ptr)
+        self.layers = [self.layer_info(i) for i in range(self.n)]
+        self.batch = self.layers[0]["batch"]
+
+    def close(self):
+        if self.ptr:
+            free_network(self.ptr)
+            self.ptr = None
+
+    def layer_info(self, i):
+        buf = (c_int * 20)()
+        lib.b200_layer_info(self.ptr, i, buf)
+        d = dict(zip(LAYER_INFO_FIELDS, list(buf)))
+        d["type_name"] = LAYER_TYPES[d["type"]]
+        return d
+
+    def kernel(self, i):
+        return lib.b200_layer_kernel(self.ptr, i).decode()
+
+    def predict(self, x):
+        """network_predict: x is float32 [batch, c, h, w] (C-contiguous); returns the last layer's host output."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = predict(self.ptr, _fptr(x))
+        last = self.layers[-1]
+        return np.ctypeslib.as_array(out, shape=(self.batch * last["outputs"],)).copy()
+
+    def layer_output(self, i):
+        """device -> host fp32 in darknet layout, shape [batch, outputs]"""
+        li = self.layers[i]
+        out = np.empty((self.batch, li["outputs"]), dtype=np.float32)
+        lib.b200_fetch_layer_output(self.ptr, i, _fptr(out))
+        return out
+
+    def set_layer_output(self, i, a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        lib.b200_set_layer_output(self.ptr, i, _fptr(a))
+
+    def run_layers(self, start, end):
+        lib.b200_run_layers(self.ptr, start, end)
+
+    def boxes(self, b, w, h, thresh, relative=1):
+        """get_network_boxes_batch -> (dets pointer, count); caller frees with free_detections"""
+        num = c_int(0)
+        dets = lib.get_network_boxes_batch(self.ptr, b, w, h, thresh, .5, None, relative, byref(num))
+        return dets, num.value
+
+    def detect_batch(self, x, w, h, thresh, nms, relative=1, max_out=1 << 20):
+        """fused device path; x host float32 array or None (resident input). Returns (structured array, counts)."""
+        out = (B200_DET * max_out)()
+        counts = (c_int * self.batch)()
+        xp = None
+        if x is not None:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            xp = x.ctypes.data_as(c_void_p)
+        n = lib.b200_detect_batch(self.ptr, xp, w, h, thresh, nms, relative, out, max_out, counts)
+        rec = np.ctypeslib.as_array(out)[:n].copy() if n else np.zeros(0, dtype=np.dtype(B200_DET))
+        return rec, np.array(list(counts))
+
+
+def dets_to_arrays(dets, n, classes):
+    """DETECTION* -> (boxes [n,4], objectness [n], probs [n,classes]) numpy copies"""
+    boxes = np.zeros((n, 4), np.float32); obj = np.zeros(n, np.float32); probs = np.zeros((n, classes), np.float32)
+    for i in range(n):
+        d = dets[i]
+        boxes[i] = (d.bbox.x, d.bbox.y, d.bbox.w, d.bbox.h)
+        obj[i] = d.objectness
+        probs[i] = np.ctypeslib.as_array(d.prob, shape=(classes,))
+    return boxes, obj, probs
+
+
+def nms_sort_arrays(boxes, probs, thresh):
+    boxes = np.ascontiguousarray(boxes, np.float32); probs = np.array(probs, np.float32, copy=True, order="C")
+    lib.b200_nms_sort_arrays(_fptr(boxes), _fptr(probs), boxes.shape[0], probs.shape[1], thresh)
+    return probs
+
+
+def detect(net, meta, image, thresh=.5, hier_thresh=.5, nms=.45):
+    """python/darknet.py:125-143, unchanged semantics (do_nms_obj, relative=0)."""
+    im = load_image(image, 0, 0)
+    num = c_int(0)
+    pnum = pointer(num)
+    predict_image(net, im)
+    dets = get_network_boxes(net, im.w, im.h, thresh, hier_thresh, None, 0, pnum)
+    num = pnum[0]
+    if nms:
+        do_nms_obj(dets, num, meta.classes, nms)
+    res = []
+    for j in range(num):
+        for i in range(meta.classes):
+            if dets[j].prob[i] > 0:
+                b = dets[j].bbox
+                res.append((meta.names[i], dets[j].prob[i], (b.x, b.y, b.w, b.h)))
+    res = sorted(res, key=lambda x: -x[1])
+    free_image(im)
+    free_detections(dets, num)
+    return res
