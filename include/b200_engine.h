@@ -61,6 +61,11 @@ const char *b200_layer_kernel(network *net, int i);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
 
+/* the CUDA stream (cudaStream_t) every kernel of this network is launched on: time it with events recorded there */
+void *b200_engine_stream(network *net);
+/* average device milliseconds per layer over `iters` forwards (CUDA events between layers); ms has net->n entries */
+void b200_profile_layers(network *net, int iters, float *ms);
+
 /* accessors for FFI callers: 20 ints = type, batch, inputs, outputs, h, w, c, out_h, out_w, out_c, n, size, stride, pad,
  * classes, coords, batch_normalize, activation, nweights, index */
 int b200_network_layers(const network *net);

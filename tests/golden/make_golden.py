@@ -1,0 +1,87 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference CPU build (oracle/_ref, built from
+/root/reference by oracle/Makefile) on seeded synthetic cfg/weights/images.  Run in the authoring container
+(where /root/reference exists); the fixtures are committed, /root/reference never travels to the GPU box.
+
+  python tests/golden/make_golden.py            # writes the fixtures
+  python tests/golden/make_golden.py --calibrate  # prints the undamped head-logit std used by synth.HEAD_RAW_STD
+
+Each fixture holds, for one (model, size, batch): a strided sample of EVERY layer's output, the full head
+outputs, the reference's get_network_boxes result per image and its do_nms_sort result (identity-indexed).
+"""
+import os, sys
+import numpy as np
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from yolo_tensorflow_b200 import synth
+from oracle import ref_darknet as R
+
+WORK = "/tmp/b200_golden"
+CASES = [  # name, model, size, batch, image seed, thresh, nms
+    ("yolov3-tiny_96_b2", "yolov3-tiny", 96, 2, 1000, .5, .45),
+    ("yolov3-tiny_416_b1", "yolov3-tiny", 416, 1, 1000, .5, .45),       # BASELINE configs[0]
+    ("yolov3_96_b1", "yolov3", 96, 1, 1002, .05, .45),
+    ("yolov2_96_b2", "yolov2", 96, 2, 1001, .05, .45),
+    ("yolov1_448_b1", "yolov1", 448, 1, 1004, .2, .4),
+]
+SAMPLE = 512
+
+
+def sample_idx(n):
+    return np.unique(np.linspace(0, n - 1, min(n, SAMPLE)).astype(np.int64))
+
+
+def build(name, model, size, batch, seed, thresh, nms):
+    cfg = synth.make_cfg(model, WORK, batch=batch, width=size, height=size)
+    wpath = os.path.join(WORK, f"{model}.weights")
+    if not os.path.exists(wpath):
+        synth.write_weights(cfg, wpath, seed=0, damp_heads=True)
+    net = R.RefNet(cfg, wpath)
+    x = synth.make_images(batch, 3, size, size, seed)
+    net.predict(x)
+    d = dict(model=model, size=size, batch=batch, seed=seed, thresh=thresh, nms=nms, nlayers=net.n)
+    heads = net.head_layers()
+    for i in range(net.n):
+        o = net.layer_output(i)
+        idx = sample_idx(o.shape[1])
+        d[f"layer{i}_idx"] = idx
+        d[f"layer{i}_val"] = o[:, idx]
+        d[f"layer{i}_absmax"] = np.abs(o).max()
+        if i in heads and (size <= 96 or model == "yolov1"):
+            d[f"head{i}"] = o
+    d["heads"] = np.array(heads)
+    w_, h_ = (1, 1) if model == "yolov1" else (size, size)
+    for b in range(batch):
+        dets, n = net.boxes(b, w_, h_, thresh)
+        boxes, obj, probs = net.dets_arrays(dets, n)
+        after = R.ref_nms_sort_arrays(boxes, probs, nms, obj)
+        d[f"img{b}_boxes"], d[f"img{b}_obj"] = boxes, obj
+        nz = np.nonzero(probs)
+        d[f"img{b}_prob_rc"] = np.stack(nz).astype(np.int32)
+        d[f"img{b}_prob_v"] = probs[nz]
+        d[f"img{b}_kept_rc"] = np.stack(np.nonzero(after)).astype(np.int32)
+        net.free_dets(dets, n)
+    net.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(name, "layers", d["nlayers"], "dets/img", [len(d[f"img{b}_obj"]) for b in range(batch)],
+          "kept", [d[f"img{b}_kept_rc"].shape[1] for b in range(batch)])
+
+
+def calibrate():
+    for model, seed in (("yolov3-tiny", 1000), ("yolov3", 1002), ("yolov2", 1001), ("yolov1", 1004)):
+        cfg = synth.make_cfg(model, WORK, batch=1)
+        wpath = os.path.join(WORK, f"{model}_raw.weights")
+        synth.write_weights(cfg, wpath, seed=0, damp_heads=False)
+        net = R.RefNet(cfg, wpath)
+        net.predict(synth.make_images(1, 3, net.h, net.w, seed))
+        print(model, [float(net.layer_output(i - 1).std()) for i in net.head_layers()])
+        net.close()
+
+
+if __name__ == "__main__":
+    os.makedirs(WORK, exist_ok=True)
+    if "--calibrate" in sys.argv:
+        calibrate()
+    else:
+        for c in CASES:
+            build(*c)

@@ -1,0 +1,425 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C-ABI library
+(yolo_tensorflow_b200/lib/libdarknet.so); the oracle is only the checker.
+
+Tolerances (BASELINE.json north star):
+  * fp32 mode (CUDA-core fp32 path): per-layer activations and decoded boxes within rtol 1e-4 of the reference,
+    measured as max|diff| <= 1e-4 * max|ref| per layer; detection identity and NMS keep-lists exact.
+  * bf16 mode (tcgen05 path): teacher-forced per-layer activations within 1e-2 * max|ref|;
+    free-running head outputs within 5e-2 * max|ref| (error of 75 stacked bf16 convolutions).
+  * NMS: bit-exact keep-lists when fed the oracle's boxes.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden_probs, load_golden, model_files
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from oracle import np_darknet as P  # noqa: E402
+from oracle import ref_darknet as R  # noqa: E402
+from yolo_tensorflow_b200 import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL, BF16_LAYER_TOL, BF16_E2E_TOL = 1e-4, 1e-2, 5e-2
+CASES = ["yolov3-tiny_96_b2", "yolov3-tiny_416_b1", "yolov3_96_b1", "yolov2_96_b2", "yolov1_448_b1"]
+
+
+@pytest.fixture(scope="module")
+def dn():
+    from yolo_tensorflow_b200 import darknet
+    return darknet
+
+
+def open_net(dn, model, batch, size, workdir, prec, damp=True):
+    cfg, wpath = model_files(model, batch, size, workdir, damp)
+    fd = os.dup(2); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 2)
+    try:
+        net = dn.Network(cfg, wpath, precision=prec)
+    finally:
+        os.dup2(fd, 2); os.close(fd); os.close(devnull)
+    return net, cfg, wpath
+
+
+def kept_set(probs):
+    r, c = np.nonzero(probs)
+    return set(zip(r.tolist(), c.tolist()))
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures produced by the unmodified reference CPU build
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_matches_reference_golden(dn, name, workdir):
+    g = load_golden(name)
+    model, size, batch = str(g["model"]), int(g["size"]), int(g["batch"])
+    net, _, _ = open_net(dn, model, batch, size, workdir, dn.PREC_FP32)
+    x = synth.make_images(batch, 3, size, size, int(g["seed"]))
+    net.predict(x)
+    for i in range(net.n):
+        got = net.layer_output(i)[:, g[f"layer{i}_idx"]]
+        tol = FP32_TOL * float(g[f"layer{i}_absmax"]) + 1e-7
+        assert np.abs(got - g[f"layer{i}_val"]).max() <= tol, (i, net.layers[i]["type_name"], net.kernel(i))
+    classes = net.layers[-1]["classes"]
+    thresh, nms = float(g["thresh"]), float(g["nms"])
+    w_, h_ = (1, 1) if model == "yolov1" else (size, size)
+    rec, counts = net.detect_batch(x, w_, h_, thresh, nms)
+    for b in range(batch):
+        dets, n = net.boxes(b, w_, h_, thresh)
+        boxes, obj, probs = dn.dets_to_arrays(dets, n, classes)
+        assert n == len(g[f"img{b}_obj"])
+        if n:
+            np.testing.assert_allclose(boxes, g[f"img{b}_boxes"], rtol=2e-3, atol=1e-5)
+            np.testing.assert_allclose(obj, g[f"img{b}_obj"], rtol=1e-4, atol=1e-6)
+            gp = golden_probs(g, b, classes)
+            close = np.isclose(probs, gp, rtol=1e-3, atol=1e-5)
+            border = np.abs(np.maximum(probs, gp) - thresh) < 1e-4
+            assert (close | border).all()
+        # do_nms_sort through the drop-in API on the engine's own detections == reference keep-list
+        dn.do_nms_sort(dets, n, classes, nms)
+        _, obj2, after = dn.dets_to_arrays(dets, n, classes)
+        dn.free_detections(dets, n)
+        golden_kept = g[f"img{b}_kept_rc"].shape[1]
+        assert abs(int((after > 0).sum()) - golden_kept) <= max(2, golden_kept // 100)
+        # fused device path agrees with the API path
+        assert int((rec["image"] == b).sum()) == int((after > 0).sum())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_nms_kernel_bit_exact_on_reference_boxes(dn, name):
+    """feed the REFERENCE's boxes/probs to the device NMS: keep-list must equal the reference's exactly"""
+    g = load_golden(name)
+    classes = 20 if str(g["model"]) == "yolov1" else 80
+    for b in range(int(g["batch"])):
+        boxes, obj = g[f"img{b}_boxes"], g[f"img{b}_obj"]
+        probs = golden_probs(g, b, classes)
+        live = obj != 0                                     # do_nms_sort's partition (box.c:60-70)
+        out = dn.nms_sort_arrays(boxes[live], probs[live], float(g["nms"]))
+        full = probs.copy(); full[live] = out
+        rc = np.stack(np.nonzero(full)).astype(np.int32)
+        assert np.array_equal(rc, g[f"img{b}_kept_rc"])
+        kept_vals = full[rc[0], rc[1]]
+        assert np.array_equal(kept_vals, probs[rc[0], rc[1]])      # survivors keep their exact bits
+
+
+# ---------------------------------------------------------------------------------------------------
+# teacher-forced per-layer parity against the (golden-pinned) numpy port
+# ---------------------------------------------------------------------------------------------------
+def layer_sources(L, i):
+    if L.type == "route":
+        return L.src
+    if L.type == "shortcut":
+        return [i - 1, L.src]
+    return [i - 1]
+
+
+@pytest.mark.parametrize("model,size,batch", [("yolov3-tiny", 416, 1), ("yolov3", 160, 3), ("yolov2", 160, 2), ("yolov1", 448, 2)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_teacher_forced_layers(dn, model, size, batch, prec, workdir):
+    net, cfg, wpath = open_net(dn, model, batch, size, workdir, dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16)
+    port = P.Net(cfg, wpath)
+    x = synth.make_images(batch, 3, size, size, 77)
+    outs = port.forward(x)
+    tol = FP32_TOL if prec == "fp32" else BF16_LAYER_TOL
+    net.predict(x)
+    a0 = net.layer_output(0); r0 = outs[0].reshape(batch, -1)
+    assert np.abs(a0 - r0).max() <= tol * np.abs(r0).max()
+    kernels = set()
+    for i, L in enumerate(port.layers):
+        if i == 0:
+            continue
+        for j in layer_sources(L, i):
+            net.set_layer_output(j, outs[j].reshape(batch, -1))
+        net.run_layers(i, i + 1)
+        a = net.layer_output(i); r = outs[i].reshape(batch, -1)
+        kernels.add(net.kernel(i))
+        assert np.isfinite(a).all(), (i, L.type)
+        assert np.abs(a - r).max() <= tol * np.abs(r).max() + 1e-7, (i, L.type, net.kernel(i))
+    if prec == "bf16":
+        assert "conv_tc" in kernels            # the tcgen05 path is the one that ran
+    else:
+        assert "conv_simt" in kernels
+
+
+@pytest.mark.parametrize("model,size,batch", [("yolov3", 416, 2), ("yolov2", 416, 2)])
+def test_bf16_end_to_end_heads(dn, model, size, batch, workdir):
+    net, cfg, wpath = open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
+    port = P.Net(cfg, wpath)
+    x = synth.make_images(batch, 3, size, size, 1002)
+    outs = port.forward(x)
+    net.predict(x)
+    for i, L in enumerate(port.layers):
+        if L.type in ("yolo", "region"):
+            a = net.layer_output(i); r = outs[i].reshape(batch, -1)
+            assert np.abs(a - r).max() <= BF16_E2E_TOL * np.abs(r).max()
+            host = np.ctypeslib.as_array(dn.lib.b200_layer_output_host(net.ptr, i), shape=(batch * L.outputs,))
+            assert np.array_equal(host.reshape(batch, -1), a)        # l.output on the host is populated (network.c:505)
+    # detections: same boxes up to the bf16 noise at the threshold
+    for b in range(batch):
+        dets, n = net.boxes(b, size, size, .5)
+        pb, po, pp, _ = P.get_network_boxes(port, outs, b, size, size, .5)
+        dn.free_detections(dets, n)
+        if model == "yolov3":
+            assert abs(n - len(po)) <= max(3, len(po) // 20)
+        else:
+            assert n == len(po)
+
+
+# ---------------------------------------------------------------------------------------------------
+# conv_tc shape zoo (single-layer networks)
+# ---------------------------------------------------------------------------------------------------
+def single_conv_cfg(path, h, w, c, filters, size, stride, batch, bn=1, act="leaky", pre=16):
+    """a stem conv (so the tested layer gets bf16 NHWC input with `c` channels) followed by the conv under test"""
+    text = f"[net]\nbatch={batch}\nsubdivisions=1\nheight={h}\nwidth={w}\nchannels=3\nmomentum=0.9\ndecay=0.0005\nlearning_rate=0.001\nmax_batches=1\npolicy=constant\n"
+    text += f"[convolutional]\nbatch_normalize=1\nfilters={c}\nsize=3\nstride=1\npad=1\nactivation=leaky\n"
+    text += f"[convolutional]\n{'batch_normalize=1' if bn else ''}\nfilters={filters}\nsize={size}\nstride={stride}\npad=1\nactivation={act}\n"
+    open(path, "w").write(text)
+
+
+SHAPES = [  # h, w, c, filters, size, stride, batch
+    (13, 13, 64, 128, 3, 1, 5),      # 13x13 tile spanning images, batch not a multiple of TN
+    (26, 26, 32, 64, 3, 2, 3),       # stride 2, SW64 (C=32)
+    (27, 19, 16, 32, 3, 2, 2),       # odd sizes, stride 2, SW32 (C=16)
+    (52, 52, 128, 255, 1, 1, 2),     # 1x1 dense mode, 255 filters (padded to 256), linear below
+    (20, 20, 192, 512, 3, 1, 2),     # C=192 (3 k-blocks per tap), two filter tiles
+    (9, 9, 256, 1024, 1, 1, 4),      # four filter tiles
+    (16, 16, 64, 48, 5, 1, 2),       # 5x5 taps
+    (7, 7, 1024, 425, 1, 1, 3),      # YOLOv2 head shape: 425 filters -> 432 padded, ragged last filter tile
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_tc_shape(dn, shape, tmp_path):
+    h, w, c, filters, size, stride, batch = shape
+    cfg = str(tmp_path / "one.cfg")
+    act = "linear" if filters in (255, 425) else "leaky"
+    single_conv_cfg(cfg, h, w, c, filters, size, stride, batch, bn=0 if act == "linear" else 1, act=act)
+    wpath = str(tmp_path / "one.weights")
+    synth.write_weights(cfg, wpath, seed=3, damp_heads=False)
+    fd = os.dup(2); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 2)
+    try:
+        net = dn.Network(cfg, wpath, precision=dn.PREC_BF16)
+    finally:
+        os.dup2(fd, 2); os.close(fd); os.close(devnull)
+    assert net.kernel(1) == "conv_tc"
+    port = P.Net(cfg, wpath)
+    x = synth.make_images(batch, 3, h, w, 5)
+    outs = port.forward(x)
+    # teacher-force the bf16-rounded input so that only the conv under test contributes error
+    import torch
+    inp = torch.from_numpy(outs[0]).to(torch.bfloat16).to(torch.float32).numpy()
+    port_in = inp
+    L = port.layers[1]
+    ref = P.fwd_conv(port, L, port_in, [])
+    net.predict(x)
+    net.set_layer_output(0, inp.reshape(batch, -1))
+    net.run_layers(1, 2)
+    got = net.layer_output(1).reshape(ref.shape)
+    # weights are rounded to bf16 inside the engine: compare against the oracle run with the same rounding
+    L2 = P.Layer(L); L2.weights = torch.from_numpy(L.weights).to(torch.bfloat16).to(torch.float32).numpy()
+    ref_bf = P.fwd_conv(port, L2, port_in, [])
+    out_round = 2 ** -8 if act != "linear" else 1e-5        # bf16 output rounding (head convs store fp32)
+    assert np.abs(got - ref_bf).max() <= (out_round + 2e-4) * np.abs(ref_bf).max()
+    assert np.abs(got - ref).max() <= BF16_LAYER_TOL * np.abs(ref).max()
+    net.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# NMS kernel: bit-exact against the oracle on synthetic boxes, all sizes and edge cases
+# ---------------------------------------------------------------------------------------------------
+def random_dets(rng, n, classes, density=.5):
+    centre = rng.random((n, 2)).astype(np.float32)
+    size = (rng.random((n, 2)) * .3 + .02).astype(np.float32)
+    boxes = np.concatenate([centre, size], axis=1)
+    probs = (rng.random((n, classes)) * (rng.random((n, classes)) < density)).astype(np.float32)
+    return boxes, probs
+
+
+@pytest.mark.parametrize("n,classes", [(1, 1), (2, 3), (31, 80), (32, 1), (33, 20), (257, 5), (512, 80), (513, 3), (1500, 2), (4000, 1)])
+def test_nms_sort_bit_exact(dn, n, classes):
+    rng = np.random.default_rng(n * 131 + classes)
+    boxes, probs = random_dets(rng, n, classes)
+    got = dn.nms_sort_arrays(boxes, probs, .45)
+    want = P.do_nms_sort(boxes, np.ones(n, np.float32), probs, .45)
+    assert np.array_equal(got, want)
+    if R.available() and n <= 1500:
+        assert np.array_equal(got, R.ref_nms_sort_arrays(boxes, probs, .45))
+    # idempotence: a second pass over the survivors changes nothing
+    assert np.array_equal(dn.nms_sort_arrays(boxes, got, .45), got)
+
+
+def test_nms_edge_cases(dn):
+    # empty
+    assert dn.nms_sort_arrays(np.zeros((0, 4), np.float32), np.zeros((0, 3), np.float32), .45).shape == (0, 3)
+    # identical boxes: only the best per class survives
+    boxes = np.tile(np.array([[.5, .5, .2, .2]], np.float32), (40, 1))
+    probs = np.linspace(.1, .9, 40, dtype=np.float32).reshape(40, 1)
+    out = dn.nms_sort_arrays(boxes, probs, .45)
+    assert int((out > 0).sum()) == 1 and out[39, 0] == probs[39, 0]
+    # zero-area boxes: union 0 -> NaN IoU never suppresses (box.c:179-182)
+    z = np.zeros((5, 4), np.float32)
+    assert (dn.nms_sort_arrays(z, np.ones((5, 2), np.float32), .45) == 1).all()
+    # equal scores: ties resolved by input order, identical to the oracle
+    boxes, probs = random_dets(np.random.default_rng(9), 100, 2)
+    probs[probs > 0] = .5
+    assert np.array_equal(dn.nms_sort_arrays(boxes, probs, .3), P.do_nms_sort(boxes, np.ones(100, np.float32), probs, .3))
+    # threshold is strict '>' : two boxes with IoU exactly 1/3 at thresh 1/3 both survive
+    b = np.array([[.25, .5, .5, 1.], [.5, .5, .5, 1.]], np.float32)
+    iou = P.box_iou(b[0], b[1])
+    assert int((dn.nms_sort_arrays(b, np.array([[.9], [.8]], np.float32), float(iou)) > 0).sum()) == 2
+
+
+def test_do_nms_sort_and_obj_through_detection_structs(dn):
+    rng = np.random.default_rng(21)
+    n, classes = 300, 7
+    boxes, probs = random_dets(rng, n, classes)
+    obj = (rng.random(n) * (rng.random(n) > .2)).astype(np.float32)          # some objectness == 0 rows
+    def build():
+        arr = (dn.DETECTION * n)()
+        keep = []
+        for i in range(n):
+            p = (ctypes.c_float * classes)(*probs[i].tolist()); keep.append(p)
+            arr[i].bbox = dn.BOX(*[float(v) for v in boxes[i]]); arr[i].classes = classes
+            arr[i].prob = ctypes.cast(p, ctypes.POINTER(ctypes.c_float)); arr[i].objectness = float(obj[i]); arr[i].sort_class = i
+        return arr, keep
+    arr, keep = build()
+    addr = {ctypes.addressof(p): i for i, p in enumerate(keep)}
+    dn.do_nms_sort(arr, n, classes, .45)
+    got = np.zeros_like(probs)
+    live_seen = 0
+    for j in range(n):
+        row = addr[ctypes.cast(arr[j].prob, ctypes.c_void_p).value]
+        got[row] = np.ctypeslib.as_array(arr[j].prob, shape=(classes,))
+        if j < int((obj != 0).sum()):
+            assert arr[j].objectness != 0            # objectness-0 rows were partitioned to the tail (box.c:60-70)
+            live_seen += 1
+    assert np.array_equal(got, P.do_nms_sort(boxes, obj, probs, .45))
+    # do_nms_obj (python/darknet.py detect() uses it): class-agnostic, zeroes objectness and all probs
+    arr, keep = build()
+    addr = {ctypes.addressof(p): i for i, p in enumerate(keep)}
+    dn.do_nms_obj(arr, n, classes, .45)
+    want_obj, want_probs = P.do_nms_obj(boxes, obj, probs, .45)
+    for j in range(n):
+        row = addr[ctypes.cast(arr[j].prob, ctypes.c_void_p).value]
+        assert arr[j].objectness == want_obj[row]
+        assert np.array_equal(np.ctypeslib.as_array(arr[j].prob, shape=(classes,)), want_probs[row])
+
+
+# ---------------------------------------------------------------------------------------------------
+# batch semantics
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_batched_forward_is_per_image_independent(dn, prec, workdir):
+    p = dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16
+    net3, _, _ = open_net(dn, "yolov3-tiny", 3, 160, workdir, p)
+    net1, _, _ = open_net(dn, "yolov3-tiny", 1, 160, workdir, p)
+    x = synth.make_images(3, 3, 160, 160, 31)
+    net3.predict(x)
+    heads = [i for i, L in enumerate(net3.layers) if L["type_name"] == "YOLO"]
+    big = {i: net3.layer_output(i) for i in heads}
+    for b in range(3):
+        net1.predict(x[b:b + 1])
+        for i in heads:
+            assert np.array_equal(net1.layer_output(i)[0], big[i][b])
+        d1, n1 = net1.boxes(0, 160, 160, .3)
+        d3, n3 = net3.boxes(b, 160, 160, .3)
+        assert n1 == n3
+        a1, a3 = dn.dets_to_arrays(d1, n1, 80), dn.dets_to_arrays(d3, n3, 80)
+        for u, v in zip(a1, a3):
+            assert np.array_equal(u, v)
+        dn.free_detections(d1, n1); dn.free_detections(d3, n3)
+    # set_batch_network lowers the logical batch only (network.c:339-356)
+    dn.set_batch_network(net3.ptr, 1)
+    net3.batch = 1
+    net3.predict(x[2:3])
+    for i in heads:
+        assert np.array_equal(net3.layer_output(i)[0], big[i][2])
+
+
+def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
+    net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
+    x = synth.make_images(2, 3, 160, 160, 41)
+    net.predict(x)
+    num = ctypes.c_int(0)
+    dets = dn.get_network_boxes(net.ptr, 160, 160, .3, .5, None, 1, ctypes.byref(num))
+    d0, n0 = net.boxes(0, 160, 160, .3)
+    assert num.value == n0
+    for u, v in zip(dn.dets_to_arrays(dets, num.value, 80), dn.dets_to_arrays(d0, n0, 80)):
+        assert np.array_equal(u, v)
+    dn.free_detections(dets, num.value); dn.free_detections(d0, n0)
+    # make_network_boxes + fill_network_boxes (the pair python/darknet.py and demo.c use)
+    m = ctypes.c_int(0)
+    dn.make_network_boxes.restype = ctypes.POINTER(dn.DETECTION)
+    made = dn.make_network_boxes(net.ptr, .3, ctypes.byref(m))
+    assert m.value == n0
+    dn.free_detections(made, m.value)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size configuration: size-independent properties (BASELINE configs[2]: YOLOv3 416 batch 64 bf16)
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_yolov3_batch64_properties(dn, workdir):
+    net, cfg, wpath = open_net(dn, "yolov3", 64, 416, workdir, dn.PREC_BF16)
+    base = synth.make_images(4, 3, 416, 416, 1002)
+    x = np.concatenate([base] * 16)                       # every image appears 16 times across the batch
+    rec, counts = net.detect_batch(x, 416, 416, .5, .45)
+    assert len(rec) > 0 and (counts > 0).all()
+    # (a) replicas of the same image give identical detections wherever they sit in the batch
+    per = {}
+    for b in range(64):
+        r = rec[rec["image"] == b]
+        key = sorted(zip(r["box_id"].tolist(), r["cls"].tolist(), r["prob"].tolist()))
+        per.setdefault(b % 4, []).append(key)
+    for k, lst in per.items():
+        assert all(v == lst[0] for v in lst), k
+    assert (counts.reshape(16, 4) == counts[:4]).all()
+    # (b) image 0 against the oracle run on the same image: same candidates up to bf16 threshold noise
+    port = P.Net(synth.make_cfg("yolov3", workdir, batch=1, width=416, height=416), wpath)
+    outs = port.forward(base[:1])
+    pb, po, pp, pid = P.get_network_boxes(port, outs, 0, 416, 416, .5)
+    assert abs(int(counts[0]) - len(po)) <= max(3, len(po) // 20)
+    kept = P.do_nms_sort(pb, po, pp, .45)
+    want = set(zip(pid[np.nonzero(kept)[0]].tolist(), np.nonzero(kept)[1].tolist()))
+    r0 = rec[rec["image"] == 0]
+    got = set(zip(r0["box_id"].tolist(), r0["cls"].tolist()))
+    assert len(got & want) >= 0.85 * max(len(want), 1)
+    # (c) NMS idempotence on the engine's own survivors
+    boxes = np.stack([r0["bbox"]["x"], r0["bbox"]["y"], r0["bbox"]["w"], r0["bbox"]["h"]], axis=1).astype(np.float32)
+    ids = sorted(set(r0["box_id"].tolist()))
+    row = {v: i for i, v in enumerate(ids)}
+    bx = np.zeros((len(ids), 4), np.float32); pr = np.zeros((len(ids), 80), np.float32)
+    for j in range(len(r0)):
+        bx[row[int(r0["box_id"][j])]] = boxes[j]; pr[row[int(r0["box_id"][j])], int(r0["cls"][j])] = r0["prob"][j]
+    assert np.array_equal(dn.nms_sort_arrays(bx, pr, .45), pr)
+
+
+def test_python_wrapper_detect_on_ppm(dn, workdir, tmp_path):
+    """python/darknet.py detect(): load_image_color -> network_predict_image (letterbox) -> boxes -> do_nms_obj"""
+    net, cfg, wpath = open_net(dn, "yolov3-tiny", 1, 416, workdir, dn.PREC_FP32)
+    rng = np.random.default_rng(4)
+    img = (rng.random((120, 200, 3)) * 255).astype(np.uint8)
+    ppm = tmp_path / "x.ppm"
+    with open(ppm, "wb") as f:
+        f.write(b"P6\n200 120\n255\n" + img.tobytes())
+    names = tmp_path / "n.names"; names.write_text("\n".join(f"c{i}" for i in range(80)) + "\n")
+    data = tmp_path / "c.data"; data.write_text(f"classes=80\nnames={names}\n")
+    meta = dn.load_meta(str(data).encode())
+    assert meta.classes == 80 and meta.names[3] == b"c3"
+    res = dn.detect(net.ptr, meta, str(ppm).encode(), thresh=.3)
+    # oracle: same letterboxed input through the port
+    chw = img.astype(np.float32).transpose(2, 0, 1) / 255.
+    im = dn.make_image(200, 120, 3)
+    ctypes.memmove(im.data, chw.ctypes.data, chw.nbytes)
+    boxed = dn.letterbox_image(im, 416, 416)
+    lb = np.ctypeslib.as_array(boxed.data, shape=(1, 3, 416, 416)).copy()
+    assert abs(float(lb[0, 0, 0, 0]) - .5) < 1e-6                     # grey bars (image.c:972)
+    port = P.Net(cfg, wpath)
+    outs = port.forward(lb)
+    pb, po, pp, _ = P.get_network_boxes(port, outs, 0, 200, 120, .3, relative=0)
+    o2, p2 = P.do_nms_obj(pb, po, pp, .45)
+    assert len(res) == int((p2 > 0).sum())
+    dn.free_image(im); dn.free_image(boxed)

@@ -588,6 +588,35 @@ extern "C" void b200_run_layers(network *net, int start, int end)
     B200_CHECK(cudaStreamSynchronize(e->stream));
 }
 
+extern "C" void *b200_engine_stream(network *net) { return (void *)b200_engine_of(net)->stream; }
+
+// per-layer device time (ms, averaged over `iters` forwards) measured with CUDA events on the engine stream;
+// ms[net->n] receives the decode+NMS+collect tail when thresh >= 0.  Used by bench.py's roofline section.
+extern "C" void b200_profile_layers(network *net, int iters, float *ms)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_profile_layers");
+    int batch = logical_batch(e, net);
+    std::vector<cudaEvent_t> ev(net->n + 1);
+    for (auto &x : ev) B200_CHECK(cudaEventCreate(&x));
+    for (int i = 0; i < net->n; ++i) ms[i] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        if (!e->L[0].stem) { TView v = e->in_view; v.n = batch; launch_nchw_f32_to_view(e->d_input, v, e->stream); }
+        B200_CHECK(cudaEventRecord(ev[0], e->stream));
+        for (int i = 0; i < net->n; ++i) {
+            run_layer(e, net, i, batch);
+            B200_CHECK(cudaEventRecord(ev[i + 1], e->stream));
+        }
+        B200_CHECK(cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < net->n; ++i) {
+            float t = 0.f;
+            B200_CHECK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            ms[i] += t / iters;
+        }
+    }
+    for (auto &x : ev) cudaEventDestroy(x);
+}
+
 extern "C" const char *b200_layer_kernel(network *net, int i)
 {
     b200_engine *e = b200_engine_of(net);

@@ -93,6 +93,8 @@ lib.b200_engine_of.argtypes = [c_void_p]; lib.b200_engine_of.restype = c_void_p
 lib.b200_engine_forward_resident.argtypes = [c_void_p, c_void_p]
 lib.b200_engine_input_device.argtypes = [c_void_p]; lib.b200_engine_input_device.restype = c_void_p
 lib.b200_engine_sync.argtypes = [c_void_p]
+lib.b200_engine_stream.argtypes = [c_void_p]; lib.b200_engine_stream.restype = c_void_p
+lib.b200_profile_layers.argtypes = [c_void_p, c_int, POINTER(c_float)]
 lib.get_network_boxes_batch.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_float, POINTER(c_int), c_int, POINTER(c_int)]
 lib.get_network_boxes_batch.restype = POINTER(DETECTION)
 lib.b200_detect_batch.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(B200_DET), c_int, POINTER(c_int)]
@@ -162,6 +164,25 @@ class Network:
 
     def run_layers(self, start, end):
         lib.b200_run_layers(self.ptr, start, end)
+
+    def profile_layers(self, iters=3):
+        ms = np.zeros(self.n, dtype=np.float32)
+        lib.b200_profile_layers(self.ptr, iters, _fptr(ms))
+        return ms
+
+    def stream_ptr(self):
+        return lib.b200_engine_stream(self.ptr)
+
+    def input_device_ptr(self):
+        return lib.b200_engine_input_device(lib.b200_engine_of(self.ptr))
+
+    def weights_arena(self):
+        n = c_size_t(0)
+        p = lib.b200_weights_arena(self.ptr, byref(n))
+        return p, n.value
+
+    def set_head_sync(self, on):
+        lib.b200_set_head_sync(self.ptr, int(on))
 
     def boxes(self, b, w, h, thresh, relative=1):
         """get_network_boxes_batch -> (dets pointer, count); caller frees with free_detections"""
