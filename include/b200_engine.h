@@ -58,6 +58,8 @@ void b200_set_layer_output(network *net, int i, const float *in);
 void b200_run_layers(network *net, int start, int end);
 /* name of the kernel family that executes layer i ("conv_tc", "conv_simt", "conv_stem", "maxpool", ...) */
 const char *b200_layer_kernel(network *net, int i);
+/* human-readable tiling plan of a tcgen05 convolution layer ("" for other layers) */
+const char *b200_layer_plan(network *net, int i);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
 

@@ -59,8 +59,99 @@ conv_stem_kernel(const float *__restrict__ in, int N, int H, int W, int C, T *__
     }
 }
 
+// Specialised first-layer kernel (SIZE x SIZE taps, CIN input channels, 32 filters per thread):
+//  * one thread = one output pixel x 32 filters; consecutive threads = consecutive pixels, so the fp32 NCHW
+//    image reads are coalesced per (channel, tap) and served from L1 (each input value is reused SIZE^2 times),
+//  * the [K][32] weight slab lives in shared memory and is read as broadcast float4 (one wavefront per 4 FMAs),
+//  * all loops are compile-time unrolled, borders are handled once while loading the patch row into registers,
+//  * the 32 results leave as 16-byte vector stores (64 contiguous bytes per pixel in bf16 NHWC).
+template <typename T, bool EXACT, int SIZE, int CIN>
+__global__ void __launch_bounds__(256)
+conv_stem_fast_kernel(const float *__restrict__ in, int N, int H, int W, T *__restrict__ out, int OH, int OW, int ldo,
+                      int Cout, int stride, int pad, const T *__restrict__ wt, const float *__restrict__ scale,
+                      const float *__restrict__ shift, int act)
+{
+    constexpr int K = SIZE * SIZE * CIN;
+    __shared__ __align__(16) float ws[K * 32];
+    __shared__ float s_scale[32], s_shift[32];
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+        int k = i / 32, j = i % 32;
+        ws[i] = (c0 + j < Cout) ? Elem<T>::load(wt + (size_t)(c0 + j) * K + k) : 0.f;
+    }
+    if (threadIdx.x < 32) {
+        s_scale[threadIdx.x] = c0 + threadIdx.x < Cout ? scale[c0 + threadIdx.x] : 0.f;
+        s_shift[threadIdx.x] = c0 + threadIdx.x < Cout ? shift[c0 + threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    const long long total = (long long)N * OH * OW;
+    const size_t plane = (size_t)H * W;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+        const float *img = in + (size_t)n * CIN * plane;
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < SIZE; ++ky) {
+            const int y = oy * stride + ky - pad;
+            const bool yok = y >= 0 && y < H;
+            float v[SIZE * CIN];
+#pragma unroll
+            for (int kx = 0; kx < SIZE; ++kx) {
+                const int x = ox * stride + kx - pad;
+                const bool ok = yok && x >= 0 && x < W;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) v[kx * CIN + c] = ok ? __ldg(img + c * plane + (size_t)y * W + x) : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < SIZE * CIN; ++t) {
+                const float4 *wrow = reinterpret_cast<const float4 *>(ws + (ky * SIZE * CIN + t) * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 w4 = wrow[q];
+                    acc[4 * q + 0] = fmaf(v[t], w4.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(v[t], w4.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(v[t], w4.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(v[t], w4.w, acc[4 * q + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = apply_act<EXACT>(fmaf(acc[j], s_scale[j], s_shift[j]), act);
+        T *dst = out + (size_t)pix * ldo + c0;
+        constexpr int V = Elem<T>::VEC;
+#pragma unroll
+        for (int j = 0; j < 32; j += V)
+            if (c0 + j < Cout) store_vec<T>(dst + j, acc + j);
+    }
+}
+
+template <typename T, bool EXACT>
+static bool try_stem_fast(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
+{
+    if (c != 3 || (p.size != 3 && p.size != 7)) return false;
+    if (out.c % Elem<T>::VEC != 0 || out.ld % Elem<T>::VEC != 0 || ((uintptr_t)out.p & 15)) return false;
+    long long pixels = (long long)n * out.h * out.w;
+    int gx = (int)((pixels + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid(gx, div_up(out.c, 32));
+    if (p.size == 3)
+        conv_stem_fast_kernel<T, EXACT, 3, 3><<<grid, 256, 0, s>>>(in_nchw, n, h, w, (T *)out.p, out.h, out.w, out.ld, out.c, p.stride, p.pad,
+                                                                     (const T *)p.w, p.scale, p.shift, p.act);
+    else
+        conv_stem_fast_kernel<T, EXACT, 7, 3><<<grid, 256, 0, s>>>(in_nchw, n, h, w, (T *)out.p, out.h, out.w, out.ld, out.c, p.stride, p.pad,
+                                                                     (const T *)p.w, p.scale, p.shift, p.act);
+    return true;
+}
+
 void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
 {
+    if (out.dtype == DT_F32 ? try_stem_fast<float, true>(in_nchw, n, h, w, c, out, p, s)
+                            : try_stem_fast<bf16, false>(in_nchw, n, h, w, c, out, p, s)) {
+        B200_LAUNCHED();
+        return;
+    }
     int K = p.size * p.size * c;
     // ws is read 32 filters at a time: pad the allocation so the tail chunk stays in bounds
     size_t smem = ((size_t)K * out.c + 32) * sizeof(float);

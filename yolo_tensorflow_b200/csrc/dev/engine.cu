@@ -588,6 +588,12 @@ extern "C" void b200_run_layers(network *net, int start, int end)
     B200_CHECK(cudaStreamSynchronize(e->stream));
 }
 
+extern "C" const char *b200_layer_plan(network *net, int i)
+{
+    b200_engine *e = b200_engine_of(net);
+    return e->L[i].tc ? conv_tc_plan_desc(e->L[i].tc) : "";
+}
+
 extern "C" void *b200_engine_stream(network *net) { return (void *)b200_engine_of(net)->stream; }
 
 // per-layer device time (ms, averaged over `iters` forwards) measured with CUDA events on the engine stream;

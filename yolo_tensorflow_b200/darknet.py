@@ -85,6 +85,7 @@ lib.b200_set_layer_output.argtypes = [c_void_p, c_int, POINTER(c_float)]
 lib.b200_run_layers.argtypes = [c_void_p, c_int, c_int]
 lib.b200_layer_kernel.argtypes = [c_void_p, c_int]; lib.b200_layer_kernel.restype = c_char_p
 lib.b200_launch_count.restype = c_ulonglong
+lib.b200_layer_plan.argtypes = [c_void_p, c_int]; lib.b200_layer_plan.restype = c_char_p
 lib.b200_network_layers.argtypes = [c_void_p]; lib.b200_network_layers.restype = c_int
 lib.b200_layer_info.argtypes = [c_void_p, c_int, POINTER(c_int)]; lib.b200_layer_info.restype = c_int
 lib.b200_layer_output_host.argtypes = [c_void_p, c_int]; lib.b200_layer_output_host.restype = POINTER(c_float)
