@@ -21,6 +21,12 @@ extern "C" {
 void b200_set_default_precision(int prec);     /* applies to networks parsed afterwards (env B200_PRECISION=fp32|bf16 too) */
 int  b200_get_precision(const network *net);
 
+/* Layer fusion (default on; env B200_FUSE=0 turns it off): a [convolutional] -> [shortcut] pair runs as ONE kernel, the
+ * residual add riding in the convolution epilogue; the convolution's own output is then never materialised and
+ * b200_fetch_layer_output() on it aborts.  Applies to networks parsed afterwards; -1 restores the default. */
+void b200_set_default_fusion(int on);
+int  b200_get_default_fusion(void);
+
 /* conv kernel selection for the bf16 path: 0 = auto (tcgen05 wherever the shape allows), 1 = force CUDA-core kernel */
 void b200_set_conv_backend(network *net, int backend);
 

@@ -19,7 +19,7 @@ if not os.path.exists(wpath):
 port = P.Net(cfg, wpath)
 x = synth.make_images(batch, 3, port.h, port.w, 1000)
 t = time.time(); outs = port.forward(x); print("oracle forward %.2fs" % (time.time() - t))
-net = dn.Network(cfg, wpath, precision=dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16)
+net = dn.Network(cfg, wpath, precision=dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16, fuse=False)
 t = time.time(); net.predict(x); print("engine first predict %.3fs" % (time.time() - t))
 t = time.time(); net.predict(x); print("engine second predict %.3fs" % (time.time() - t))
 SUMMARY = os.environ.get("SUMMARY", "0") == "1"

@@ -35,11 +35,11 @@ def dn():
     return darknet
 
 
-def open_net(dn, model, batch, size, workdir, prec, damp=True):
+def open_net(dn, model, batch, size, workdir, prec, damp=True, fuse=None):
     cfg, wpath = model_files(model, batch, size, workdir, damp)
     fd = os.dup(2); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 2)
     try:
-        net = dn.Network(cfg, wpath, precision=prec)
+        net = dn.Network(cfg, wpath, precision=prec, fuse=fuse)
     finally:
         os.dup2(fd, 2); os.close(fd); os.close(devnull)
     return net, cfg, wpath
@@ -120,7 +120,8 @@ def layer_sources(L, i):
 @pytest.mark.parametrize("model,size,batch", [("yolov3-tiny", 416, 1), ("yolov3", 160, 3), ("yolov2", 160, 2), ("yolov1", 448, 2)])
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_teacher_forced_layers(dn, model, size, batch, prec, workdir):
-    net, cfg, wpath = open_net(dn, model, batch, size, workdir, dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16)
+    # fuse=False: every layer's output is materialised so each one can be teacher-forced and inspected
+    net, cfg, wpath = open_net(dn, model, batch, size, workdir, dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16, fuse=False)
     port = P.Net(cfg, wpath)
     x = synth.make_images(batch, 3, size, size, 77)
     outs = port.forward(x)
@@ -167,6 +168,27 @@ def test_bf16_end_to_end_heads(dn, model, size, batch, workdir):
             assert abs(n - len(po)) <= max(3, len(po) // 20)
         else:
             assert n == len(po)
+
+
+def test_shortcut_fusion_matches_unfused(dn, workdir):
+    """conv+shortcut fused into one tcgen05 kernel vs the two-kernel plan: every shortcut output within bf16 rounding"""
+    fused, cfg, wpath = open_net(dn, "yolov3", 2, 160, workdir, dn.PREC_BF16, fuse=True)
+    plain, _, _ = open_net(dn, "yolov3", 2, 160, workdir, dn.PREC_BF16, fuse=False)
+    x = synth.make_images(2, 3, 160, 160, 5)
+    fused.predict(x); plain.predict(x)
+    n_fused = sum(1 for i in range(fused.n) if fused.kernel(i) == "conv_tc+shortcut")
+    assert n_fused == 23 and all(plain.kernel(i) != "fused" for i in range(plain.n))
+    port = P.Net(cfg, wpath)
+    outs = port.forward(x)
+    for i, L in enumerate(port.layers):
+        if L.type == "shortcut":
+            a, b, r = fused.layer_output(i), plain.layer_output(i), outs[i].reshape(2, -1)
+            scale = np.abs(r).max()
+            assert np.abs(a - b).max() <= 2e-2 * scale                 # both are bf16 pipelines; they differ by rounding order only
+            assert np.abs(a - r).max() <= BF16_E2E_TOL * scale
+    for i, L in enumerate(port.layers):
+        if L.type == "yolo":
+            assert np.abs(fused.layer_output(i) - outs[i].reshape(2, -1)).max() <= BF16_E2E_TOL * np.abs(outs[i]).max()
 
 
 # ---------------------------------------------------------------------------------------------------

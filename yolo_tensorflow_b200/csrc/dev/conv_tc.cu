@@ -87,6 +87,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -107,9 +117,13 @@ struct ConvTcArgs {
     int b_stage_bytes;       // 1024-aligned
     int tmem_cols;
     int act;
+    int resident_b;          // 1: the whole [block_n x K] weight slab stays in shared memory for the CTA's lifetime
     long long npix;
     const float *scale, *shift;
     void *out;
+    const bf16 *res;         // optional residual (shortcut fused into the epilogue): out = alpha*act(conv) + beta*res
+    int ldr;
+    float res_alpha, res_beta;
 };
 
 static constexpr int kTcThreads = 192;
@@ -122,6 +136,43 @@ template <int BLOCK_K> __device__ __forceinline__ uint64_t make_desc(uint32_t sm
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
+// epilogue math for NC accumulator columns of one pixel row: folded-BN scale/shift, activation, optional
+// residual, cast, 16-byte stores.  `sc`/`sh` point at the tile's per-filter constants in shared memory.
+template <typename OutT, bool LEAKY, int NC>
+__device__ __forceinline__ void emit_columns(const uint32_t *r, const float *sc, const float *sh, OutT *dst, const bf16 *res,
+                                             float alpha, float beta, int cols_left)
+{
+    constexpr int VEC = 16 / (int)sizeof(OutT);
+#pragma unroll
+    for (int j = 0; j < NC; j += VEC) {
+        if (j < cols_left) {
+            float v[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; q += 4) {
+                const float4 s4 = *reinterpret_cast<const float4 *>(sc + j + q);
+                const float4 h4 = *reinterpret_cast<const float4 *>(sh + j + q);
+                v[q + 0] = fmaf(__uint_as_float(r[j + q + 0]), s4.x, h4.x);
+                v[q + 1] = fmaf(__uint_as_float(r[j + q + 1]), s4.y, h4.y);
+                v[q + 2] = fmaf(__uint_as_float(r[j + q + 2]), s4.z, h4.z);
+                v[q + 3] = fmaf(__uint_as_float(r[j + q + 3]), s4.w, h4.w);
+            }
+            if (LEAKY) {
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) v[q] = v[q] > 0.f ? v[q] : 0.1f * v[q];
+            }
+            if constexpr (sizeof(OutT) == 2) {                 // a residual is only ever fused into a bf16 output
+                if (res) {
+                    float a[VEC];
+                    load_vec<bf16>(res + j, a);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) v[q] = fmaf(alpha, v[q], beta * a[q]);
+                }
+            }
+            store_vec<OutT>(dst + j, v);
+        }
+    }
+}
+
 template <int BLOCK_K, typename OutT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
@@ -132,12 +183,14 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
     const int stages = args.stages;
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)stages * A_BYTES;
-    uint8_t *aux = sB + (size_t)stages * args.b_stage_bytes;
+    const int b_slots = args.resident_b ? args.num_kblocks : stages;
+    uint8_t *aux = sB + (size_t)b_slots * args.b_stage_bytes;
     uint64_t *full = (uint64_t *)aux;                 // [stages]
     uint64_t *empty = full + 8;                       // [stages]
     uint64_t *tfull = empty + 8;                      // [2]
     uint64_t *tempty = tfull + 2;                     // [2]
-    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    uint64_t *wfull = tempty + 2;                     // resident weights landed
+    uint32_t *tmem_slot = (uint32_t *)(wfull + 1);
     float *s_scale = (float *)(aux + 256);            // [2][256]
     float *s_shift = s_scale + 512;                   // [2][256]
 
@@ -147,6 +200,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -163,7 +217,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(args.a_rows * BLOCK_K * 2 + args.block_n * BLOCK_K * 2);
+            const uint32_t b_bytes = (uint32_t)(args.block_n * BLOCK_K * 2);
+            const uint32_t tx_bytes = (uint32_t)(args.a_rows * BLOCK_K * 2) + (args.resident_b ? 0u : b_bytes);
+            if (args.resident_b && (int)blockIdx.x < num_tiles) {          // n_tiles == 1: one slab serves every tile
+                mbar_expect_tx(wfull, b_bytes * (uint32_t)args.num_kblocks);
+                for (int kb = 0; kb < args.num_kblocks; ++kb)
+                    tma_load_2d(&maps.b, sB + (size_t)kb * args.b_stage_bytes, wfull, kb * BLOCK_K, 0);
+            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % args.n_tiles, m_tile = tile / args.n_tiles;
                 int ox0 = 0, oy0 = 0, n0 = 0;
@@ -189,7 +249,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
                             tma_load_4d(&maps.a[py * 2 + px], dstA, &full[stage], cb * BLOCK_K, ox0 + xoff, oy0 + yoff, n0);
                         }
                     }
-                    tma_load_2d(&maps.b, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n);
+                    if (!args.resident_b)
+                        tma_load_2d(&maps.b, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -200,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.block_n >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            if (args.resident_b && (int)blockIdx.x < num_tiles) mbar_wait(wfull, 0);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -208,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint64_t adesc = make_desc<BLOCK_K>(smem_u32(sA + (size_t)stage * A_BYTES));
-                    const uint64_t bdesc = make_desc<BLOCK_K>(smem_u32(sB + (size_t)stage * args.b_stage_bytes));
+                    const uint64_t bdesc = make_desc<BLOCK_K>(smem_u32(sB + (size_t)(args.resident_b ? kb : stage) * args.b_stage_bytes));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k)
                         tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -225,50 +287,63 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
         const int row = quarter * 32 + lane;
         const int ep_tid = threadIdx.x - 64;
         int acc = 0; uint32_t acc_phase = 0;
-        constexpr int VEC = 16 / (int)sizeof(OutT);           // elements per 16-byte store
+        // row -> position inside the pixel tile is the same for every tile
+        int rx = 0, ry = 0, rn = 0;
+        if (args.mode == 1) { rx = row % args.TW; ry = (row / args.TW) % args.TH; rn = row / (args.TW * args.TH); }
+        const bool hoist = args.n_tiles == 1;                  // one filter tile: its constants are staged once
+        if (hoist) {
+            for (int c = ep_tid; c < args.block_n; c += 128) {
+                s_scale[c] = c < args.cout_pad ? args.scale[c] : 0.f;
+                s_shift[c] = c < args.cout_pad ? args.shift[c] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const bool leaky = args.act == ACT_LEAKY;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n_tile = tile % args.n_tiles, m_tile = tile / args.n_tiles;
             const int col0 = n_tile * args.block_n;
-            for (int c = ep_tid; c < args.block_n; c += 128) {
-                int co = col0 + c;
-                s_scale[acc * 256 + c] = co < args.cout_pad ? args.scale[co] : 0.f;
-                s_shift[acc * 256 + c] = co < args.cout_pad ? args.shift[co] : 0.f;
+            if (!hoist) {
+                for (int c = ep_tid; c < args.block_n; c += 128) {
+                    int co = col0 + c;
+                    s_scale[acc * 256 + c] = co < args.cout_pad ? args.scale[co] : 0.f;
+                    s_shift[acc * 256 + c] = co < args.cout_pad ? args.shift[co] : 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // which output pixel does this TMEM lane hold?
             long long pix = -1;
             if (args.mode == 0) {
                 long long p = (long long)m_tile * 128 + row;
                 if (p < args.npix) pix = p;
             } else {
                 int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
-                int rx = row % args.TW, ry = (row / args.TW) % args.TH, rn = row / (args.TW * args.TH);
                 int ox = tx * args.TW + rx, oy = ty * args.TH + ry, n = tn * args.TN + rn;
                 if (row < args.a_rows && ox < args.OW && oy < args.OH && n < args.batch) pix = ((long long)n * args.OH + oy) * args.OW + ox;
             }
             OutT *orow = pix >= 0 ? (OutT *)args.out + pix * args.ldo + col0 : nullptr;
+            const bf16 *rrow = (args.res && pix >= 0) ? args.res + pix * args.ldr + col0 : nullptr;
+            const int cols_valid = args.cout_pad - col0;        // columns of this tile that exist in the output row
 
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
-            const float *sc = s_scale + acc * 256, *sh = s_shift + acc * 256;
-            for (int c0 = 0; c0 < args.block_n; c0 += 16) {
+            const float *sc = s_scale + (hoist ? 0 : acc * 256), *sh = s_shift + (hoist ? 0 : acc * 256);
+            int c0 = 0;
+            for (; c0 + 32 <= args.block_n; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+                if (orow) {
+                    if (leaky) emit_columns<OutT, true, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                    else emit_columns<OutT, false, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                }
+            }
+            if (c0 < args.block_n) {                            // 16-column tail (block_n is a multiple of 16)
                 uint32_t r[16];
                 tmem_ld16(taddr + c0, r);
                 tmem_ld_wait();
                 if (orow) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float y = fmaf(__uint_as_float(r[j]), sc[c0 + j], sh[c0 + j]);
-                        if (args.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
-                        else if (args.act == ACT_RELU) y = y > 0.f ? y : 0.f;
-                        else if (args.act == ACT_LOGISTIC) y = 1.f / (1.f + __expf(-y));
-                        v[j] = y;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; j += VEC)
-                        if (col0 + c0 + j < args.cout_pad) store_vec<OutT>(orow + c0 + j, v + j);
+                    if (leaky) emit_columns<OutT, true, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                    else emit_columns<OutT, false, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
                 }
             }
             tc_fence_before();
@@ -359,12 +434,21 @@ void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
 }
 
 void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
+
+// shape test shared with the planner (engine.cu decides about shortcut fusion before buffers exist)
+bool conv_tc_shape_supported(int cin, int stride, int act)
+{
+    if (getenv("B200_DISABLE_TC")) return false;
+    return cin % 16 == 0 && (stride == 1 || stride == 2) && (act == ACT_LEAKY || act == ACT_LINEAR);
+}
 const char *conv_tc_plan_desc(ConvTcPlan *p) { return p->desc.c_str(); }
 
-ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual)
+ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual, float res_alpha, float res_beta)
 {
-    if (residual) return nullptr;                               // (residual fusion: later round)
     if (in.dtype != DT_BF16) return nullptr;
+    if (residual && (residual->dtype != DT_BF16 || out.dtype != DT_BF16 || residual->ld % 8 != 0 || ((uintptr_t)residual->p & 15) ||
+                     residual->c != out.c || residual->h != out.h || residual->w != out.w)) return nullptr;
+    if (cp.act != ACT_LEAKY && cp.act != ACT_LINEAR) return nullptr;
     if (getenv("B200_DISABLE_TC")) return nullptr;
     const int C = in.c;
     int block_k = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 0));
@@ -385,6 +469,9 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     a.size = cp.size; a.stride = cp.stride; a.pad = cp.pad; a.cin_blocks = C / block_k;
     a.num_kblocks = cp.size * cp.size * a.cin_blocks;
     a.act = cp.act; a.scale = cp.scale; a.shift = cp.shift; a.out = out.p;
+    a.res = residual ? (const bf16 *)residual->p : nullptr;
+    a.ldr = residual ? residual->ld : 0;
+    a.res_alpha = res_alpha; a.res_beta = res_beta;
     a.npix = (long long)in.n * out.h * out.w;
     a.block_n = cp.cout_pad < 256 ? cp.cout_pad : 256;
     a.n_tiles = (cp.cout_pad + a.block_n - 1) / a.block_n;
@@ -448,20 +535,32 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     const int a_bytes = 128 * block_k * 2;
     a.b_stage_bytes = (a.block_n * block_k * 2 + 1023) / 1024 * 1024;
     const int aux_bytes = 256 + 2 * 512 * 4;
-    int stages = (227 * 1024 - 1024 - aux_bytes) / (a_bytes + a.b_stage_bytes);
-    if (stages > 8) stages = 8;
-    if (stages > a.num_kblocks && a.num_kblocks >= 2) stages = a.num_kblocks;
-    if (stages < 2) { delete p; return nullptr; }
+    const int budget = 227 * 1024 - 1024 - aux_bytes;
+    // weight-stationary variant: when one filter tile covers all filters and its whole [block_n x K] slab fits next
+    // to >= 4 activation stages, load it once per CTA and stream only activations (halves the TMA rows per k-block)
+    const long long slab = (long long)a.num_kblocks * a.b_stage_bytes;
+    a.resident_b = (a.n_tiles == 1 && slab + 4LL * a_bytes <= budget && !getenv("B200_NO_RESIDENT_B")) ? 1 : 0;
+    int stages;
+    if (a.resident_b) {
+        stages = (int)((budget - slab) / a_bytes);
+        if (stages > 8) stages = 8;
+        p->smem_bytes = (size_t)stages * a_bytes + (size_t)slab + aux_bytes + 1024;
+    } else {
+        stages = budget / (a_bytes + a.b_stage_bytes);
+        if (stages > 8) stages = 8;
+        if (stages < 2) { delete p; return nullptr; }
+        p->smem_bytes = (size_t)stages * (a_bytes + a.b_stage_bytes) + aux_bytes + 1024;
+    }
     a.stages = stages;
-    p->smem_bytes = (size_t)stages * (a_bytes + a.b_stage_bytes) + aux_bytes + 1024;
     int cols = 2 * a.block_n;
     a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     int tiles = a.m_tiles * a.n_tiles;
     p->grid = tiles < 148 ? tiles : 148;
     p->flops = 2.0 * (double)a.npix * out.c * K;
     char buf[256];
-    snprintf(buf, sizeof buf, "conv_tc mode%d k%d n%d tile %dx%dx%d rows %d m_tiles %d n_tiles %d stages %d smem %zu grid %d",
-             a.mode, block_k, a.block_n, a.TW, a.TH, a.TN, a.a_rows, a.m_tiles, a.n_tiles, stages, p->smem_bytes, p->grid);
+    snprintf(buf, sizeof buf, "conv_tc mode%d k%d n%d tile %dx%dx%d rows %d m_tiles %d n_tiles %d stages %d smem %zu grid %d%s%s",
+             a.mode, block_k, a.block_n, a.TW, a.TH, a.TN, a.a_rows, a.m_tiles, a.n_tiles, stages, p->smem_bytes, p->grid,
+             a.resident_b ? " residentB" : "", a.res ? " +residual" : "");
     p->desc = buf;
     return p;
 }

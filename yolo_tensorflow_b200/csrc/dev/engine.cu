@@ -28,6 +28,8 @@ struct DevLayer {
     int cout_pad;
     ConvTcPlan *tc;
     bool stem;
+    int fused_into;            // conv whose epilogue also performs shortcut layer `fused_into` (its own output is not materialised)
+    bool fused_away;           // shortcut executed inside the previous conv's epilogue
     std::string kernel;
 };
 
@@ -35,7 +37,7 @@ struct b200_engine {
     int precision, act_dtype;
     int n, cap;                // layers, batch capacity
     int device;
-    int conv_backend, head_sync;
+    int conv_backend, head_sync, fusion;
     cudaStream_t stream;
     std::vector<DevLayer> L;
     float *d_input;            // fp32 NCHW network input [cap][inputs]
@@ -141,6 +143,22 @@ static void build_engine_device_state(b200_engine *e, network *net)
     e->d_input = (float *)dev_alloc((size_t)e->cap * net->inputs * sizeof(float));
     size_t max_floats = (size_t)e->cap * net->inputs;
 
+    // ---- shortcut fusion: conv -> shortcut pairs whose add can ride in the conv epilogue --------------
+    for (int i = 1; i + 1 < net->n; ++i) {
+        const layer &c = net->layers[i], &sc = net->layers[i + 1];
+        if (!e->fusion || e->precision != B200_PREC_BF16) break;
+        if (c.type != CONVOLUTIONAL || sc.type != SHORTCUT) continue;
+        if (cons[i].size() != 1 || cons[i][0] != i + 1 || sc.index == i) continue;
+        if (sc.activation != LINEAR || sc.w != sc.out_w || sc.h != sc.out_h || sc.c != sc.out_c) continue;
+        if (c.activation != LEAKY && c.activation != LINEAR) continue;
+        if (c.size == 1 && (c.stride != 1 || c.pad != 0)) continue;
+        if (!conv_tc_shape_supported(c.c, c.stride, act_id(c.activation)) || c.out_c % 16 != 0) continue;
+        LAYER_TYPE src = net->layers[sc.index].type;
+        if (src == YOLO || src == REGION || src == DETECTION || src == CONNECTED) continue;
+        e->L[i].fused_into = i + 1;
+        e->L[i + 1].fused_away = true;
+    }
+
     // ---- output views ------------------------------------------------------------------------------
     for (int i = 0; i < net->n; ++i) {
         const layer &l = net->layers[i];
@@ -156,6 +174,11 @@ static void build_engine_device_state(b200_engine *e, network *net)
         case CONVOLUTIONAL: {
             // row pitch padded to 16 filters (255 -> 256): keeps every pixel row 16-byte aligned for vector stores
             int ld = (int)align_up(l.out_c, 16);
+            if (d.fused_into >= 0) {            // written straight into the shortcut's buffer, never materialised
+                d.out = TView{nullptr, e->cap, l.out_h, l.out_w, l.out_c, ld, dtype};
+                d.owns_out = false;
+                break;
+            }
             d.out = TView{dev_alloc((size_t)e->cap * l.out_h * l.out_w * ld * dt_size(dtype)), e->cap, l.out_h, l.out_w, l.out_c, ld, dtype};
             d.owns_out = true;
             break;
@@ -245,14 +268,21 @@ static void build_engine_device_state(b200_engine *e, network *net)
             d.kernel = d.stem ? "conv_stem" : "conv_simt";
             if (!d.stem && e->precision == B200_PREC_BF16) {
                 ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
-                d.tc = conv_tc_plan_create(e->L[i - 1].out, d.out, p, nullptr);
-                if (d.tc) d.kernel = "conv_tc";
+                if (d.fused_into >= 0) {
+                    const layer &sc = net->layers[d.fused_into];
+                    d.tc = conv_tc_plan_create(e->L[i - 1].out, e->L[d.fused_into].out, p, &e->L[sc.index].out, sc.alpha, sc.beta);
+                    if (!d.tc) { fprintf(stderr, "b200-darknet: internal error: fused conv %d has no tcgen05 plan\n", i); abort(); }
+                    d.kernel = "conv_tc+shortcut";
+                } else {
+                    d.tc = conv_tc_plan_create(e->L[i - 1].out, d.out, p, nullptr, 1.f, 1.f);
+                    if (d.tc) d.kernel = "conv_tc";
+                }
             }
             break;
         }
         case MAXPOOL: d.kernel = "maxpool"; break;
         case UPSAMPLE: d.kernel = "upsample"; break;
-        case SHORTCUT: d.kernel = "shortcut"; break;
+        case SHORTCUT: d.kernel = d.fused_away ? "fused" : "shortcut"; break;
         case REORG: d.kernel = "reorg"; break;
         case ROUTE: d.kernel = l.n == 1 ? "alias" : "route_copy"; break;
         case DROPOUT: d.kernel = "alias"; break;
@@ -304,7 +334,8 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.owns_out = false; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.owns_out = false; d.fused_into = -1; d.fused_away = false; }
+    e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
     memset(&e->cand, 0, sizeof e->cand); e->cand_slots = 0;
@@ -447,7 +478,9 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
     }
     case MAXPOOL: launch_maxpool(in, out, l.size, l.stride, l.pad, s); break;
     case UPSAMPLE: launch_upsample(in, out, l.stride, l.scale, s); break;
-    case SHORTCUT: launch_shortcut(in, view_of(e->L[l.index], batch), out, l.alpha, l.beta, act_id(l.activation), s); break;
+    case SHORTCUT:
+        if (!d.fused_away || e->conv_backend != 0) launch_shortcut(in, view_of(e->L[l.index], batch), out, l.alpha, l.beta, act_id(l.activation), s);
+        break;
     case REORG:
         if (l.reverse) { fprintf(stderr, "b200-darknet: reorg reverse=1 is outside the YOLO inference path\n"); abort(); }
         launch_reorg(in, out, l.stride, s);
@@ -538,16 +571,35 @@ extern "C" float *b200_engine_input_device(b200_engine *e) { return e->d_input; 
 extern "C" void b200_engine_sync(b200_engine *e) { need_device(e, "sync"); B200_CHECK(cudaStreamSynchronize(e->stream)); }
 
 extern "C" int b200_get_precision(const network *net) { return b200_engine_of(net)->precision; }
-extern "C" void b200_set_conv_backend(network *net, int backend) { b200_engine_of(net)->conv_backend = backend; }
+extern "C" void b200_set_conv_backend(network *net, int backend)
+{
+    b200_engine *e = b200_engine_of(net);
+    for (auto &d : e->L)
+        if (backend != 0 && d.fused_into >= 0) {
+            fprintf(stderr, "b200-darknet: the CUDA-core conv backend needs an unfused plan (parse with B200_FUSE=0)\n");
+            abort();
+        }
+    e->conv_backend = backend;
+}
 extern "C" void b200_set_head_sync(network *net, int on) { b200_engine_of(net)->head_sync = on; }
 
 // ----------------------------------------------------------------------------------------------------
 // inspection hooks
 // ----------------------------------------------------------------------------------------------------
+static void need_materialised(const b200_engine *e, int i)
+{
+    if (e->L[i].fused_into >= 0) {
+        fprintf(stderr, "b200-darknet: layer %d's output is not materialised: its shortcut (layer %d) is fused into the conv epilogue. "
+                        "Parse with B200_FUSE=0 (or b200_set_default_fusion(0)) to inspect it.\n", i, e->L[i].fused_into);
+        abort();
+    }
+}
+
 extern "C" void b200_fetch_layer_output(network *net, int i, float *out)
 {
     b200_engine *e = b200_engine_of(net);
     need_device(e, "b200_fetch_layer_output");
+    need_materialised(e, i);
     int batch = logical_batch(e, net);
     size_t bytes = (size_t)batch * net->layers[i].outputs * sizeof(float);
     if (e->L[i].head_out) {
@@ -563,6 +615,7 @@ extern "C" void b200_set_layer_output(network *net, int i, const float *in)
 {
     b200_engine *e = b200_engine_of(net);
     need_device(e, "b200_set_layer_output");
+    need_materialised(e, i);
     int batch = logical_batch(e, net);
     size_t bytes = (size_t)batch * net->layers[i].outputs * sizeof(float);
     if (e->L[i].head_out) {

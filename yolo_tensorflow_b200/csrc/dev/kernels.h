@@ -40,8 +40,9 @@ void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView ou
 void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
 // tcgen05/TMEM/TMA implicit-GEMM (bf16 in, fp32 accumulate).  Plans live in conv_tc.cu.
 struct ConvTcPlan;
-ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams p, const TView *residual);   // nullptr if shape unsupported
+ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams p, const TView *residual, float res_alpha, float res_beta);   // nullptr if unsupported
 void conv_tc_plan_destroy(ConvTcPlan *plan);
+bool conv_tc_shape_supported(int cin, int stride, int act);
 void launch_conv_tc(ConvTcPlan *plan, cudaStream_t s);
 const char *conv_tc_plan_desc(ConvTcPlan *plan);
 

@@ -19,6 +19,15 @@ static int g_default_precision = -1;
 
 void b200_set_default_precision(int prec) { g_default_precision = prec; }
 
+static int g_default_fusion = -1;
+void b200_set_default_fusion(int on) { g_default_fusion = on; }
+int b200_get_default_fusion(void)
+{
+    if (g_default_fusion >= 0) return g_default_fusion;
+    const char *env = getenv("B200_FUSE");
+    return !(env && env[0] == '0');
+}
+
 static int resolve_precision(void)
 {
     if (g_default_precision >= 0) return g_default_precision;

@@ -77,6 +77,7 @@ predict_image = lib.network_predict_image; predict_image.argtypes = [c_void_p, I
 # ---- additive surface (include/b200_engine.h) --------------------------------------------------------
 PREC_BF16, PREC_FP32 = 0, 1
 lib.b200_set_default_precision.argtypes = [c_int]
+lib.b200_set_default_fusion.argtypes = [c_int]
 lib.b200_get_precision.argtypes = [c_void_p]; lib.b200_get_precision.restype = c_int
 lib.b200_set_conv_backend.argtypes = [c_void_p, c_int]
 lib.b200_set_head_sync.argtypes = [c_void_p, c_int]
@@ -117,12 +118,16 @@ def _fptr(a):
 class Network:
     """Convenience owner of a `network*` (what the reference wrapper passes around as c_void_p)."""
 
-    def __init__(self, cfg, weights=None, precision=None):
+    def __init__(self, cfg, weights=None, precision=None, fuse=None):
         if precision is not None:
             lib.b200_set_default_precision(int(precision))
+        if fuse is not None:
+            lib.b200_set_default_fusion(int(bool(fuse)))
         self.ptr = parse_network_cfg(str(cfg).encode())
         if precision is not None:
             lib.b200_set_default_precision(-1)
+        if fuse is not None:
+            lib.b200_set_default_fusion(-1)
         if weights:
             load_weights(self.ptr, str(weights).encode())
         self.n = lib.b200_network_layers(self.ptr)
