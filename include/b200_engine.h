@@ -74,6 +74,9 @@ void *b200_engine_stream(network *net);
 /* average device milliseconds per layer over `iters` forwards (CUDA events between layers); ms has net->n entries */
 void b200_profile_layers(network *net, int iters, float *ms);
 
+/* device milliseconds of the post-network tail on the current head outputs: ms[0] decode+compaction, ms[1] NMS, ms[2] collect */
+void b200_profile_tail(network *net, int w, int h, float thresh, float nms_thresh, int iters, float *ms);
+
 /* accessors for FFI callers: 20 ints = type, batch, inputs, outputs, h, w, c, out_h, out_w, out_c, n, size, stride, pad,
  * classes, coords, batch_normalize, activation, nweights, index */
 int b200_network_layers(const network *net);

@@ -28,3 +28,6 @@ for i, L in enumerate(net.layers):
     print("%3d %-13s %-10s %8.4f %9.2f %8.1f  %s" % (i, L["type_name"], net.kernel(i), ms[i], fl / 1e9, fl / (ms[i] * 1e-3) / 1e12 if ms[i] > 0 and fl else 0,
           dn.lib.b200_layer_plan(net.ptr, i).decode().replace("conv_tc ", "")))
 print("total %.3f ms, %.1f TFLOP/s overall" % (tot, totf / (tot * 1e-3) / 1e12))
+th, nms = (0.2, 0.4) if model == "yolov1" else (0.5, 0.45)
+tail = net.profile_tail(size, size, th, nms, 5)
+print("tail: decode %.4f ms, nms %.4f ms, collect %.4f ms" % tuple(tail))

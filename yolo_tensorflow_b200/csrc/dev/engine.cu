@@ -641,6 +641,40 @@ extern "C" void b200_run_layers(network *net, int start, int end)
     B200_CHECK(cudaStreamSynchronize(e->stream));
 }
 
+static void ensure_candidates(b200_engine *e, int slots);
+
+// device time (ms) of the post-network tail: [0] decode+compaction, [1] class-wise NMS, [2] record collection
+extern "C" void b200_profile_tail(network *net, int w, int h, float thresh, float nms_thresh, int iters, float *ms)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_profile_tail");
+    int batch = logical_batch(e, net);
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (e->heads.empty()) return;
+    ensure_candidates(e, e->cap);
+    int max_out = 1 << 20;
+    if (e->records_cap < max_out) { cudaFree(e->d_records); e->d_records = (DetRecord *)dev_alloc((size_t)max_out * sizeof(DetRecord)); e->records_cap = max_out; }
+    if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
+    cudaEvent_t ev[4];
+    for (auto &x : ev) B200_CHECK(cudaEventCreate(&x));
+    for (int it = -1; it < iters; ++it) {                 // iteration -1 is an untimed warm-up (scratch allocation)
+        B200_CHECK(cudaEventRecord(ev[0], e->stream));
+        launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, 1, 1, e->cand, e->stream);
+        B200_CHECK(cudaEventRecord(ev[1], e->stream));
+        launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
+                        e->boxes_per_image, &e->nms_scratch, e->stream);
+        B200_CHECK(cudaEventRecord(ev[2], e->stream));
+        B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));
+        launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
+                       e->d_records, max_out, e->d_record_count, e->stream);
+        B200_CHECK(cudaEventRecord(ev[3], e->stream));
+        B200_CHECK(cudaStreamSynchronize(e->stream));
+        if (it < 0) continue;
+        for (int k = 0; k < 3; ++k) { float t; B200_CHECK(cudaEventElapsedTime(&t, ev[k], ev[k + 1])); ms[k] += t / iters; }
+    }
+    for (auto &x : ev) cudaEventDestroy(x);
+}
+
 extern "C" const char *b200_layer_plan(network *net, int i)
 {
     b200_engine *e = b200_engine_of(net);

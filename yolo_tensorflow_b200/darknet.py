@@ -97,6 +97,7 @@ lib.b200_engine_input_device.argtypes = [c_void_p]; lib.b200_engine_input_device
 lib.b200_engine_sync.argtypes = [c_void_p]
 lib.b200_engine_stream.argtypes = [c_void_p]; lib.b200_engine_stream.restype = c_void_p
 lib.b200_profile_layers.argtypes = [c_void_p, c_int, POINTER(c_float)]
+lib.b200_profile_tail.argtypes = [c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(c_float)]
 lib.get_network_boxes_batch.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_float, POINTER(c_int), c_int, POINTER(c_int)]
 lib.get_network_boxes_batch.restype = POINTER(DETECTION)
 lib.b200_detect_batch.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(B200_DET), c_int, POINTER(c_int)]
@@ -174,6 +175,11 @@ class Network:
     def profile_layers(self, iters=3):
         ms = np.zeros(self.n, dtype=np.float32)
         lib.b200_profile_layers(self.ptr, iters, _fptr(ms))
+        return ms
+
+    def profile_tail(self, w, h, thresh, nms, iters=3):
+        ms = np.zeros(3, dtype=np.float32)
+        lib.b200_profile_tail(self.ptr, w, h, thresh, nms, iters, _fptr(ms))
         return ms
 
     def stream_ptr(self):
