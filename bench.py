@@ -256,10 +256,11 @@ def main_engine(args):
         pk = peaks()
         # roofline of the dominant kernel family, measured live with CUDA events between layers
         per_layer = net.profile_layers(3)
-        conv_ms = sum(float(per_layer[i]) for i in range(net.n) if net.kernel(i) == "conv_tc")
+        is_tc = [net.kernel(i).startswith("conv_tc") for i in range(net.n)]      # "conv_tc" and "conv_tc+shortcut" launches
+        conv_ms = sum(float(per_layer[i]) for i in range(net.n) if is_tc[i])
         conv_flops = sum(2.0 * L["n"] * L["size"] ** 2 * L["c"] * L["out_h"] * L["out_w"] * BATCH
-                         for i, L in enumerate(net.layers) if net.kernel(i) == "conv_tc")
-        n_conv = sum(1 for i in range(net.n) if net.kernel(i) == "conv_tc")
+                         for i, L in enumerate(net.layers) if is_tc[i])
+        n_conv = sum(is_tc)
         by_kernel = {}
         for i in range(net.n):
             by_kernel[net.kernel(i)] = by_kernel.get(net.kernel(i), 0.0) + float(per_layer[i])
