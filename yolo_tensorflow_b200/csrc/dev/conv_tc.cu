@@ -99,6 +99,53 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cta_group::2 (CTA pair) flavours ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads issued by EITHER CTA of the pair; completion bytes are credited to the LEADER's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc2_commit_both(uint64_t *bar)      // arrives on `bar` in BOTH CTAs of the pair
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)   // arrive on the copy of `bar` that lives in CTA rank 0
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remote;\n\t"
+        "mapa.shared::cluster.u32 remote, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t"
+        "}" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // kernel arguments
 // ---------------------------------------------------------------------------------------------------
@@ -118,6 +165,7 @@ struct ConvTcArgs {
     int tmem_cols;
     int act;
     int resident_b;          // 1: the whole [block_n x K] weight slab stays in shared memory for the CTA's lifetime
+    int pair;                // 1: cta_group::2 kernel (two CTAs share one 256 x block_n accumulator tile and its weights)
     long long npix;
     const float *scale, *shift;
     void *out;
@@ -362,6 +410,197 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// cta_group::2 variant: a CTA pair (two SMs of one TPC) computes a 256-pixel x BLOCK_N tile.  Each CTA loads its own
+// 128 pixel rows of A and HALF of the weight tile; tcgen05.mma.cta_group::2 (issued by the leader only) reads both
+// halves, so the weight bytes pulled through L2 per FLOP are halved — the measured bottleneck of the 1-CTA kernel.
+// Barriers: full[s] lives in the leader and collects the TMA bytes of both CTAs; empty[s] / tfull[a] are signalled
+// in both CTAs by a multicast tcgen05.commit; tempty[a] lives in the leader and collects the 8 epilogue warps.
+// ---------------------------------------------------------------------------------------------------
+template <int BLOCK_K, typename OutT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = 128 * BLOCK_K * 2;
+    const int stages = args.stages;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)stages * A_BYTES;
+    uint8_t *aux = sB + (size_t)stages * args.b_stage_bytes;       // b_stage_bytes = half tile here
+    uint64_t *full = (uint64_t *)aux;
+    uint64_t *empty = full + 8;
+    uint64_t *tfull = empty + 8;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 3);
+    float *s_scale = (float *)(aux + 256);
+    float *s_shift = s_scale + 512;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int m_pairs = (args.m_tiles + 1) / 2;
+    const int num_tiles = m_pairs * args.n_tiles;                   // pair tiles
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(args.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                             // peer barriers are initialised before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int half_n = args.block_n / 2;
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs) =========================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx_bytes = 2u * (uint32_t)(args.a_rows * BLOCK_K * 2 + half_n * BLOCK_K * 2);
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                const int n_tile = tile % args.n_tiles, m_tile = 2 * (tile / args.n_tiles) + (int)rank;
+                int ox0 = 0, oy0 = 0, n0 = 0;
+                if (args.mode == 1) {
+                    int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
+                    ox0 = tx * args.TW; oy0 = ty * args.TH; n0 = tn * args.TN;      // a phantom last tile lands past the batch: TMA zero-fills
+                }
+                for (int kb = 0; kb < args.num_kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&full[stage], tx_bytes);
+                    const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
+                    void *dstA = sA + (size_t)stage * A_BYTES;
+                    if (args.mode == 0) {
+                        tma2_load_2d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, m_tile * 128);
+                    } else {
+                        const int ky = tap / args.size, kx = tap - ky * args.size;
+                        int dy = ky - args.pad, dx = kx - args.pad;
+                        if (args.stride == 1) {
+                            tma2_load_4d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, ox0 + dx, oy0 + dy, n0);
+                        } else {
+                            int px = dx & 1, py = dy & 1;
+                            int xoff = (dx - px) / 2, yoff = (dy - py) / 2;
+                            tma2_load_4d(&maps.a[py * 2 + px], dstA, &full[stage], cb * BLOCK_K, ox0 + xoff, oy0 + yoff, n0);
+                        }
+                    }
+                    tma2_load_2d(&maps.b, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K,
+                                 n_tile * args.block_n + (int)rank * half_n);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.block_n >> 3) << 17) | ((256u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * args.block_n);
+                for (int kb = 0; kb < args.num_kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc<BLOCK_K>(smem_u32(sA + (size_t)stage * A_BYTES));
+                    const uint64_t bdesc = make_desc<BLOCK_K>(smem_u32(sB + (size_t)stage * args.b_stage_bytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        tc2_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc2_commit_both(&empty[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                tc2_commit_both(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================== epilogue (warps 2..5, both CTAs) =================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int ep_tid = threadIdx.x - 64;
+        int acc = 0; uint32_t acc_phase = 0;
+        int rx = 0, ry = 0, rn = 0;
+        if (args.mode == 1) { rx = row % args.TW; ry = (row / args.TW) % args.TH; rn = row / (args.TW * args.TH); }
+        const bool hoist = args.n_tiles == 1;
+        if (hoist) {
+            for (int c = ep_tid; c < args.block_n; c += 128) {
+                s_scale[c] = c < args.cout_pad ? args.scale[c] : 0.f;
+                s_shift[c] = c < args.cout_pad ? args.shift[c] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const bool leaky = args.act == ACT_LEAKY;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            const int n_tile = tile % args.n_tiles, m_tile = 2 * (tile / args.n_tiles) + (int)rank;
+            const int col0 = n_tile * args.block_n;
+            if (!hoist) {
+                for (int c = ep_tid; c < args.block_n; c += 128) {
+                    int co = col0 + c;
+                    s_scale[acc * 256 + c] = co < args.cout_pad ? args.scale[co] : 0.f;
+                    s_shift[acc * 256 + c] = co < args.cout_pad ? args.shift[co] : 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            long long pix = -1;
+            if (m_tile < args.m_tiles) {
+                if (args.mode == 0) {
+                    long long p = (long long)m_tile * 128 + row;
+                    if (p < args.npix) pix = p;
+                } else {
+                    int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
+                    int ox = tx * args.TW + rx, oy = ty * args.TH + ry, n = tn * args.TN + rn;
+                    if (row < args.a_rows && ox < args.OW && oy < args.OH && n < args.batch) pix = ((long long)n * args.OH + oy) * args.OW + ox;
+                }
+            }
+            OutT *orow = pix >= 0 ? (OutT *)args.out + pix * args.ldo + col0 : nullptr;
+            const bf16 *rrow = (args.res && pix >= 0) ? args.res + pix * args.ldr + col0 : nullptr;
+            const int cols_valid = args.cout_pad - col0;
+
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
+            const float *sc = s_scale + (hoist ? 0 : acc * 256), *sh = s_shift + (hoist ? 0 : acc * 256);
+            int c0 = 0;
+            for (; c0 + 32 <= args.block_n; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+                if (orow) {
+                    if (leaky) emit_columns<OutT, true, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                    else emit_columns<OutT, false, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                }
+            }
+            if (c0 < args.block_n) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c0, r);
+                tmem_ld_wait();
+                if (orow) {
+                    if (leaky) emit_columns<OutT, true, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                    else emit_columns<OutT, false, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                      // the leader's MMAs read the peer's shared memory: nobody leaves early
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(args.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -419,8 +658,40 @@ template <int BLOCK_K, typename OutT> static void launch_variant(ConvTcPlan *p, 
     conv_tc_kernel<BLOCK_K, OutT><<<p->grid, kTcThreads, p->smem_bytes, s>>>(p->maps, p->args);
 }
 
+template <int BLOCK_K, typename OutT> static void launch_pair_variant(ConvTcPlan *p, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_pair_kernel<BLOCK_K, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p->grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = p->smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    B200_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<BLOCK_K, OutT>, p->maps, p->args));
+}
+
 void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
 {
+    if (p->args.pair) {
+        if (p->out_dtype == DT_BF16) {
+            if (p->block_k == 64) launch_pair_variant<64, bf16>(p, s);
+            else if (p->block_k == 32) launch_pair_variant<32, bf16>(p, s);
+            else launch_pair_variant<16, bf16>(p, s);
+        } else {
+            if (p->block_k == 64) launch_pair_variant<64, float>(p, s);
+            else if (p->block_k == 32) launch_pair_variant<32, float>(p, s);
+            else launch_pair_variant<16, float>(p, s);
+        }
+        B200_LAUNCHED();
+        return;
+    }
     if (p->out_dtype == DT_BF16) {
         if (p->block_k == 64) launch_variant<64, bf16>(p, s);
         else if (p->block_k == 32) launch_variant<32, bf16>(p, s);
@@ -524,22 +795,28 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                 }
         }
     }
+    // ---- CTA-pair (cta_group::2) eligibility: compute-heavy layers whose weights cannot stay resident ----
+    const int a_bytes_ = 128 * block_k * 2;
+    const long long slab_ = (long long)a.num_kblocks * ((a.block_n * block_k * 2 + 1023) / 1024 * 1024);
+    const bool could_reside = a.n_tiles == 1 && slab_ + 4LL * a_bytes_ <= 227 * 1024 - 1024 - (256 + 4096);
+    a.pair = (!getenv("B200_NO_PAIR") && !could_reside && a.block_n % 32 == 0 && a.block_n >= 64 && a.m_tiles >= 2 &&
+              (long long)a.num_kblocks * a.block_n >= 4 * 256) ? 1 : 0;
     // ---- B view ----
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cp.cout_pad};
         cuuint64_t strides[1] = {(cuuint64_t)K * esz};
-        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)a.block_n};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)(a.pair ? a.block_n / 2 : a.block_n)};
         encode(&p->maps.b, (void *)cp.w, 2, dims, strides, box, block_k);
     }
     // ---- smem / tmem budget ----
     const int a_bytes = 128 * block_k * 2;
-    a.b_stage_bytes = (a.block_n * block_k * 2 + 1023) / 1024 * 1024;
+    a.b_stage_bytes = ((a.pair ? a.block_n / 2 : a.block_n) * block_k * 2 + 1023) / 1024 * 1024;
     const int aux_bytes = 256 + 2 * 512 * 4;
     const int budget = 227 * 1024 - 1024 - aux_bytes;
     // weight-stationary variant: when one filter tile covers all filters and its whole [block_n x K] slab fits next
     // to >= 4 activation stages, load it once per CTA and stream only activations (halves the TMA rows per k-block)
     const long long slab = (long long)a.num_kblocks * a.b_stage_bytes;
-    a.resident_b = (a.n_tiles == 1 && slab + 4LL * a_bytes <= budget && !getenv("B200_NO_RESIDENT_B")) ? 1 : 0;
+    a.resident_b = (!a.pair && a.n_tiles == 1 && slab + 4LL * a_bytes <= budget && !getenv("B200_NO_RESIDENT_B")) ? 1 : 0;
     int stages;
     if (a.resident_b) {
         stages = (int)((budget - slab) / a_bytes);
@@ -556,11 +833,15 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     int tiles = a.m_tiles * a.n_tiles;
     p->grid = tiles < 148 ? tiles : 148;
+    if (a.pair) {
+        int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+        p->grid = 2 * (pair_tiles < 74 ? pair_tiles : 74);
+    }
     p->flops = 2.0 * (double)a.npix * out.c * K;
     char buf[256];
     snprintf(buf, sizeof buf, "conv_tc mode%d k%d n%d tile %dx%dx%d rows %d m_tiles %d n_tiles %d stages %d smem %zu grid %d%s%s",
              a.mode, block_k, a.block_n, a.TW, a.TH, a.TN, a.a_rows, a.m_tiles, a.n_tiles, stages, p->smem_bytes, p->grid,
-             a.resident_b ? " residentB" : "", a.res ? " +residual" : "");
+             a.pair ? " PAIR(cta_group::2)" : (a.resident_b ? " residentB" : ""), a.res ? " +residual" : "");
     p->desc = buf;
     return p;
 }
