@@ -99,6 +99,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- TMA tile stores + swizzled shared-memory staging (epilogue) ---------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- cta_group::2 (CTA pair) flavours ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -152,6 +174,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)   // arrive on
 struct alignas(64) ConvTcMaps {
     CUtensorMap a[4];        // mode 0: a[0] dense [pixels][C]; mode 1: a[py*2+px] parity-phase views (stride 1 uses a[0])
     CUtensorMap b;           // weights [cout_pad][K]
+    CUtensorMap c;           // output tile store (staged epilogue): same pixel-tile geometry as A, 64-channel boxes
+    CUtensorMap r;           // residual tile load (fused shortcut), same geometry
 };
 
 struct ConvTcArgs {
@@ -165,6 +189,7 @@ struct ConvTcArgs {
     int tmem_cols;
     int act;
     int resident_b;          // 1: the whole [block_n x K] weight slab stays in shared memory for the CTA's lifetime
+    int staged;              // 1: epilogue goes TMEM -> registers -> swizzled smem tile -> TMA store (and TMA-loads the residual)
     int pair;                // 1: cta_group::2 kernel (two CTAs share one 256 x block_n accumulator tile and its weights)
     long long npix;
     const float *scale, *shift;
@@ -221,6 +246,165 @@ __device__ __forceinline__ void emit_columns(const uint32_t *r, const float *sc,
     }
 }
 
+// staged variant: the thread's pixel row lives in a 128B-swizzled [128 rows x 64 ch] sub-tile per 64 filters (the layout
+// TMA expects); 16-byte chunk j of row r sits at chunk j ^ (r & 7), which also makes the per-row accesses of a warp
+// bank-conflict-optimal (4 wavefronts per 512-byte request).
+template <bool LEAKY, int NC>
+__device__ __forceinline__ void emit_staged(const uint32_t *r, const float *sc, const float *sh, uint32_t sC_addr, int row, int c0,
+                                            bool has_res, float alpha, float beta)
+{
+#pragma unroll
+    for (int j = 0; j < NC; j += 8) {
+        const int c = c0 + j;
+        const uint32_t addr = sC_addr + (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u + ((uint32_t)(((c & 63) >> 3) ^ (row & 7)) << 4);
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q += 4) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(sc + j + q);
+            const float4 h4 = *reinterpret_cast<const float4 *>(sh + j + q);
+            v[q + 0] = fmaf(__uint_as_float(r[j + q + 0]), s4.x, h4.x);
+            v[q + 1] = fmaf(__uint_as_float(r[j + q + 1]), s4.y, h4.y);
+            v[q + 2] = fmaf(__uint_as_float(r[j + q + 2]), s4.z, h4.z);
+            v[q + 3] = fmaf(__uint_as_float(r[j + q + 3]), s4.w, h4.w);
+        }
+        if (LEAKY) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : 0.1f * v[q];
+        }
+        if (has_res) {
+            uint4 rr = lds128(addr);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float2 f = __bfloat1622float2(h[q]);
+                v[2 * q] = fmaf(alpha, v[2 * q], beta * f.x);
+                v[2 * q + 1] = fmaf(alpha, v[2 * q + 1], beta * f.y);
+            }
+        }
+        uint4 o;
+        __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        sts128(addr, o);
+    }
+}
+
+// The epilogue loop shared by the 1-CTA and the CTA-pair kernels (warps 2..5 = 128 threads).
+template <typename OutT, bool PAIR>
+__device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvTcArgs &args, uint64_t *tfull, uint64_t *tempty,
+                                             uint64_t *rfull, float *s_scale, float *s_shift, uint8_t *sC, uint32_t tmem_base,
+                                             int first_tile, int tile_step, int num_tiles, int rank)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quarter = warp & 3;                          // TMEM lane quarter this warp may touch
+    const int row = quarter * 32 + lane;
+    const int ep_tid = threadIdx.x - 64;
+    int acc = 0; uint32_t acc_phase = 0, rphase = 0;
+    int rx = 0, ry = 0, rn = 0;                            // row -> position inside the pixel tile (tile independent)
+    if (args.mode == 1) { rx = row % args.TW; ry = (row / args.TW) % args.TH; rn = row / (args.TW * args.TH); }
+    const bool hoist = args.n_tiles == 1;                  // one filter tile: its constants are staged once
+    if (hoist) {
+        for (int c = ep_tid; c < args.block_n; c += 128) {
+            s_scale[c] = c < args.cout_pad ? args.scale[c] : 0.f;
+            s_shift[c] = c < args.cout_pad ? args.shift[c] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const bool leaky = args.act == ACT_LEAKY;
+    const bool staged = sizeof(OutT) == 2 && args.staged;
+    const bool has_res = args.res != nullptr;
+    const int n_sub = args.block_n >> 6;
+    const uint32_t sC_addr = smem_u32(sC);
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int n_tile = tile % args.n_tiles;
+        const int m_tile = PAIR ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
+        const int col0 = n_tile * args.block_n;
+        if (!hoist) {
+            for (int c = ep_tid; c < args.block_n; c += 128) {
+                int co = col0 + c;
+                s_scale[acc * 256 + c] = co < args.cout_pad ? args.scale[co] : 0.f;
+                s_shift[acc * 256 + c] = co < args.cout_pad ? args.shift[co] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        int tx = 0, ty = 0, tn = 0;
+        if (args.mode == 1) { tx = m_tile % args.tiles_x; ty = (m_tile / args.tiles_x) % args.tiles_y; tn = m_tile / (args.tiles_x * args.tiles_y); }
+        OutT *orow = nullptr;
+        const bf16 *rrow = nullptr;
+        if (staged) {
+            if (ep_tid == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's stores are done reading sC
+                if (has_res) {                                                      // residual tile -> sC while the mainloop runs
+                    mbar_expect_tx(rfull, (uint32_t)(args.a_rows * args.block_n * 2));
+                    for (int q = 0; q < n_sub; ++q) {
+                        if (args.mode == 0) tma_load_2d(&maps.r, sC + q * 16384, rfull, col0 + 64 * q, m_tile * 128);
+                        else tma_load_4d(&maps.r, sC + q * 16384, rfull, col0 + 64 * q, tx * args.TW, ty * args.TH, tn * args.TN);
+                    }
+                }
+            }
+            if (!has_res) asm volatile("bar.sync 1, 128;" ::: "memory");           // nobody overwrites sC before that wait
+        } else {
+            long long pix = -1;
+            if (m_tile < args.m_tiles) {
+                if (args.mode == 0) {
+                    long long p = (long long)m_tile * 128 + row;
+                    if (p < args.npix) pix = p;
+                } else {
+                    int ox = tx * args.TW + rx, oy = ty * args.TH + ry, n = tn * args.TN + rn;
+                    if (row < args.a_rows && ox < args.OW && oy < args.OH && n < args.batch) pix = ((long long)n * args.OH + oy) * args.OW + ox;
+                }
+            }
+            orow = pix >= 0 ? (OutT *)args.out + pix * args.ldo + col0 : nullptr;
+            rrow = (has_res && pix >= 0) ? args.res + pix * args.ldr + col0 : nullptr;
+        }
+        const int cols_valid = args.cout_pad - col0;        // columns of this tile that exist in the output row
+
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        if (staged && has_res) { mbar_wait(rfull, rphase); rphase ^= 1; }
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
+        const float *sc = s_scale + (hoist ? 0 : acc * 256), *sh = s_shift + (hoist ? 0 : acc * 256);
+        int c0 = 0;
+        for (; c0 + 32 <= args.block_n; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+            tmem_ld_wait();
+            if (staged) {
+                if (leaky) emit_staged<true, 32>(r, sc + c0, sh + c0, sC_addr, row, c0, has_res, args.res_alpha, args.res_beta);
+                else emit_staged<false, 32>(r, sc + c0, sh + c0, sC_addr, row, c0, has_res, args.res_alpha, args.res_beta);
+            } else if (orow) {
+                if (leaky) emit_columns<OutT, true, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                else emit_columns<OutT, false, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+            }
+        }
+        if (c0 < args.block_n) {                            // 16-column tail (block_n is a multiple of 16; never staged)
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            if (orow) {
+                if (leaky) emit_columns<OutT, true, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+                else emit_columns<OutT, false, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+        if (staged) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy writes -> visible to the TMA engine
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (ep_tid == 0) {
+                for (int q = 0; q < n_sub; ++q) {
+                    if (args.mode == 0) tma_store_2d(&maps.c, sC + q * 16384, col0 + 64 * q, m_tile * 128);
+                    else tma_store_4d(&maps.c, sC + q * 16384, col0 + 64 * q, tx * args.TW, ty * args.TH, tn * args.TN);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (staged && ep_tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <int BLOCK_K, typename OutT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
@@ -232,13 +416,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)stages * A_BYTES;
     const int b_slots = args.resident_b ? args.num_kblocks : stages;
-    uint8_t *aux = sB + (size_t)b_slots * args.b_stage_bytes;
+    uint8_t *sC = sB + (size_t)b_slots * args.b_stage_bytes;       // staged-epilogue tile: (block_n/64) x 16 KB, 1024-aligned
+    uint8_t *aux = sC + (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0);
     uint64_t *full = (uint64_t *)aux;                 // [stages]
     uint64_t *empty = full + 8;                       // [stages]
     uint64_t *tfull = empty + 8;                      // [2]
     uint64_t *tempty = tfull + 2;                     // [2]
     uint64_t *wfull = tempty + 2;                     // resident weights landed
-    uint32_t *tmem_slot = (uint32_t *)(wfull + 1);
+    uint64_t *rfull = wfull + 1;                      // residual tile landed (staged epilogue)
+    uint32_t *tmem_slot = (uint32_t *)(rfull + 1);
     float *s_scale = (float *)(aux + 256);            // [2][256]
     float *s_shift = s_scale + 512;                   // [2][256]
 
@@ -249,6 +435,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         mbar_init(wfull, 1);
+        mbar_init(rfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -331,74 +518,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
         }
     } else {
         // ===================================== epilogue (warps 2..5) ============================
-        const int quarter = warp & 3;                          // TMEM lane quarter this warp may touch
-        const int row = quarter * 32 + lane;
-        const int ep_tid = threadIdx.x - 64;
-        int acc = 0; uint32_t acc_phase = 0;
-        // row -> position inside the pixel tile is the same for every tile
-        int rx = 0, ry = 0, rn = 0;
-        if (args.mode == 1) { rx = row % args.TW; ry = (row / args.TW) % args.TH; rn = row / (args.TW * args.TH); }
-        const bool hoist = args.n_tiles == 1;                  // one filter tile: its constants are staged once
-        if (hoist) {
-            for (int c = ep_tid; c < args.block_n; c += 128) {
-                s_scale[c] = c < args.cout_pad ? args.scale[c] : 0.f;
-                s_shift[c] = c < args.cout_pad ? args.shift[c] : 0.f;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        const bool leaky = args.act == ACT_LEAKY;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int n_tile = tile % args.n_tiles, m_tile = tile / args.n_tiles;
-            const int col0 = n_tile * args.block_n;
-            if (!hoist) {
-                for (int c = ep_tid; c < args.block_n; c += 128) {
-                    int co = col0 + c;
-                    s_scale[acc * 256 + c] = co < args.cout_pad ? args.scale[co] : 0.f;
-                    s_shift[acc * 256 + c] = co < args.cout_pad ? args.shift[co] : 0.f;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            long long pix = -1;
-            if (args.mode == 0) {
-                long long p = (long long)m_tile * 128 + row;
-                if (p < args.npix) pix = p;
-            } else {
-                int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
-                int ox = tx * args.TW + rx, oy = ty * args.TH + ry, n = tn * args.TN + rn;
-                if (row < args.a_rows && ox < args.OW && oy < args.OH && n < args.batch) pix = ((long long)n * args.OH + oy) * args.OW + ox;
-            }
-            OutT *orow = pix >= 0 ? (OutT *)args.out + pix * args.ldo + col0 : nullptr;
-            const bf16 *rrow = (args.res && pix >= 0) ? args.res + pix * args.ldr + col0 : nullptr;
-            const int cols_valid = args.cout_pad - col0;        // columns of this tile that exist in the output row
-
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
-            const float *sc = s_scale + (hoist ? 0 : acc * 256), *sh = s_shift + (hoist ? 0 : acc * 256);
-            int c0 = 0;
-            for (; c0 + 32 <= args.block_n; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
-                tmem_ld_wait();
-                if (orow) {
-                    if (leaky) emit_columns<OutT, true, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                    else emit_columns<OutT, false, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                }
-            }
-            if (c0 < args.block_n) {                            // 16-column tail (block_n is a multiple of 16)
-                uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
-                tmem_ld_wait();
-                if (orow) {
-                    if (leaky) emit_columns<OutT, true, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                    else emit_columns<OutT, false, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
+        run_epilogue<OutT, false>(maps, args, tfull, tempty, rfull, s_scale, s_shift, sC, tmem_base, blockIdx.x, gridDim.x, num_tiles, 0);
     }
 
     tc_fence_before();
@@ -426,12 +546,14 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
     const int stages = args.stages;
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)stages * A_BYTES;
-    uint8_t *aux = sB + (size_t)stages * args.b_stage_bytes;       // b_stage_bytes = half tile here
+    uint8_t *sC = sB + (size_t)stages * args.b_stage_bytes;        // b_stage_bytes = half tile here
+    uint8_t *aux = sC + (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0);
     uint64_t *full = (uint64_t *)aux;
     uint64_t *empty = full + 8;
     uint64_t *tfull = empty + 8;
     uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = (uint32_t *)(tempty + 3);
+    uint64_t *rfull = tempty + 3;
+    uint32_t *tmem_slot = (uint32_t *)(rfull + 1);
     float *s_scale = (float *)(aux + 256);
     float *s_shift = s_scale + 512;
 
@@ -445,6 +567,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        mbar_init(rfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -521,75 +644,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
         }
     } else {
         // ===================================== epilogue (warps 2..5, both CTAs) =================
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const int ep_tid = threadIdx.x - 64;
-        int acc = 0; uint32_t acc_phase = 0;
-        int rx = 0, ry = 0, rn = 0;
-        if (args.mode == 1) { rx = row % args.TW; ry = (row / args.TW) % args.TH; rn = row / (args.TW * args.TH); }
-        const bool hoist = args.n_tiles == 1;
-        if (hoist) {
-            for (int c = ep_tid; c < args.block_n; c += 128) {
-                s_scale[c] = c < args.cout_pad ? args.scale[c] : 0.f;
-                s_shift[c] = c < args.cout_pad ? args.shift[c] : 0.f;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        const bool leaky = args.act == ACT_LEAKY;
-        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-            const int n_tile = tile % args.n_tiles, m_tile = 2 * (tile / args.n_tiles) + (int)rank;
-            const int col0 = n_tile * args.block_n;
-            if (!hoist) {
-                for (int c = ep_tid; c < args.block_n; c += 128) {
-                    int co = col0 + c;
-                    s_scale[acc * 256 + c] = co < args.cout_pad ? args.scale[co] : 0.f;
-                    s_shift[acc * 256 + c] = co < args.cout_pad ? args.shift[co] : 0.f;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            long long pix = -1;
-            if (m_tile < args.m_tiles) {
-                if (args.mode == 0) {
-                    long long p = (long long)m_tile * 128 + row;
-                    if (p < args.npix) pix = p;
-                } else {
-                    int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
-                    int ox = tx * args.TW + rx, oy = ty * args.TH + ry, n = tn * args.TN + rn;
-                    if (row < args.a_rows && ox < args.OW && oy < args.OH && n < args.batch) pix = ((long long)n * args.OH + oy) * args.OW + ox;
-                }
-            }
-            OutT *orow = pix >= 0 ? (OutT *)args.out + pix * args.ldo + col0 : nullptr;
-            const bf16 *rrow = (args.res && pix >= 0) ? args.res + pix * args.ldr + col0 : nullptr;
-            const int cols_valid = args.cout_pad - col0;
-
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
-            const float *sc = s_scale + (hoist ? 0 : acc * 256), *sh = s_shift + (hoist ? 0 : acc * 256);
-            int c0 = 0;
-            for (; c0 + 32 <= args.block_n; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
-                tmem_ld_wait();
-                if (orow) {
-                    if (leaky) emit_columns<OutT, true, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                    else emit_columns<OutT, false, 32>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                }
-            }
-            if (c0 < args.block_n) {
-                uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
-                tmem_ld_wait();
-                if (orow) {
-                    if (leaky) emit_columns<OutT, true, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                    else emit_columns<OutT, false, 16>(r, sc + c0, sh + c0, orow + c0, rrow ? rrow + c0 : nullptr, args.res_alpha, args.res_beta, cols_valid - c0);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
+        run_epilogue<OutT, true>(maps, args, tfull, tempty, rfull, s_scale, s_shift, sC, tmem_base, pair_id, num_pairs, num_tiles, (int)rank);
     }
 
     tc_fence_before();
@@ -636,6 +691,23 @@ static void encode(CUtensorMap *map, void *base, int rank, const cuuint64_t *dim
         fprintf(stderr, "b200-darknet: cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu box %u %u\n", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
         abort();
+    }
+}
+
+// 64-channel x pixel-tile boxes of an NHWC bf16 tensor, 128B-swizzled: the staged epilogue's store / residual-load view
+static void encode_tile_view(CUtensorMap *map, const TView &t, int channels, const ConvTcArgs &a)
+{
+    const size_t esz = 2;
+    if (a.mode == 0) {
+        cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)a.npix};
+        cuuint64_t strides[1] = {(cuuint64_t)t.ld * esz};
+        cuuint32_t box[2] = {64, 128};
+        encode(map, t.p, 2, dims, strides, box, 64);
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
+        cuuint64_t strides[3] = {(cuuint64_t)t.ld * esz, (cuuint64_t)t.w * t.ld * esz, (cuuint64_t)t.h * t.w * t.ld * esz};
+        cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, (cuuint32_t)a.TN};
+        encode(map, t.p, 4, dims, strides, box, 64);
     }
 }
 
@@ -795,10 +867,16 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                 }
         }
     }
-    // ---- CTA-pair (cta_group::2) eligibility: compute-heavy layers whose weights cannot stay resident ----
+    // ---- epilogue staging / weight residency / CTA pairing -------------------------------------------------
+    // staged epilogue (TMEM -> registers -> swizzled smem tile -> TMA store, residual TMA-loaded into the same tile) is used
+    // where a shortcut is fused: the per-row residual reads of the direct epilogue are what made fused layers slow.
     const int a_bytes_ = 128 * block_k * 2;
+    const int sc_bytes = (a.block_n / 64) * 16384;
+    const int budget_all = 227 * 1024 - 1024 - (256 + 4096);
+    const bool want_staged = residual && !getenv("B200_NO_STAGED") && out.dtype == DT_BF16 && a.block_n % 64 == 0 && cp.cout_pad % 64 == 0;
     const long long slab_ = (long long)a.num_kblocks * ((a.block_n * block_k * 2 + 1023) / 1024 * 1024);
-    const bool could_reside = a.n_tiles == 1 && slab_ + 4LL * a_bytes_ <= 227 * 1024 - 1024 - (256 + 4096);
+    const bool could_reside = a.n_tiles == 1 && !getenv("B200_NO_RESIDENT_B") &&
+                              slab_ + (want_staged ? 3LL * a_bytes_ + sc_bytes : 4LL * a_bytes_) <= budget_all;
     a.pair = (!getenv("B200_NO_PAIR") && !could_reside && a.block_n % 32 == 0 && a.block_n >= 64 && a.m_tiles >= 2 &&
               (long long)a.num_kblocks * a.block_n >= 4 * 256) ? 1 : 0;
     // ---- B view ----
@@ -812,23 +890,32 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     const int a_bytes = 128 * block_k * 2;
     a.b_stage_bytes = ((a.pair ? a.block_n / 2 : a.block_n) * block_k * 2 + 1023) / 1024 * 1024;
     const int aux_bytes = 256 + 2 * 512 * 4;
-    const int budget = 227 * 1024 - 1024 - aux_bytes;
+    int budget = 227 * 1024 - 1024 - aux_bytes;
+    a.staged = 0;
+    if (want_staged) {
+        const long long need = could_reside ? slab_ + 3LL * a_bytes : 3LL * (a_bytes + a.b_stage_bytes);
+        if (need + sc_bytes <= budget) { a.staged = 1; budget -= sc_bytes; }
+    }
     // weight-stationary variant: when one filter tile covers all filters and its whole [block_n x K] slab fits next
     // to >= 4 activation stages, load it once per CTA and stream only activations (halves the TMA rows per k-block)
     const long long slab = (long long)a.num_kblocks * a.b_stage_bytes;
-    a.resident_b = (!a.pair && a.n_tiles == 1 && slab + 4LL * a_bytes <= budget && !getenv("B200_NO_RESIDENT_B")) ? 1 : 0;
+    a.resident_b = (!a.pair && could_reside && slab + 3LL * a_bytes <= budget) ? 1 : 0;
     int stages;
     if (a.resident_b) {
         stages = (int)((budget - slab) / a_bytes);
         if (stages > 8) stages = 8;
-        p->smem_bytes = (size_t)stages * a_bytes + (size_t)slab + aux_bytes + 1024;
+        p->smem_bytes = (size_t)stages * a_bytes + (size_t)slab + (a.staged ? sc_bytes : 0) + aux_bytes + 1024;
     } else {
         stages = budget / (a_bytes + a.b_stage_bytes);
         if (stages > 8) stages = 8;
         if (stages < 2) { delete p; return nullptr; }
-        p->smem_bytes = (size_t)stages * (a_bytes + a.b_stage_bytes) + aux_bytes + 1024;
+        p->smem_bytes = (size_t)stages * (a_bytes + a.b_stage_bytes) + (a.staged ? sc_bytes : 0) + aux_bytes + 1024;
     }
     a.stages = stages;
+    if (a.staged) {
+        encode_tile_view(&p->maps.c, out, cp.cout_pad, a);
+        if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a);
+    }
     int cols = 2 * a.block_n;
     a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     int tiles = a.m_tiles * a.n_tiles;
@@ -842,6 +929,8 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     snprintf(buf, sizeof buf, "conv_tc mode%d k%d n%d tile %dx%dx%d rows %d m_tiles %d n_tiles %d stages %d smem %zu grid %d%s%s",
              a.mode, block_k, a.block_n, a.TW, a.TH, a.TN, a.a_rows, a.m_tiles, a.n_tiles, stages, p->smem_bytes, p->grid,
              a.pair ? " PAIR(cta_group::2)" : (a.resident_b ? " residentB" : ""), a.res ? " +residual" : "");
+
     p->desc = buf;
+    if (a.staged) p->desc += " stagedEpilogue";
     return p;
 }
