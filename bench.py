@@ -94,8 +94,9 @@ def cpu_reference_run(steps, warmup, images_per_step=1):
     from yolo_tensorflow_b200 import synth
     from oracle import ref_darknet as R
     cfg, wpath = prepare_files(1)
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host thread it can
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("B200_REF_THREADS", str(cores))
     kind = "reference"
     if R.available():
         net = R.RefNet(cfg, wpath)
