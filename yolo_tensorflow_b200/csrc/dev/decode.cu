@@ -5,10 +5,10 @@
 // get_detection_detections (detection_layer.c:225-252), including the reference's float/double promotion at
 // every step, for EVERY image of the batch (the reference only reads batch item 0).
 //
-// One 1024-thread CTA per image walks the heads in layer order and each head's boxes in the reference's
-// enumeration order; survivors are appended with a warp-ballot + block prefix sum, so the compacted list has
-// exactly the order fill_network_boxes produces (deterministic, no atomics).  Only survivors touch HBM on the
-// write side: (4 + 1 + classes) floats each.
+// Boxes are numbered per image in the reference's enumeration order (heads in layer order; inside a head the
+// order of get_*_detections).  A warp ballot per 32 boxes builds a keep bitmap, a per-image prefix sum of the
+// popcounts gives every survivor its slot, so the compacted list has exactly the order fill_network_boxes
+// produces (deterministic, no atomics).  Only survivors touch HBM on the write side: (4 + 1 + classes) floats each.
 #include "kernels.h"
 #include "darknet.h"
 
@@ -51,106 +51,175 @@ __device__ __forceinline__ int block_rank(bool flag, int *warp_totals, int &tota
     return before + within;
 }
 
-__global__ void __launch_bounds__(DEC_THREADS)
-decode_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, int netw, int neth, int imw, int imh,
-              float thresh, int relative, int mode, CandBuffers cb)
+// ---------------------------------------------------------------------------------------------------
+// three small, fully parallel kernels instead of one serial CTA per image:
+//   flags : one thread per anchor box evaluates the threshold test; a warp ballot becomes one bitmap word
+//   scan  : one CTA per image turns the word popcounts into exclusive offsets (=> the reference's output order)
+//   emit  : one thread per surviving box decodes it and writes it to slot offset[word] + rank-in-word
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_head(const HeadDesc *heads, int nheads, int t, int &local)
 {
-    __shared__ int warp_totals[DEC_THREADS / 32];
-    const int img = first_image + blockIdx.x;      // image inside the batch
-    const int slot = blockIdx.x;                   // slot inside the candidate buffers
-    float *cbox = cb.box + (size_t)slot * cb.cap * 4;
-    float *cobj = cb.obj + (size_t)slot * cb.cap;
-    float *cprob = cb.prob + (size_t)slot * cb.cap * cb.classes;
-    int *cid = cb.id + (size_t)slot * cb.cap;
-    int written = 0;
+    int hi = 0;
+    for (int i = 1; i < nheads; ++i) if (t >= heads[i].box_base) hi = i;
+    local = t - heads[hi].box_base;
+    return hi;
+}
 
-    for (int hi = 0; hi < nheads; ++hi) {
-        const HeadDesc hd = heads[hi];
+__device__ __forceinline__ bool box_keep(const HeadDesc &hd, const float *pred, int t, float thresh, int mode, float &objectness,
+                                         float &scale, int &cell, int &a)
+{
+    const int wh = hd.w * hd.h;
+    if (hd.type == YOLO) {
+        cell = t / hd.n; a = t % hd.n;
+        objectness = pred[(size_t)a * wh * (hd.classes + 5) + 4 * wh + cell];
+        scale = objectness;
+        return objectness > thresh;
+    }
+    if (hd.type == REGION) {
+        a = t / wh; cell = t % wh;
+        scale = pred[(size_t)a * wh * (hd.coords + hd.classes + 1) + hd.coords * wh + cell];
+        objectness = scale > thresh ? scale : 0.f;
+        return mode == 0 ? true : (objectness != 0.f);
+    }
+    cell = t / hd.n; a = t % hd.n;                                  // DETECTION
+    scale = pred[hd.side * hd.side * hd.classes + cell * hd.n + a];
+    objectness = scale;
+    return mode == 0 ? true : (objectness != 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+decode_flags_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, int boxes, int words, float thresh, int mode,
+                    unsigned *__restrict__ flags)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = first_image + blockIdx.y;
+    bool keep = false;
+    if (t < boxes) {
+        int local;
+        const HeadDesc &hd = heads[find_head(heads, nheads, t, local)];
+        float o, s; int cell, a;
+        keep = box_keep(hd, hd.out + (size_t)img * hd.outputs, local, thresh, mode, o, s, cell, a);
+    }
+    unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && (t >> 5) < words) flags[(size_t)blockIdx.y * words + (t >> 5)] = b;
+}
+
+__global__ void __launch_bounds__(1024)
+decode_scan_kernel(const unsigned *__restrict__ flags, int words, int cap, int *__restrict__ offsets, int *__restrict__ count)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int chunk_total;
+    const int slot = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int running = 0;
+    for (int w0 = 0; w0 < words; w0 += 1024) {
+        const int w = w0 + threadIdx.x;
+        const int c = w < words ? __popc(flags[(size_t)slot * words + w]) : 0;
+        int inc = c;                                               // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = warp_sums[lane];
+            int incw = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incw, o); if (lane >= o) incw += u; }
+            warp_sums[lane] = incw - v;                            // exclusive prefix of the warp totals
+            if (lane == 31) chunk_total = incw;
+        }
+        __syncthreads();
+        if (w < words) offsets[(size_t)slot * words + w] = running + warp_sums[warp] + inc - c;
+        running += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[slot] = running < cap ? running : cap;
+}
+
+__global__ void __launch_bounds__(256)
+decode_emit_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, int boxes, int words, int netw, int neth,
+                   int imw, int imh, float thresh, int relative, int mode, const unsigned *__restrict__ flags,
+                   const int *__restrict__ offsets, CandBuffers cb)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= boxes) return;
+    const int slot = blockIdx.y, img = first_image + blockIdx.y, lane = threadIdx.x & 31;
+    const unsigned bits = flags[(size_t)slot * words + (t >> 5)];
+    if (!((bits >> lane) & 1u)) return;
+    const int dst = offsets[(size_t)slot * words + (t >> 5)] + __popc(bits & ((1u << lane) - 1));
+    if (dst >= cb.cap) return;
+    int local;
+    const HeadDesc &hd = heads[find_head(heads, nheads, t, local)];
+    const float *pred = hd.out + (size_t)img * hd.outputs;
+    float objectness, scale; int cell, a;
+    box_keep(hd, pred, local, thresh, mode, objectness, scale, cell, a);
+    const int wh = hd.w * hd.h;
+    const int row = cell / hd.w, col = cell % hd.w;
+    BoxF b;
+    if (hd.type == YOLO) {
+        const float *e = pred + (size_t)a * wh * (hd.classes + 5) + cell;
+        b.x = __fdiv_rn(__fadd_rn((float)col, e[0]), (float)hd.w);
+        b.y = __fdiv_rn(__fadd_rn((float)row, e[wh]), (float)hd.h);
+        b.w = (float)(exp((double)e[2 * wh]) * (double)hd.anchors[2 * a] / netw);
+        b.h = (float)(exp((double)e[3 * wh]) * (double)hd.anchors[2 * a + 1] / neth);
+        b = correct_box(b, imw, imh, netw, neth, relative);
+    } else if (hd.type == REGION) {
+        const float *e = pred + (size_t)a * wh * (hd.coords + hd.classes + 1) + cell;
+        b.x = __fdiv_rn(__fadd_rn((float)col, e[0]), (float)hd.w);
+        b.y = __fdiv_rn(__fadd_rn((float)row, e[wh]), (float)hd.h);
+        b.w = (float)(exp((double)e[2 * wh]) * (double)hd.anchors[2 * a] / hd.w);
+        b.h = (float)(exp((double)e[3 * wh]) * (double)hd.anchors[2 * a + 1] / hd.h);
+        b = correct_box(b, imw, imh, netw, neth, relative);
+    } else {
+        const float *bx = pred + hd.side * hd.side * (hd.classes + hd.n) + (cell * hd.n + a) * 4;
+        b.x = __fmul_rn(__fdiv_rn(__fadd_rn(bx[0], (float)col), (float)hd.side), (float)imw);
+        b.y = __fmul_rn(__fdiv_rn(__fadd_rn(bx[1], (float)row), (float)hd.side), (float)imh);
+        b.w = (float)(pow((double)bx[2], (double)(hd.sqrt_ ? 2 : 1)) * imw);
+        b.h = (float)(pow((double)bx[3], (double)(hd.sqrt_ ? 2 : 1)) * imh);
+    }
+    float *cbox = cb.box + ((size_t)slot * cb.cap + dst) * 4;
+    cbox[0] = b.x; cbox[1] = b.y; cbox[2] = b.w; cbox[3] = b.h;
+    cb.obj[(size_t)slot * cb.cap + dst] = objectness;
+    cb.id[(size_t)slot * cb.cap + dst] = t;
+}
+
+// class probabilities of the survivors: one warp per survivor, lanes over classes (coalesced writes, 32 loads in flight)
+__global__ void __launch_bounds__(256)
+decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, float thresh, int mode, CandBuffers cb)
+{
+    const int slot = blockIdx.y, img = first_image + blockIdx.y, lane = threadIdx.x & 31;
+    const int n = cb.count[slot];
+    for (int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); d < n; d += gridDim.x * (blockDim.x >> 5)) {
+        int local;
+        const HeadDesc &hd = heads[find_head(heads, nheads, cb.id[(size_t)slot * cb.cap + d], local)];
         const float *pred = hd.out + (size_t)img * hd.outputs;
+        float objectness, scale; int cell, a;
+        box_keep(hd, pred, local, thresh, mode, objectness, scale, cell, a);
         const int wh = hd.w * hd.h;
-        const int nboxes = wh * hd.n;
-        for (int t0 = 0; t0 < nboxes; t0 += DEC_THREADS) {
-            const int t = t0 + threadIdx.x;
-            bool keep = false;
-            float objectness = 0.f, scale = 0.f;
-            int cell = 0, a = 0;
-            if (t < nboxes) {
-                if (hd.type == YOLO) {
-                    cell = t / hd.n; a = t % hd.n;
-                    objectness = pred[(size_t)a * wh * (hd.classes + 5) + 4 * wh + cell];
-                    scale = objectness;
-                    keep = objectness > thresh;
-                } else if (hd.type == REGION) {
-                    a = t / wh; cell = t % wh;
-                    scale = pred[(size_t)a * wh * (hd.coords + hd.classes + 1) + hd.coords * wh + cell];
-                    objectness = scale > thresh ? scale : 0.f;
-                    keep = mode == 0 ? true : (objectness != 0.f);
-                } else {                                          // DETECTION
-                    cell = t / hd.n; a = t % hd.n;
-                    scale = pred[hd.side * hd.side * hd.classes + cell * hd.n + a];
-                    objectness = scale;
-                    keep = mode == 0 ? true : (objectness != 0.f);
-                }
-            }
-            int total;
-            int rank = block_rank(keep, warp_totals, total);
-            if (keep && written + rank < cb.cap) {
-                const int dst = written + rank;
-                const int row = cell / hd.w, col = cell % hd.w;
-                BoxF b;
-                float *pr = cprob + (size_t)dst * cb.classes;
-                if (hd.type == YOLO) {
-                    const float *e = pred + (size_t)a * wh * (hd.classes + 5) + cell;
-                    b.x = __fdiv_rn(__fadd_rn((float)col, e[0]), (float)hd.w);
-                    b.y = __fdiv_rn(__fadd_rn((float)row, e[wh]), (float)hd.h);
-                    b.w = (float)(exp((double)e[2 * wh]) * (double)hd.anchors[2 * a] / netw);
-                    b.h = (float)(exp((double)e[3 * wh]) * (double)hd.anchors[2 * a + 1] / neth);
-                    for (int j = 0; j < hd.classes; ++j) {
-                        float p = __fmul_rn(objectness, e[(size_t)(5 + j) * wh]);
-                        pr[j] = p > thresh ? p : 0.f;
-                    }
-                    b = correct_box(b, imw, imh, netw, neth, relative);
-                } else if (hd.type == REGION) {
-                    const float *e = pred + (size_t)a * wh * (hd.coords + hd.classes + 1) + cell;
-                    b.x = __fdiv_rn(__fadd_rn((float)col, e[0]), (float)hd.w);
-                    b.y = __fdiv_rn(__fadd_rn((float)row, e[wh]), (float)hd.h);
-                    b.w = (float)(exp((double)e[2 * wh]) * (double)hd.anchors[2 * a] / hd.w);
-                    b.h = (float)(exp((double)e[3 * wh]) * (double)hd.anchors[2 * a + 1] / hd.h);
-                    for (int j = 0; j < hd.classes; ++j) {
-                        float p = 0.f;
-                        if (objectness != 0.f) {
-                            p = __fmul_rn(scale, e[(size_t)(hd.coords + 1 + j) * wh]);
-                            p = p > thresh ? p : 0.f;
-                        }
-                        pr[j] = p;
-                    }
-                    b = correct_box(b, imw, imh, netw, neth, relative);
-                } else {
-                    const float *bx = pred + hd.side * hd.side * (hd.classes + hd.n) + (cell * hd.n + a) * 4;
-                    b.x = __fmul_rn(__fdiv_rn(__fadd_rn(bx[0], (float)col), (float)hd.side), (float)imw);
-                    b.y = __fmul_rn(__fdiv_rn(__fadd_rn(bx[1], (float)row), (float)hd.side), (float)imh);
-                    b.w = (float)(pow((double)bx[2], (double)(hd.sqrt_ ? 2 : 1)) * imw);
-                    b.h = (float)(pow((double)bx[3], (double)(hd.sqrt_ ? 2 : 1)) * imh);
-                    const float *cls = pred + cell * hd.classes;
-                    for (int j = 0; j < hd.classes; ++j) {
-                        float p = __fmul_rn(scale, cls[j]);
-                        pr[j] = p > thresh ? p : 0.f;
-                    }
-                }
-                cbox[dst * 4 + 0] = b.x; cbox[dst * 4 + 1] = b.y; cbox[dst * 4 + 2] = b.w; cbox[dst * 4 + 3] = b.h;
-                cobj[dst] = objectness;
-                cid[dst] = hd.box_base + t;
-            }
-            written += total;
+        float *pr = cb.prob + ((size_t)slot * cb.cap + d) * cb.classes;
+        for (int j = lane; j < hd.classes; j += 32) {
+            float p;
+            if (hd.type == YOLO) p = __fmul_rn(objectness, pred[(size_t)a * wh * (hd.classes + 5) + (size_t)(5 + j) * wh + cell]);
+            else if (hd.type == REGION) p = objectness != 0.f ? __fmul_rn(scale, pred[(size_t)a * wh * (hd.coords + hd.classes + 1) + (size_t)(hd.coords + 1 + j) * wh + cell]) : 0.f;
+            else p = __fmul_rn(scale, pred[cell * hd.classes + j]);
+            pr[j] = p > thresh ? p : 0.f;
         }
     }
-    if (threadIdx.x == 0) cb.count[slot] = written < cb.cap ? written : cb.cap;
 }
 
 void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
                    int imw, int imh, float thresh, int relative, int mode, CandBuffers cb, cudaStream_t s)
 {
-    decode_kernel<<<nimages, DEC_THREADS, 0, s>>>(heads_dev, nheads, first_image, netw, neth, imw, imh, thresh, relative, mode, cb);
+    const int boxes = cb.cap;                                       // cap == anchor boxes per image
+    const int words = (boxes + 31) / 32;
+    dim3 grid(div_up(boxes, 256), nimages);
+    decode_flags_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, thresh, mode, cb.flags);
+    B200_LAUNCHED();
+    decode_scan_kernel<<<nimages, 1024, 0, s>>>(cb.flags, words, cb.cap, cb.offsets, cb.count);
+    B200_LAUNCHED();
+    decode_emit_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, netw, neth, imw, imh, thresh, relative, mode,
+                                            cb.flags, cb.offsets, cb);
+    B200_LAUNCHED();
+    decode_probs_kernel<<<dim3(8, nimages), 256, 0, s>>>(heads_dev, nheads, first_image, thresh, mode, cb);
     B200_LAUNCHED();
 }
 

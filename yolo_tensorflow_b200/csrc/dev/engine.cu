@@ -372,6 +372,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         }
         cudaFree(e->d_input); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
         cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
+        cudaFree(e->cand.flags); cudaFree(e->cand.offsets); cudaFree(e->cand.cls_count);
         cudaFree(e->nms_scratch.mask); cudaFree(e->d_records); cudaFree(e->d_record_count);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
         cudaStreamDestroy(e->stream);
@@ -662,7 +663,7 @@ extern "C" void b200_profile_tail(network *net, int w, int h, float thresh, floa
         launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, 1, 1, e->cand, e->stream);
         B200_CHECK(cudaEventRecord(ev[1], e->stream));
         launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
-                        e->boxes_per_image, &e->nms_scratch, e->stream);
+                        e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, e->stream);
         B200_CHECK(cudaEventRecord(ev[2], e->stream));
         B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));
         launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
@@ -724,6 +725,7 @@ static void ensure_candidates(b200_engine *e, int slots)
 {
     if (e->cand_slots >= slots) return;
     cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
+    cudaFree(e->cand.flags); cudaFree(e->cand.offsets); cudaFree(e->cand.cls_count);
     int cap = e->boxes_per_image, cls = e->classes;
     e->cand.cap = cap; e->cand.classes = cls;
     e->cand.box = (float *)dev_alloc((size_t)slots * cap * 4 * sizeof(float));
@@ -731,6 +733,9 @@ static void ensure_candidates(b200_engine *e, int slots)
     e->cand.prob = (float *)dev_alloc((size_t)slots * cap * cls * sizeof(float));
     e->cand.id = (int *)dev_alloc((size_t)slots * cap * sizeof(int));
     e->cand.count = (int *)dev_alloc((size_t)slots * sizeof(int));
+    e->cand.flags = (unsigned *)dev_alloc((size_t)slots * ((cap + 31) / 32) * sizeof(unsigned));
+    e->cand.offsets = (int *)dev_alloc((size_t)slots * ((cap + 31) / 32) * sizeof(int));
+    e->cand.cls_count = (int *)dev_alloc((size_t)slots * cls * sizeof(int));
     e->cand_slots = slots;
     if (e->h_cap < cap) {
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
@@ -796,7 +801,7 @@ extern "C" int b200_detect_batch(network *net, const float *input, int w, int h,
     if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
     launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, e->cand, e->stream);
     launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
-                    e->boxes_per_image, &e->nms_scratch, e->stream);
+                    e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, e->stream);
     B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));
     launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
                    e->d_records, max_out, e->d_record_count, e->stream);
@@ -834,10 +839,11 @@ extern "C" void b200_nms_sort_arrays(const float *boxes, float *probs, int n, in
     float *d_prob = (float *)dev_alloc((size_t)n * classes * sizeof(float));
     B200_CHECK(cudaMemcpyAsync(d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
     B200_CHECK(cudaMemcpyAsync(d_prob, probs, (size_t)n * classes * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
-    launch_nms_sort(d_box, d_prob, nullptr, nullptr, 1, n, classes, thresh, n, &g_nms_scratch, g_nms_stream);
+    int *d_cls = (int *)dev_alloc((size_t)classes * sizeof(int));
+    launch_nms_sort(d_box, d_prob, nullptr, nullptr, 1, n, classes, thresh, n, &g_nms_scratch, d_cls, g_nms_stream);
     B200_CHECK(cudaMemcpyAsync(probs, d_prob, (size_t)n * classes * sizeof(float), cudaMemcpyDeviceToHost, g_nms_stream));
     B200_CHECK(cudaStreamSynchronize(g_nms_stream));
-    cudaFree(d_box); cudaFree(d_prob);
+    cudaFree(d_box); cudaFree(d_prob); cudaFree(d_cls);
 }
 
 extern "C" void b200_nms_obj_arrays(const float *boxes, float *objectness, int n, float thresh, unsigned char *suppressed)

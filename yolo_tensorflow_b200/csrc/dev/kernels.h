@@ -70,6 +70,9 @@ struct CandBuffers {
     float *prob;       // [batch][cap][classes]
     int   *id;         // [batch][cap] global box id
     int   *count;      // [batch]
+    unsigned *flags;   // [batch][ceil(cap/32)] keep bitmap (decode scratch)
+    int   *offsets;    // [batch][ceil(cap/32)+1] exclusive prefix of the bitmap popcounts (decode scratch)
+    int   *cls_count;  // [batch][classes] live detections with a non-zero score per class (NMS scheduling)
     int cap, classes;
 };
 // mode 0 = reference get_network_boxes semantics (yolo: obj>thresh only; region/detection: every box)
@@ -80,7 +83,7 @@ void launch_count_yolo(const HeadDesc *heads_dev, int nheads, int image, float t
 
 struct NmsScratch { unsigned *mask; size_t words_per_cta; int ctas; };
 void launch_nms_sort(const float *box, float *prob, const float *obj, const int *count, int images, int cap,
-                     int classes, float thresh, int max_count, NmsScratch *scratch, cudaStream_t s);
+                     int classes, float thresh, int max_count, NmsScratch *scratch, int *cls_count, cudaStream_t s);
 void launch_nms_obj(const float *box, float *obj, float *prob, const int *count, int images, int cap, int classes,
                     float thresh, int max_count, NmsScratch *scratch, cudaStream_t s);
 // gathers surviving (box,class) pairs into compact records; returns via counter

@@ -3,7 +3,8 @@
 // Reference algorithm, per class k: order the live detections by prob[k] descending (qsort with nms_comparator,
 // box.c:6-19), then greedily, for each i with prob[k] != 0, zero prob[k] of every later j whose
 // box_iou(i,j) > thresh (strict, fp32, box.c:152-182).  Classes are independent (class k only reads/writes
-// prob[k] and the boxes), so every (image, class) pair is one unit of work for one CTA:
+// prob[k] and the boxes), so every (image, class) pair is one unit of work for one CTA (a 64-thread CTA with
+// everything in shared memory when the class has <= 128 survivors, the general kernel below otherwise):
 //   1. ordered gather of the detections with prob[k] != 0 (warp-ballot compaction keeps the original order),
 //   2. rank sort, descending, ties broken by original index (a stable order; the reference's qsort leaves tie
 //      order unspecified, and entries with prob 0 can never suppress or be suppressed so they are not sorted),
@@ -34,6 +35,18 @@ __device__ __forceinline__ float iou_ref(float4 a, float4 b)      // (x,y,w,h) c
     float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
     return __fdiv_rn(inter, uni);
+}
+
+// box_iou(a,b) > thresh, bit-exact, without paying for the division when the boxes do not intersect: then the
+// reference computes 0/union = 0 (or 0/0 = NaN), and neither exceeds a non-negative threshold.
+__device__ __forceinline__ bool suppresses(float4 a, float4 b, float thresh)
+{
+    float w = overlap_ref(a.x, a.z, b.x, b.z);
+    float h = overlap_ref(a.y, a.w, b.y, b.w);
+    if (thresh >= 0.f && (w < 0 || h < 0 || w == 0.f || h == 0.f)) return false;
+    float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    return __fdiv_rn(inter, uni) > thresh;
 }
 
 // layout of the per-unit work area (either dynamic shared memory or the CTA's HBM slab)
@@ -68,11 +81,11 @@ __device__ __forceinline__ NmsWork carve(unsigned char *base, int m)
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float *__restrict__ obj,
            const int *__restrict__ count, int images, int cap, int classes, int score_stride, float thresh,
-           unsigned char *__restrict__ slab, size_t slab_bytes, unsigned char *__restrict__ suppressed_out)
+           unsigned char *__restrict__ slab, size_t slab_bytes, unsigned char *__restrict__ suppressed_out,
+           const int *__restrict__ cls_count, int small_limit)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int warp_totals[NMS_THREADS / 32];
-    __shared__ int s_m;
     // removed bitset for up to 32768 candidates lives at the front of dynamic smem (4 KB)
     unsigned *removed = (unsigned *)smem;
     unsigned char *smem_work = smem + 4096;
@@ -85,17 +98,9 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
         float *uscore = score + (size_t)img * cap * score_stride + k;
         const float *uobj = obj ? obj + (size_t)img * cap : nullptr;
 
-        // ---- pass A: count survivors (decides where the work area lives)
-        int m = 0;
-        for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
-            int i = i0 + threadIdx.x;
-            bool f = i < n && uscore[(size_t)i * score_stride] != 0.f && (!uobj || uobj[i] != 0.f);
-            unsigned b = __ballot_sync(0xffffffffu, f);
-            if (lane == 0) warp_totals[warp] = __popc(b);
-            __syncthreads();
-            for (int w = 0; w < NMS_THREADS / 32; ++w) m += warp_totals[w];
-            __syncthreads();
-        }
+        // ---- survivors of this class (counted by class_count_kernel); units the small kernel handles are skipped
+        int m = cls_count[unit];
+        if (m <= small_limit) continue;
         if (m <= 1) continue;                                   // nothing can be suppressed
         unsigned char *base = (m <= NMS_SMEM_M) ? smem_work : slab + (size_t)blockIdx.x * slab_bytes;
         if (m > NMS_SMEM_M && work_bytes(m) > slab_bytes) {     // cannot happen: host sizes the slab from max_count
@@ -146,7 +151,7 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
 #pragma unroll 4
                 for (int b = 0; b < 32; ++b) {
                     int j = j0 + b;
-                    if (j > i && j < m && iou_ref(a, wk.sbox[j]) > thresh) bits |= 1u << b;
+                    if (j > i && j < m && suppresses(a, wk.sbox[j], thresh)) bits |= 1u << b;
                 }
             }
             wk.mask[(size_t)i * words + wj] = bits;
@@ -177,6 +182,116 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// scheduling pre-pass: live detections with a non-zero score, per (image, class)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+class_count_kernel(const float *__restrict__ score, const float *__restrict__ obj, const int *__restrict__ count, int cap,
+                   int classes, int score_stride, int *__restrict__ cls_count)
+{
+    // grid = (slices, images); cls_count was zeroed by the launcher
+    extern __shared__ int sm_counts[];
+    const int img = blockIdx.y;
+    const int n = count ? count[img] : cap;
+    for (int k = threadIdx.x; k < classes; k += blockDim.x) sm_counts[k] = 0;
+    __syncthreads();
+    const long long total = (long long)n * classes;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(e / classes), k = (int)(e % classes);
+        float sc = score[((size_t)img * cap + i) * score_stride + k];
+        if (sc != 0.f && (!obj || obj[(size_t)img * cap + i] != 0.f)) atomicAdd(&sm_counts[k], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < classes; k += blockDim.x)
+        if (sm_counts[k]) atomicAdd(&cls_count[(size_t)img * classes + k], sm_counts[k]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small units (2 <= m <= NMS_SMALL_M survivors in the class): one 128-thread CTA per (image, class), everything in
+// ~15 KB of shared memory, so thousands of units are in flight at once (the work is latency-bound, not throughput-bound).
+// Same algorithm and the same bit-exact IoU as nms_kernel.
+// ---------------------------------------------------------------------------------------------------
+#define NMS_SMALL_M 256
+#define NMS_SMALL_THREADS 128
+
+__global__ void __launch_bounds__(NMS_SMALL_THREADS)
+nms_small_kernel(const float *__restrict__ box, float *__restrict__ score, const float *__restrict__ obj,
+                 const int *__restrict__ count, int cap, int classes, int score_stride, float thresh,
+                 const int *__restrict__ cls_count, unsigned char *__restrict__ suppressed_out)
+{
+    const int unit = blockIdx.x;
+    const int m = cls_count[unit];
+    if (m <= 1 || m > NMS_SMALL_M) return;
+    __shared__ float s_score[NMS_SMALL_M];
+    __shared__ int s_src[NMS_SMALL_M], s_order[NMS_SMALL_M];
+    __shared__ float4 s_box[NMS_SMALL_M];
+    __shared__ unsigned s_mask[NMS_SMALL_M][NMS_SMALL_M / 32];
+    __shared__ unsigned s_removed[NMS_SMALL_M / 32];
+    __shared__ int s_warp_tot[NMS_SMALL_THREADS / 32];
+    const int img = unit / classes, k = unit % classes;
+    const int n = count ? count[img] : cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *ubox = box + (size_t)img * cap * 4;
+    float *uscore = score + (size_t)img * cap * score_stride + k;
+    const float *uobj = obj ? obj + (size_t)img * cap : nullptr;
+
+    int written = 0;                                            // ordered gather
+    for (int i0 = 0; i0 < n; i0 += NMS_SMALL_THREADS) {
+        int i = i0 + threadIdx.x;
+        float sc = i < n ? uscore[(size_t)i * score_stride] : 0.f;
+        bool f = i < n && sc != 0.f && (!uobj || uobj[i] != 0.f);
+        unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp_tot[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < NMS_SMALL_THREADS / 32; ++w) { int c = s_warp_tot[w]; if (w < warp) before += c; tot += c; }
+        if (f) { int d = written + before + __popc(b & ((1u << lane) - 1)); if (d < NMS_SMALL_M) { s_score[d] = sc; s_src[d] = i; } }
+        written += tot;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < m; i += NMS_SMALL_THREADS) {  // rank sort: descending score, ties by original order
+        float si = s_score[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) { float sj = s_score[j]; rank += (sj > si) || (sj == si && j < i); }
+        int d = s_src[i];
+        s_order[rank] = d;
+        s_box[rank] = *reinterpret_cast<const float4 *>(ubox + (size_t)d * 4);
+    }
+    if (threadIdx.x < NMS_SMALL_M / 32) s_removed[threadIdx.x] = 0u;
+    __syncthreads();
+    const int words = (m + 31) / 32;
+    for (int t = threadIdx.x; t < m * words; t += NMS_SMALL_THREADS) {
+        int i = t / words, wj = t % words;
+        unsigned bits = 0u;
+        if (wj * 32 + 31 > i) {
+            float4 a = s_box[i];
+            for (int b = 0; b < 32; ++b) {
+                int j = wj * 32 + b;
+                if (j > i && j < m && suppresses(a, s_box[j], thresh)) bits |= 1u << b;
+            }
+        }
+        s_mask[i][wj] = bits;
+    }
+    __syncthreads();
+    if (warp == 0) {                                            // greedy scan, removed set in one register per lane < words
+        unsigned rem = 0u;
+        for (int i = 0; i < m; ++i) {
+            unsigned r = __shfl_sync(0xffffffffu, rem, i >> 5);
+            if (!((r >> (i & 31)) & 1u) && lane < words) rem |= s_mask[i][lane];
+        }
+        if (lane < words) s_removed[lane] = rem;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += NMS_SMALL_THREADS) {
+        if ((s_removed[i >> 5] >> (i & 31)) & 1u) {
+            int d = s_order[i];
+            uscore[(size_t)d * score_stride] = 0.f;
+            if (suppressed_out) suppressed_out[(size_t)img * cap + d] = 1;
+        }
+    }
+}
+
 static size_t host_work_bytes(int m)
 {
     size_t words = (m + 31) / 32;
@@ -195,12 +310,18 @@ static void ensure_scratch(NmsScratch *sc, int max_count, int ctas)
 }
 
 static void run_nms(const float *box, float *score, const float *obj, const int *count, int images, int cap, int classes,
-                    int stride, float thresh, int max_count, NmsScratch *scratch, unsigned char *supp, cudaStream_t s)
+                    int stride, float thresh, int max_count, NmsScratch *scratch, unsigned char *supp, int *cls_count, cudaStream_t s)
 {
     if (max_count > 32768) { fprintf(stderr, "b200-darknet: nms supports at most 32768 candidates per image\n"); abort(); }
     int units = images * classes;
+    if (units < 1) return;
+    B200_CHECK(cudaMemsetAsync(cls_count, 0, (size_t)units * sizeof(int), s));
+    class_count_kernel<<<dim3(8, images), 256, classes * sizeof(int), s>>>(score, obj, count, cap, classes, stride, cls_count);
+    B200_LAUNCHED();
+    nms_small_kernel<<<units, NMS_SMALL_THREADS, 0, s>>>(box, score, obj, count, cap, classes, stride, thresh, cls_count, supp);
+    B200_LAUNCHED();
+    if (max_count <= NMS_SMALL_M) return;                       // no class can exceed the small kernel's capacity
     int ctas = units < 148 * 2 ? units : 148 * 2;
-    if (ctas < 1) return;
     ensure_scratch(scratch, max_count, ctas);
     size_t smem = 4096 + host_work_bytes(NMS_SMEM_M);
     static bool attr_set = false;
@@ -209,14 +330,14 @@ static void run_nms(const float *box, float *score, const float *obj, const int 
         attr_set = true;
     }
     nms_kernel<<<ctas, NMS_THREADS, smem, s>>>(box, score, obj, count, images, cap, classes, stride, thresh,
-                                               (unsigned char *)scratch->mask, scratch->words_per_cta, supp);
+                                               (unsigned char *)scratch->mask, scratch->words_per_cta, supp, cls_count, NMS_SMALL_M);
     B200_LAUNCHED();
 }
 
 void launch_nms_sort(const float *box, float *prob, const float *obj, const int *count, int images, int cap,
-                     int classes, float thresh, int max_count, NmsScratch *scratch, cudaStream_t s)
+                     int classes, float thresh, int max_count, NmsScratch *scratch, int *cls_count, cudaStream_t s)
 {
-    run_nms(box, prob, obj, count, images, cap, classes, classes, thresh, max_count, scratch, nullptr, s);
+    run_nms(box, prob, obj, count, images, cap, classes, classes, thresh, max_count, scratch, nullptr, cls_count, s);
 }
 
 // do_nms_obj: one class-agnostic pass ordered by objectness; a suppressed detection loses objectness and all probs
@@ -235,9 +356,11 @@ void launch_nms_obj(const float *box, float *obj, float *prob, const int *count,
                     float thresh, int max_count, NmsScratch *scratch, cudaStream_t s)
 {
     unsigned char *supp = nullptr;
+    int *cls_count = nullptr;
     B200_CHECK(cudaMallocAsync((void **)&supp, (size_t)images * cap, s));
+    B200_CHECK(cudaMallocAsync((void **)&cls_count, (size_t)images * sizeof(int), s));
     B200_CHECK(cudaMemsetAsync(supp, 0, (size_t)images * cap, s));
-    run_nms(box, obj, nullptr, count, images, cap, 1, 1, thresh, max_count, scratch, supp, s);
+    run_nms(box, obj, nullptr, count, images, cap, 1, 1, thresh, max_count, scratch, supp, cls_count, s);
     if (prob) {
         long long total = (long long)images * cap * classes;
         int grid = (int)((total + 255) / 256);
@@ -246,27 +369,30 @@ void launch_nms_obj(const float *box, float *obj, float *prob, const int *count,
         B200_LAUNCHED();
     }
     B200_CHECK(cudaFreeAsync(supp, s));
+    B200_CHECK(cudaFreeAsync(cls_count, s));
 }
 
 // ---------------------------------------------------------------------------------------------------
 // collect: surviving (detection, class) pairs -> compact records (one atomic slot per warp-ballot group)
 // ---------------------------------------------------------------------------------------------------
-__global__ void collect_kernel(const float *__restrict__ box, const float *__restrict__ prob, const float *__restrict__ obj,
-                               const int *__restrict__ id, const int *__restrict__ count, int images, int cap, int classes,
-                               DetRecord *__restrict__ out, int max_out, int *__restrict__ out_count)
+__global__ void __launch_bounds__(256)
+collect_kernel(const float *__restrict__ box, const float *__restrict__ prob, const float *__restrict__ obj,
+               const int *__restrict__ id, const int *__restrict__ count, int images, int cap, int classes,
+               DetRecord *__restrict__ out, int max_out, int *__restrict__ out_count)
 {
-    const long long total = (long long)images * cap * classes;
-    const int lane = threadIdx.x & 31;
-    for (long long t0 = blockIdx.x * (long long)blockDim.x; t0 < total; t0 += (long long)gridDim.x * blockDim.x) {
+    // grid = (slices, images): only the count[img] live candidates of an image are visited
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const long long total = (long long)count[img] * classes;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x; t0 < total; t0 += step) {
         long long t = t0 + threadIdx.x;
         bool f = false;
-        int img = 0, i = 0, k = 0;
+        int i = 0, k = 0;
         float p = 0.f;
         if (t < total) {
-            k = (int)(t % classes);
-            long long d = t / classes;
-            img = (int)(d / cap); i = (int)(d % cap);
-            if (i < count[img] && obj[d] != 0.f) { p = prob[t]; f = p != 0.f; }
+            i = (int)(t / classes); k = (int)(t % classes);
+            size_t d = (size_t)img * cap + i;
+            if (obj[d] != 0.f) { p = prob[d * classes + k]; f = p != 0.f; }
         }
         unsigned b = __ballot_sync(0xffffffffu, f);
         int base = 0;
@@ -288,10 +414,8 @@ __global__ void collect_kernel(const float *__restrict__ box, const float *__res
 void launch_collect(const float *box, const float *prob, const float *obj, const int *id, const int *count, int images,
                     int cap, int classes, DetRecord *out, int max_out, int *out_count, cudaStream_t s)
 {
-    long long total = (long long)images * cap * classes;
-    int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 8) grid = 148 * 8;
-    if (grid < 1) grid = 1;
+    if (images < 1) return;
+    dim3 grid(8, images);
     collect_kernel<<<grid, 256, 0, s>>>(box, prob, obj, id, count, images, cap, classes, out, max_out, out_count);
     B200_LAUNCHED();
 }
