@@ -189,6 +189,7 @@ struct ConvTcArgs {
     int tmem_cols;
     int act;
     int resident_b;          // 1: the whole [block_n x K] weight slab stays in shared memory for the CTA's lifetime
+    int acc_stages;          // TMEM accumulator buffers (2..8): small filter tiles let the MMA run many tiles ahead of the epilogue
     int staged;              // 1: epilogue goes TMEM -> registers -> swizzled smem tile -> TMA store (and TMA-loads the residual)
     int pair;                // 1: cta_group::2 kernel (two CTAs share one 256 x block_n accumulator tile and its weights)
     long long npix;
@@ -400,7 +401,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
     if (staged && ep_tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -420,12 +421,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
     uint8_t *aux = sC + (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0);
     uint64_t *full = (uint64_t *)aux;                 // [stages]
     uint64_t *empty = full + 8;                       // [stages]
-    uint64_t *tfull = empty + 8;                      // [2]
-    uint64_t *tempty = tfull + 2;                     // [2]
-    uint64_t *wfull = tempty + 2;                     // resident weights landed
+    uint64_t *tfull = empty + 8;                      // [acc_stages <= 8]
+    uint64_t *tempty = tfull + 8;                     // [acc_stages <= 8]
+    uint64_t *wfull = tempty + 8;                     // resident weights landed
     uint64_t *rfull = wfull + 1;                      // residual tile landed (staged epilogue)
     uint32_t *tmem_slot = (uint32_t *)(rfull + 1);
-    float *s_scale = (float *)(aux + 256);            // [2][256]
+    float *s_scale = (float *)(aux + 512);            // [2][256]
     float *s_shift = s_scale + 512;                   // [2][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -433,7 +434,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < args.acc_stages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         mbar_init(wfull, 1);
         mbar_init(rfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -513,7 +514,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull[acc]);                       // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -551,10 +552,10 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
     uint64_t *full = (uint64_t *)aux;
     uint64_t *empty = full + 8;
     uint64_t *tfull = empty + 8;
-    uint64_t *tempty = tfull + 2;
-    uint64_t *rfull = tempty + 3;
+    uint64_t *tempty = tfull + 8;
+    uint64_t *rfull = tempty + 9;
     uint32_t *tmem_slot = (uint32_t *)(rfull + 1);
-    float *s_scale = (float *)(aux + 256);
+    float *s_scale = (float *)(aux + 512);
     float *s_shift = s_scale + 512;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -566,7 +567,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        for (int i = 0; i < args.acc_stages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         mbar_init(rfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -639,7 +640,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 tc2_commit_both(&tfull[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -872,7 +873,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     // where a shortcut is fused: the per-row residual reads of the direct epilogue are what made fused layers slow.
     const int a_bytes_ = 128 * block_k * 2;
     const int sc_bytes = (a.block_n / 64) * 16384;
-    const int budget_all = 227 * 1024 - 1024 - (256 + 4096);
+    const int budget_all = 227 * 1024 - 1024 - (512 + 4096);
     const bool want_staged = residual && !getenv("B200_NO_STAGED") && out.dtype == DT_BF16 && a.block_n % 64 == 0 && cp.cout_pad % 64 == 0;
     const long long slab_ = (long long)a.num_kblocks * ((a.block_n * block_k * 2 + 1023) / 1024 * 1024);
     const bool could_reside = a.n_tiles == 1 && !getenv("B200_NO_RESIDENT_B") &&
@@ -889,7 +890,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     // ---- smem / tmem budget ----
     const int a_bytes = 128 * block_k * 2;
     a.b_stage_bytes = ((a.pair ? a.block_n / 2 : a.block_n) * block_k * 2 + 1023) / 1024 * 1024;
-    const int aux_bytes = 256 + 2 * 512 * 4;
+    const int aux_bytes = 512 + 2 * 512 * 4;
     int budget = 227 * 1024 - 1024 - aux_bytes;
     a.staged = 0;
     if (want_staged) {
@@ -916,7 +917,14 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         encode_tile_view(&p->maps.c, out, cp.cout_pad, a);
         if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a);
     }
-    int cols = 2 * a.block_n;
+    a.acc_stages = 2;
+    // deeper accumulator rings were measured (YOLOv3-416 b64) to give no gain on the small-filter layers: they are bound
+    // by the TMA row rate, not by the MMA->epilogue hand-off.  Kept switchable for experiments.
+    if (a.n_tiles == 1 && getenv("B200_DEEP_TMEM")) {   // per-tile constants are hoisted, so any number of buffers works
+        int fit = 512 / a.block_n;
+        a.acc_stages = fit >= 8 ? 8 : (fit >= 4 ? 4 : 2);
+    }
+    int cols = a.acc_stages * a.block_n;
     a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     int tiles = a.m_tiles * a.n_tiles;
     p->grid = tiles < 148 ? tiles : 148;

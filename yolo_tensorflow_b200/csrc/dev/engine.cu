@@ -28,6 +28,8 @@ struct DevLayer {
     int cout_pad;
     ConvTcPlan *tc;
     bool stem;
+    int stem_kpad;             // > 0: first layer runs as im2col (fp32 NCHW -> bf16 [pixels][kpad]) + dense tcgen05 GEMM
+    bf16 *stem_cols;
     int fused_into;            // conv whose epilogue also performs shortcut layer `fused_into` (its own output is not materialised)
     bool fused_away;           // shortcut executed inside the previous conv's epilogue
     std::string kernel;
@@ -228,7 +230,13 @@ static void build_engine_device_state(b200_engine *e, network *net)
         DevLayer &d = e->L[i];
         if (l.type == CONVOLUTIONAL) {
             d.cout_pad = (int)align_up(l.n, 16);
-            d.w_bytes = (size_t)d.cout_pad * l.size * l.size * l.c * esize;
+            // experimental: first layer as im2col + dense tcgen05 GEMM (B200_STEM_TC=1).  Measured slower than the
+            // specialised CUDA-core kernel on YOLOv3-416 b64 (1.25 + 0.61 ms vs 0.83 ms), so it is off by default.
+            if (i == 0 && d.stem && e->precision == B200_PREC_BF16 && getenv("B200_STEM_TC")) {
+                int kpad = (int)align_up(l.size * l.size * l.c, 32);
+                if (kpad <= 160) d.stem_kpad = kpad;
+            }
+            d.w_bytes = (size_t)d.cout_pad * (d.stem_kpad ? d.stem_kpad : l.size * l.size * l.c) * esize;
             d.w_off = off; off = align_up(off + d.w_bytes, 256);
             d.scale_off = off; off = align_up(off + d.cout_pad * sizeof(float), 256);
             d.shift_off = off; off = align_up(off + d.cout_pad * sizeof(float), 256);
@@ -266,6 +274,14 @@ static void build_engine_device_state(b200_engine *e, network *net)
                 abort();
             }
             d.kernel = d.stem ? "conv_stem" : "conv_simt";
+            if (d.stem && d.stem_kpad) {
+                d.stem_cols = (bf16 *)dev_alloc((size_t)e->cap * l.out_h * l.out_w * d.stem_kpad * sizeof(bf16));
+                TView cols{d.stem_cols, e->cap, l.out_h, l.out_w, d.stem_kpad, d.stem_kpad, DT_BF16};
+                ConvParams p1{1, 1, 0, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
+                d.tc = conv_tc_plan_create(cols, d.out, p1, nullptr, 1.f, 1.f);
+                if (d.tc) d.kernel = "im2col+conv_tc";
+                else { cudaFree(d.stem_cols); d.stem_cols = nullptr; d.stem_kpad = -1; }   // -1: weights already sized for kpad; not reachable in practice
+            }
             if (!d.stem && e->precision == B200_PREC_BF16) {
                 ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
                 if (d.fused_into >= 0) {
@@ -334,7 +350,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.owns_out = false; d.fused_into = -1; d.fused_away = false; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; }
     e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
@@ -368,6 +384,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         for (auto &d : e->L) {
             if (d.tc) conv_tc_plan_destroy(d.tc);
             if (d.owns_out) cudaFree(d.out.p);
+            cudaFree(d.stem_cols);
             if (d.head_out && d.type != DROPOUT) cudaFree(d.head_out);
         }
         cudaFree(e->d_input); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
@@ -412,7 +429,7 @@ extern "C" void b200_engine_upload_weights(b200_engine *e, network *net)
         const layer &l = net->layers[i];
         DevLayer &d = e->L[i];
         if (l.type == CONVOLUTIONAL) {
-            const int K = l.size * l.size * l.c;
+            const int K = d.stem_kpad > 0 ? d.stem_kpad : l.size * l.size * l.c;      // the im2col stem pads K with zeros
             unsigned char *w = host.data() + d.w_off;
             for (int o = 0; o < l.n; ++o)
                 for (int c = 0; c < l.c; ++c)
@@ -472,7 +489,10 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
     switch (l.type) {
     case CONVOLUTIONAL: {
         ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
-        if (d.stem) launch_conv_stem(e->d_input, batch, l.h, l.w, l.c, out, p, s);
+        if (d.stem && d.tc && e->conv_backend == 0) {
+            launch_stem_im2col(e->d_input, batch, l.h, l.w, l.c, d.stem_cols, l.out_h, l.out_w, d.stem_kpad, l.size, l.stride, l.pad, s);
+            launch_conv_tc(d.tc, s);
+        } else if (d.stem) launch_conv_stem(e->d_input, batch, l.h, l.w, l.c, out, p, s);
         else if (d.tc && e->conv_backend == 0) launch_conv_tc(d.tc, s);
         else launch_conv_simt(in, out, p, s);
         break;
@@ -576,8 +596,8 @@ extern "C" void b200_set_conv_backend(network *net, int backend)
 {
     b200_engine *e = b200_engine_of(net);
     for (auto &d : e->L)
-        if (backend != 0 && d.fused_into >= 0) {
-            fprintf(stderr, "b200-darknet: the CUDA-core conv backend needs an unfused plan (parse with B200_FUSE=0)\n");
+        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0)) {
+            fprintf(stderr, "b200-darknet: the CUDA-core conv backend needs an unfused plan (parse with B200_FUSE=0 B200_STEM_SIMT=1)\n");
             abort();
         }
     e->conv_backend = backend;
