@@ -755,7 +755,7 @@ static void ensure_candidates(b200_engine *e, int slots)
     e->cand.count = (int *)dev_alloc((size_t)slots * sizeof(int));
     e->cand.flags = (unsigned *)dev_alloc((size_t)slots * ((cap + 31) / 32) * sizeof(unsigned));
     e->cand.offsets = (int *)dev_alloc((size_t)slots * ((cap + 31) / 32) * sizeof(int));
-    e->cand.cls_count = (int *)dev_alloc((size_t)slots * cls * sizeof(int));
+    e->cand.cls_count = (int *)dev_alloc(((size_t)slots * cls + 1) * sizeof(int));
     e->cand_slots = slots;
     if (e->h_cap < cap) {
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
@@ -859,7 +859,7 @@ extern "C" void b200_nms_sort_arrays(const float *boxes, float *probs, int n, in
     float *d_prob = (float *)dev_alloc((size_t)n * classes * sizeof(float));
     B200_CHECK(cudaMemcpyAsync(d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
     B200_CHECK(cudaMemcpyAsync(d_prob, probs, (size_t)n * classes * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
-    int *d_cls = (int *)dev_alloc((size_t)classes * sizeof(int));
+    int *d_cls = (int *)dev_alloc(((size_t)classes + 1) * sizeof(int));
     launch_nms_sort(d_box, d_prob, nullptr, nullptr, 1, n, classes, thresh, n, &g_nms_scratch, d_cls, g_nms_stream);
     B200_CHECK(cudaMemcpyAsync(probs, d_prob, (size_t)n * classes * sizeof(float), cudaMemcpyDeviceToHost, g_nms_stream));
     B200_CHECK(cudaStreamSynchronize(g_nms_stream));

@@ -18,12 +18,15 @@
 
 #define NMS_THREADS 256
 #define NMS_SMEM_M 512                       // survivors per class whose IoU bit-matrix lives in shared memory
+#define host_smem_work_bytes (512 * 28 + 512 * 16 * 4 + 64)   // == host_work_bytes(NMS_SMEM_M): size of the smem work area
 
 __device__ __forceinline__ float overlap_ref(float x1, float w1, float x2, float w2)
 {
-    float l1 = __fsub_rn(x1, __fdiv_rn(w1, 2.f)), l2 = __fsub_rn(x2, __fdiv_rn(w2, 2.f));
+    // w/2 == w*0.5f exactly in binary floating point (no IEEE division subroutine needed)
+    const float h1 = __fmul_rn(w1, 0.5f), h2 = __fmul_rn(w2, 0.5f);
+    float l1 = __fsub_rn(x1, h1), l2 = __fsub_rn(x2, h2);
     float left = l1 > l2 ? l1 : l2;
-    float r1 = __fadd_rn(x1, __fdiv_rn(w1, 2.f)), r2 = __fadd_rn(x2, __fdiv_rn(w2, 2.f));
+    float r1 = __fadd_rn(x1, h1), r2 = __fadd_rn(x2, h2);
     float right = r1 < r2 ? r1 : r2;
     return __fsub_rn(right, left);
 }
@@ -46,6 +49,11 @@ __device__ __forceinline__ bool suppresses(float4 a, float4 b, float thresh)
     if (thresh >= 0.f && (w < 0 || h < 0 || w == 0.f || h == 0.f)) return false;
     float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    // the fast approximate quotient (<= 2 ulp off) decides every pair that is not within a hair of the threshold;
+    // only those few take the IEEE division the reference performs, so the decision is still bit-exact
+    float q = __fdividef(inter, uni);
+    if (q > thresh * 1.00001f + 1e-30f && q < 3.0e38f) return true;
+    if (q < thresh * 0.99999f - 1e-30f) return false;
     return __fdiv_rn(inter, uni) > thresh;
 }
 
@@ -91,7 +99,19 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
     unsigned char *smem_work = smem + 4096;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (int unit = blockIdx.x; unit < images * classes; unit += gridDim.x) {
+    __shared__ int s_unit;
+    int *next_unit = const_cast<int *>(cls_count) + images * classes;      // work counter behind the class counts (zeroed by the launcher)
+    for (;;) {
+        // dynamic claiming: heavy classes cluster on a few class ids, a static stride would pile them on the same CTAs
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int u;
+            do { u = atomicAdd(next_unit, 1); } while (u < images * classes && cls_count[u] <= small_limit);
+            s_unit = u;
+        }
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= images * classes) break;
         const int img = unit / classes, k = unit % classes;
         const int n = count ? count[img] : cap;
         const float *ubox = box + (size_t)img * cap * 4;
@@ -108,6 +128,14 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
             __trap();
         }
         NmsWork wk = carve(base, m);
+        // slab path: only the bit-matrix has to live in HBM; scores / indices / sorted boxes stay in shared memory when they
+        // fit (28 bytes per survivor), which turns the m^2 box reads of the IoU pass into LDS instead of L1/L2 traffic
+        size_t lists_bytes = 0;
+        if (m > NMS_SMEM_M && (size_t)m * 28 + 64 + 8192 <= (size_t)host_smem_work_bytes) {
+            NmsWork in_smem = carve(smem_work, m);
+            wk.sbox = in_smem.sbox; wk.score = in_smem.score; wk.src = in_smem.src; wk.order = in_smem.order;
+            lists_bytes = ((size_t)m * 28 + 64 + 15) & ~(size_t)15;
+        }
         const int words = (m + 31) / 32;
 
         // ---- pass B: ordered gather
@@ -158,17 +186,48 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
         }
         __syncthreads();
 
-        // ---- greedy scan by warp 0
-        if (warp == 0) {
-            for (int i = 0; i < m; ++i) {
-                unsigned r = removed[i >> 5];
-                if (!((r >> (i & 31)) & 1u)) {
-                    for (int w = (i >> 5) + lane; w < words; w += 32) removed[w] |= wk.mask[(size_t)i * words + w];
+        // ---- greedy scan.  Shared-memory masks: warp 0 walks the rows directly.  HBM-slab masks (m > NMS_SMEM_M): rows are
+        // staged through shared memory a chunk at a time by the whole CTA (one L2 round trip per chunk instead of one
+        // per row; the dependent walk inside a chunk then runs at shared-memory latency).
+        if (m <= NMS_SMEM_M) {
+            if (warp == 0) {
+                for (int i = 0; i < m; ++i) {
+                    unsigned r = removed[i >> 5];
+                    if (!((r >> (i & 31)) & 1u)) {
+                        for (int w = (i >> 5) + lane; w < words; w += 32) removed[w] |= wk.mask[(size_t)i * words + w];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+            }
+            __syncthreads();
+        } else {
+            unsigned *stage = (unsigned *)(smem_work + lists_bytes);  // what is left of the smem work area in the slab path
+            const int stage_words = (int)(((size_t)host_smem_work_bytes - lists_bytes) / 4);
+            int rows_per_chunk = stage_words / words;
+            if (rows_per_chunk > 64) rows_per_chunk = 64;
+            if (rows_per_chunk < 1) rows_per_chunk = 1;
+            for (int i0 = 0; i0 < m; i0 += rows_per_chunk) {
+                const int rows = (m - i0) < rows_per_chunk ? (m - i0) : rows_per_chunk;
+                const int w_lo = i0 >> 5;                            // words left of the diagonal are never read
+                const int span = words - w_lo;
+                for (int t = threadIdx.x; t < rows * span; t += NMS_THREADS) {
+                    int rr = t / span, w = w_lo + t % span;
+                    stage[rr * span + (w - w_lo)] = wk.mask[(size_t)(i0 + rr) * words + w];
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    for (int rr = 0; rr < rows; ++rr) {
+                        const int i = i0 + rr;
+                        unsigned r = removed[i >> 5];
+                        if (!((r >> (i & 31)) & 1u)) {
+                            for (int w = (i >> 5) + lane; w < words; w += 32) removed[w] |= stage[rr * span + (w - w_lo)];
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
             }
         }
-        __syncthreads();
 
         // ---- write back
         for (int i = threadIdx.x; i < m; i += NMS_THREADS) {
@@ -315,7 +374,7 @@ static void run_nms(const float *box, float *score, const float *obj, const int 
     if (max_count > 32768) { fprintf(stderr, "b200-darknet: nms supports at most 32768 candidates per image\n"); abort(); }
     int units = images * classes;
     if (units < 1) return;
-    B200_CHECK(cudaMemsetAsync(cls_count, 0, (size_t)units * sizeof(int), s));
+    B200_CHECK(cudaMemsetAsync(cls_count, 0, ((size_t)units + 1) * sizeof(int), s));      // class counts + the work counter
     class_count_kernel<<<dim3(8, images), 256, classes * sizeof(int), s>>>(score, obj, count, cap, classes, stride, cls_count);
     B200_LAUNCHED();
     nms_small_kernel<<<units, NMS_SMALL_THREADS, 0, s>>>(box, score, obj, count, cap, classes, stride, thresh, cls_count, supp);
@@ -358,7 +417,7 @@ void launch_nms_obj(const float *box, float *obj, float *prob, const int *count,
     unsigned char *supp = nullptr;
     int *cls_count = nullptr;
     B200_CHECK(cudaMallocAsync((void **)&supp, (size_t)images * cap, s));
-    B200_CHECK(cudaMallocAsync((void **)&cls_count, (size_t)images * sizeof(int), s));
+    B200_CHECK(cudaMallocAsync((void **)&cls_count, ((size_t)images + 1) * sizeof(int), s));
     B200_CHECK(cudaMemsetAsync(supp, 0, (size_t)images * cap, s));
     run_nms(box, obj, nullptr, count, images, cap, 1, 1, thresh, max_count, scratch, supp, cls_count, s);
     if (prob) {
