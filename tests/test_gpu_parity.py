@@ -362,6 +362,20 @@ def test_batched_forward_is_per_image_independent(dn, prec, workdir):
         assert np.array_equal(net3.layer_output(i)[0], big[i][2])
 
 
+def test_fused_path_from_raw_logits_is_identical(dn, workdir):
+    """head sync off: b200_detect_batch skips forward_yolo_layer and decodes from the head convs' fp32 logits;
+    the records must be identical to the path that materialises l.output"""
+    net, _, _ = open_net(dn, "yolov3", 3, 160, workdir, dn.PREC_BF16)
+    x = synth.make_images(3, 3, 160, 160, 19)
+    rec1, c1 = net.detect_batch(x, 160, 160, .3, .45)
+    net.set_head_sync(0)
+    rec0, c0 = net.detect_batch(x, 160, 160, .3, .45)
+    assert np.array_equal(c0, c1) and len(rec0) == len(rec1) and len(rec0) > 0
+    key = lambda r: np.lexsort((r["cls"], r["box_id"], r["image"]))
+    a, b = rec0[key(rec0)], rec1[key(rec1)]
+    assert a.tobytes() == b.tobytes()
+
+
 def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
     net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
     x = synth.make_images(2, 3, 160, 160, 41)

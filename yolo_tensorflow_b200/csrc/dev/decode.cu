@@ -65,13 +65,23 @@ __device__ __forceinline__ int find_head(const HeadDesc *heads, int nheads, int 
     return hi;
 }
 
+// entry e of anchor a at `cell` of a YOLO head, either from l.output (activations already applied by forward_yolo_layer)
+// or straight from the head convolution's logits with the same double-precision logistic (activations.h:32) on the fly
+__device__ __forceinline__ float yolo_entry(const HeadDesc &hd, const float *pred, int img, int a, int e, int cell, int use_raw)
+{
+    const int wh = hd.w * hd.h;
+    if (!use_raw) return pred[(size_t)a * wh * (hd.classes + 5) + (size_t)e * wh + cell];
+    float v = hd.raw[((size_t)img * wh + cell) * hd.raw_ld + a * (hd.classes + 5) + e];
+    return (e == 2 || e == 3) ? v : (float)(1. / (1. + exp(-(double)v)));
+}
+
 __device__ __forceinline__ bool box_keep(const HeadDesc &hd, const float *pred, int t, float thresh, int mode, float &objectness,
-                                         float &scale, int &cell, int &a)
+                                         float &scale, int &cell, int &a, int img = 0, int use_raw = 0)
 {
     const int wh = hd.w * hd.h;
     if (hd.type == YOLO) {
         cell = t / hd.n; a = t % hd.n;
-        objectness = pred[(size_t)a * wh * (hd.classes + 5) + 4 * wh + cell];
+        objectness = yolo_entry(hd, pred, img, a, 4, cell, use_raw);
         scale = objectness;
         return objectness > thresh;
     }
@@ -89,7 +99,7 @@ __device__ __forceinline__ bool box_keep(const HeadDesc &hd, const float *pred, 
 
 __global__ void __launch_bounds__(256)
 decode_flags_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, int boxes, int words, float thresh, int mode,
-                    unsigned *__restrict__ flags)
+                    int use_raw, unsigned *__restrict__ flags)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int img = first_image + blockIdx.y;
@@ -98,7 +108,7 @@ decode_flags_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_im
         int local;
         const HeadDesc &hd = heads[find_head(heads, nheads, t, local)];
         float o, s; int cell, a;
-        keep = box_keep(hd, hd.out + (size_t)img * hd.outputs, local, thresh, mode, o, s, cell, a);
+        keep = box_keep(hd, hd.out + (size_t)img * hd.outputs, local, thresh, mode, o, s, cell, a, img, use_raw);
     }
     unsigned b = __ballot_sync(0xffffffffu, keep);
     if ((threadIdx.x & 31) == 0 && (t >> 5) < words) flags[(size_t)blockIdx.y * words + (t >> 5)] = b;
@@ -137,7 +147,7 @@ decode_scan_kernel(const unsigned *__restrict__ flags, int words, int cap, int *
 
 __global__ void __launch_bounds__(256)
 decode_emit_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, int boxes, int words, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, const unsigned *__restrict__ flags,
+                   int imw, int imh, float thresh, int relative, int mode, int use_raw, const unsigned *__restrict__ flags,
                    const int *__restrict__ offsets, CandBuffers cb)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,16 +161,17 @@ decode_emit_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_ima
     const HeadDesc &hd = heads[find_head(heads, nheads, t, local)];
     const float *pred = hd.out + (size_t)img * hd.outputs;
     float objectness, scale; int cell, a;
-    box_keep(hd, pred, local, thresh, mode, objectness, scale, cell, a);
+    box_keep(hd, pred, local, thresh, mode, objectness, scale, cell, a, img, use_raw);
     const int wh = hd.w * hd.h;
     const int row = cell / hd.w, col = cell % hd.w;
     BoxF b;
     if (hd.type == YOLO) {
-        const float *e = pred + (size_t)a * wh * (hd.classes + 5) + cell;
-        b.x = __fdiv_rn(__fadd_rn((float)col, e[0]), (float)hd.w);
-        b.y = __fdiv_rn(__fadd_rn((float)row, e[wh]), (float)hd.h);
-        b.w = (float)(exp((double)e[2 * wh]) * (double)hd.anchors[2 * a] / netw);
-        b.h = (float)(exp((double)e[3 * wh]) * (double)hd.anchors[2 * a + 1] / neth);
+        const float e0 = yolo_entry(hd, pred, img, a, 0, cell, use_raw), e1 = yolo_entry(hd, pred, img, a, 1, cell, use_raw);
+        const float e2 = yolo_entry(hd, pred, img, a, 2, cell, use_raw), e3 = yolo_entry(hd, pred, img, a, 3, cell, use_raw);
+        b.x = __fdiv_rn(__fadd_rn((float)col, e0), (float)hd.w);
+        b.y = __fdiv_rn(__fadd_rn((float)row, e1), (float)hd.h);
+        b.w = (float)(exp((double)e2) * (double)hd.anchors[2 * a] / netw);
+        b.h = (float)(exp((double)e3) * (double)hd.anchors[2 * a + 1] / neth);
         b = correct_box(b, imw, imh, netw, neth, relative);
     } else if (hd.type == REGION) {
         const float *e = pred + (size_t)a * wh * (hd.coords + hd.classes + 1) + cell;
@@ -184,7 +195,7 @@ decode_emit_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_ima
 
 // class probabilities of the survivors: one warp per survivor, lanes over classes (coalesced writes, 32 loads in flight)
 __global__ void __launch_bounds__(256)
-decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, float thresh, int mode, CandBuffers cb)
+decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, float thresh, int mode, int use_raw, CandBuffers cb)
 {
     const int slot = blockIdx.y, img = first_image + blockIdx.y, lane = threadIdx.x & 31;
     const int n = cb.count[slot];
@@ -193,12 +204,12 @@ decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_im
         const HeadDesc &hd = heads[find_head(heads, nheads, cb.id[(size_t)slot * cb.cap + d], local)];
         const float *pred = hd.out + (size_t)img * hd.outputs;
         float objectness, scale; int cell, a;
-        box_keep(hd, pred, local, thresh, mode, objectness, scale, cell, a);
+        box_keep(hd, pred, local, thresh, mode, objectness, scale, cell, a, img, use_raw);
         const int wh = hd.w * hd.h;
         float *pr = cb.prob + ((size_t)slot * cb.cap + d) * cb.classes;
         for (int j = lane; j < hd.classes; j += 32) {
             float p;
-            if (hd.type == YOLO) p = __fmul_rn(objectness, pred[(size_t)a * wh * (hd.classes + 5) + (size_t)(5 + j) * wh + cell]);
+            if (hd.type == YOLO) p = __fmul_rn(objectness, yolo_entry(hd, pred, img, a, 5 + j, cell, use_raw));
             else if (hd.type == REGION) p = objectness != 0.f ? __fmul_rn(scale, pred[(size_t)a * wh * (hd.coords + hd.classes + 1) + (size_t)(hd.coords + 1 + j) * wh + cell]) : 0.f;
             else p = __fmul_rn(scale, pred[cell * hd.classes + j]);
             pr[j] = p > thresh ? p : 0.f;
@@ -207,19 +218,19 @@ decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_im
 }
 
 void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, CandBuffers cb, cudaStream_t s)
+                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s)
 {
     const int boxes = cb.cap;                                       // cap == anchor boxes per image
     const int words = (boxes + 31) / 32;
     dim3 grid(div_up(boxes, 256), nimages);
-    decode_flags_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, thresh, mode, cb.flags);
+    decode_flags_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, thresh, mode, use_raw, cb.flags);
     B200_LAUNCHED();
     decode_scan_kernel<<<nimages, 1024, 0, s>>>(cb.flags, words, cb.cap, cb.offsets, cb.count);
     B200_LAUNCHED();
     decode_emit_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, netw, neth, imw, imh, thresh, relative, mode,
-                                            cb.flags, cb.offsets, cb);
+                                            use_raw, cb.flags, cb.offsets, cb);
     B200_LAUNCHED();
-    decode_probs_kernel<<<dim3(8, nimages), 256, 0, s>>>(heads_dev, nheads, first_image, thresh, mode, cb);
+    decode_probs_kernel<<<dim3(8, nimages), 256, 0, s>>>(heads_dev, nheads, first_image, thresh, mode, use_raw, cb);
     B200_LAUNCHED();
 }
 

@@ -41,6 +41,8 @@ struct b200_engine {
     int device;
     int conv_backend, head_sync, fusion;
     cudaStream_t stream;
+    cudaStream_t copy_stream;  // H2D of the input batch, chunked so the first layer starts while later images are still in flight
+    cudaEvent_t copy_done[8];
     std::vector<DevLayer> L;
     float *d_input;            // fp32 NCHW network input [cap][inputs]
     TView in_view;             // NHWC copy of the input (only when layer 0 is not a stem conv)
@@ -52,6 +54,7 @@ struct b200_engine {
     std::vector<HeadDesc> heads;
     HeadDesc *d_heads;
     int boxes_per_image, classes;
+    bool raw_decode_ok;        // every head is a [yolo] layer fed by an fp32-logit convolution: the fused path may skip yolo_forward
     CandBuffers cand;          // device
     int cand_slots;
     NmsScratch nms_scratch;
@@ -139,6 +142,8 @@ static void build_engine_device_state(b200_engine *e, network *net)
     require_device(net->gpu_index);
     B200_CHECK(cudaGetDevice(&e->device));
     B200_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    B200_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : e->copy_done) B200_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     const int esize = (int)dt_size(e->act_dtype);
     auto cons = consumers_of(net);
 
@@ -313,6 +318,7 @@ static void build_engine_device_state(b200_engine *e, network *net)
 
     // ---- heads for decode ---------------------------------------------------------------------------------------
     int base = 0;
+    e->raw_decode_ok = !getenv("B200_NO_RAW_DECODE");
     for (int i = 0; i < net->n; ++i) {
         const layer &l = net->layers[i];
         if (l.type != YOLO && l.type != REGION && l.type != DETECTION) continue;
@@ -321,6 +327,10 @@ static void build_engine_device_state(b200_engine *e, network *net)
         h.type = l.type; h.w = l.w; h.h = l.h; h.n = l.n; h.classes = l.classes; h.coords = l.coords;
         h.outputs = l.outputs; h.side = l.side; h.sqrt_ = l.sqrt;
         h.out = e->L[i].head_out;
+        if (l.type == YOLO && i > 0 && net->layers[i - 1].type == CONVOLUTIONAL && e->L[i - 1].out.dtype == DT_F32 && e->L[i - 1].out.p) {
+            h.raw = (const float *)e->L[i - 1].out.p;
+            h.raw_ld = e->L[i - 1].out.ld;
+        } else e->raw_decode_ok = false;
         if (l.n > 16) { fprintf(stderr, "b200-darknet: more than 16 anchors per head\n"); abort(); }
         for (int a = 0; a < l.n && l.type != DETECTION; ++a) {
             int src = l.type == YOLO ? l.mask[a] : a;
@@ -392,6 +402,8 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaFree(e->cand.flags); cudaFree(e->cand.offsets); cudaFree(e->cand.cls_count);
         cudaFree(e->nms_scratch.mask); cudaFree(e->d_records); cudaFree(e->d_record_count);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
+        for (auto &ev : e->copy_done) cudaEventDestroy(ev);
+        cudaStreamDestroy(e->copy_stream);
         cudaStreamDestroy(e->stream);
     }
     delete e;
@@ -544,14 +556,53 @@ static int logical_batch(const b200_engine *e, const network *net)
     return net->batch;
 }
 
-static void forward_layers(b200_engine *e, network *net, int start, int end)
+static void forward_layers(b200_engine *e, network *net, int start, int end, bool skip_yolo_forward = false)
 {
     int batch = logical_batch(e, net);
     if (start == 0 && !e->L[0].stem) {
         TView v = e->in_view; v.n = batch;
         launch_nchw_f32_to_view(e->d_input, v, e->stream);
     }
-    for (int i = start; i < end; ++i) run_layer(e, net, i, batch);
+    for (int i = start; i < end; ++i) {
+        if (skip_yolo_forward && net->layers[i].type == YOLO) continue;   // the fused detection path decodes from the raw logits
+        run_layer(e, net, i, batch);
+    }
+}
+
+// H2D of a host batch.  When the first layer is the stem convolution (it reads the fp32 NCHW input directly and has no
+// cross-image dependency) the copy is issued in chunks on a second stream and the stem runs chunk by chunk behind it, so
+// its time hides under the PCIe transfer.  Returns the index of the first layer that still has to run.
+static int stage_input(b200_engine *e, network *net, const float *input)
+{
+    const int batch = logical_batch(e, net);
+    const layer &l0 = net->layers[0];
+    DevLayer &d0 = e->L[0];
+    int chunks = 1;
+    if (d0.stem && !(d0.tc && e->conv_backend == 0) && !getenv("B200_NO_COPY_OVERLAP")) {
+        if (batch % 8 == 0 && batch >= 16) chunks = 8;
+        else if (batch % 4 == 0 && batch >= 8) chunks = 4;
+        else if (batch % 2 == 0 && batch >= 4) chunks = 2;
+    }
+    if (chunks == 1) {
+        B200_CHECK(cudaMemcpyAsync(e->d_input, input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        return 0;
+    }
+    const int per = batch / chunks;
+    const size_t in_stride = (size_t)per * net->inputs;
+    for (int k = 0; k < chunks; ++k) {
+        B200_CHECK(cudaMemcpyAsync(e->d_input + k * in_stride, input + k * in_stride, in_stride * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+        B200_CHECK(cudaEventRecord(e->copy_done[k], e->copy_stream));
+    }
+    ConvParams p{l0.size, l0.stride, l0.pad, act_id(l0.activation), d0.w, d0.scale, d0.shift, d0.cout_pad};
+    const size_t out_stride = (size_t)per * l0.out_h * l0.out_w * d0.out.ld * dt_size(d0.out.dtype);
+    for (int k = 0; k < chunks; ++k) {
+        B200_CHECK(cudaStreamWaitEvent(e->stream, e->copy_done[k], 0));
+        TView out = d0.out;
+        out.n = per;
+        out.p = (unsigned char *)d0.out.p + k * out_stride;
+        launch_conv_stem(e->d_input + k * in_stride, per, l0.h, l0.w, l0.c, out, p, e->stream);
+    }
+    return 1;
 }
 
 static void sync_heads_to_host(b200_engine *e, network *net)
@@ -575,9 +626,8 @@ static void sync_heads_to_host(b200_engine *e, network *net)
 extern "C" void b200_engine_forward(b200_engine *e, network *net, const float *input)
 {
     need_device(e, "network_predict");
-    int batch = logical_batch(e, net);
-    B200_CHECK(cudaMemcpyAsync(e->d_input, input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    forward_layers(e, net, 0, net->n);
+    int first = stage_input(e, net, input);
+    forward_layers(e, net, first, net->n);
     if (e->head_sync) sync_heads_to_host(e, net);
     B200_CHECK(cudaStreamSynchronize(e->stream));
 }
@@ -680,7 +730,7 @@ extern "C" void b200_profile_tail(network *net, int w, int h, float thresh, floa
     for (auto &x : ev) B200_CHECK(cudaEventCreate(&x));
     for (int it = -1; it < iters; ++it) {                 // iteration -1 is an untimed warm-up (scratch allocation)
         B200_CHECK(cudaEventRecord(ev[0], e->stream));
-        launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, 1, 1, e->cand, e->stream);
+        launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, 1, 1, 0, e->cand, e->stream);
         B200_CHECK(cudaEventRecord(ev[1], e->stream));
         launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
                         e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, e->stream);
@@ -786,7 +836,7 @@ extern "C" int b200_engine_decode_image(b200_engine *e, network *net, int image,
     need_device(e, "get_network_boxes");
     if (e->heads.empty()) return 0;
     ensure_candidates(e, 1);
-    launch_decode(e->d_heads, (int)e->heads.size(), image, 1, net->w, net->h, w, h, thresh, relative, 0, e->cand, e->stream);
+    launch_decode(e->d_heads, (int)e->heads.size(), image, 1, net->w, net->h, w, h, thresh, relative, 0, 0, e->cand, e->stream);
     int n = 0;
     B200_CHECK(cudaMemcpyAsync(&n, e->cand.count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     B200_CHECK(cudaStreamSynchronize(e->stream));
@@ -809,8 +859,11 @@ extern "C" int b200_detect_batch(network *net, const float *input, int w, int h,
     b200_engine *e = b200_engine_of(net);
     need_device(e, "b200_detect_batch");
     int batch = logical_batch(e, net);
-    if (input) B200_CHECK(cudaMemcpyAsync(e->d_input, input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    forward_layers(e, net, 0, net->n);
+    const int first = input ? stage_input(e, net, input) : 0;
+    // with head sync off nobody reads l.output of the heads: skip forward_yolo_layer and decode from the head convolutions'
+    // fp32 logits (identical arithmetic: the logistic is evaluated on the fly for the objectness test and for survivors)
+    const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
+    forward_layers(e, net, first, net->n, use_raw != 0);
     if (e->heads.empty()) { B200_CHECK(cudaStreamSynchronize(e->stream)); return 0; }
     ensure_candidates(e, e->cap);
     if (e->records_cap < max_out) {
@@ -819,7 +872,7 @@ extern "C" int b200_detect_batch(network *net, const float *input, int w, int h,
         e->records_cap = max_out;
     }
     if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
-    launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, e->cand, e->stream);
+    launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, use_raw, e->cand, e->stream);
     launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
                     e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, e->stream);
     B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));

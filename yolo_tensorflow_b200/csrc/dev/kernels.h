@@ -63,6 +63,8 @@ struct HeadDesc {            // one per YOLO/REGION/DETECTION layer, device-resi
     int type;                // LAYER_TYPE value
     int w, h, n, classes, coords, outputs, side, sqrt_;
     const float *out;        // darknet-layout fp32 activations [batch][outputs]
+    const float *raw;        // YOLO heads: the feeding convolution's raw fp32 NHWC logits (or NULL); lets the fused
+    int raw_ld;              //   detection path decode without materialising l.output (logistic applied on the fly)
     float anchors[2 * 16];   // (w,h) pairs already selected through mask[]
     int box_base;            // first global box id of this head inside an image
 };
@@ -80,7 +82,7 @@ struct CandBuffers {
 // mode 0 = reference get_network_boxes semantics (yolo: obj>thresh only; region/detection: every box)
 // mode 1 = compact: additionally drops boxes whose objectness is 0 (what do_nms_sort's partition discards)
 void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, CandBuffers cb, cudaStream_t s);
+                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s);
 void launch_count_yolo(const HeadDesc *heads_dev, int nheads, int image, float thresh, int *count_dev, cudaStream_t s);
 
 struct NmsScratch { unsigned *mask; size_t words_per_cta; int ctas; };
