@@ -105,6 +105,17 @@ typedef struct {
 int b200_detect_batch(network *net, const float *input, int w, int h, float thresh, float nms_thresh,
                       int relative, b200_det *out, int max_out, int *counts);
 
+/* Double-buffered serving loop (the e2e number of bench.py): b200_submit_batch starts the asynchronous H2D of a batch
+ * (host fp32 NCHW, ideally pinned) into a spare device buffer and returns at once; b200_detect_submitted makes that batch
+ * current, starts the H2D of `next_input` (may be NULL) into the buffer that just became free, and runs forward + decode +
+ * NMS exactly like b200_detect_batch.  Pattern:
+ *     submit(b[0]); for k: n = detect_submitted(b[k+1], ...)      -> results of b[k]
+ * so the PCIe copy of batch k+1 hides under the compute of batch k.  A host buffer must stay valid until the call that
+ * returns ITS results has returned. */
+void b200_submit_batch(network *net, const float *input);
+int  b200_detect_submitted(network *net, const float *next_input, int w, int h, float thresh, float nms_thresh, int relative,
+                           b200_det *out, int max_out, int *counts);
+
 /* device NMS on caller-provided host boxes (the kernel behind do_nms_sort); exposed for parity tests:
  * boxes[n*4] (x,y,w,h), probs[n*classes] row-major, modified in place exactly like box.c:58-89 zeroes prob[k]. */
 void b200_nms_sort_arrays(const float *boxes, float *probs, int n, int classes, float thresh);

@@ -376,6 +376,24 @@ def test_fused_path_from_raw_logits_is_identical(dn, workdir):
     assert a.tobytes() == b.tobytes()
 
 
+def test_double_buffered_serving_loop_matches_synchronous_call(dn, workdir):
+    """b200_submit_batch / b200_detect_submitted (H2D of batch k+1 overlapped with batch k) == b200_detect_batch"""
+    net, _, _ = open_net(dn, "yolov3-tiny", 4, 160, workdir, dn.PREC_BF16)
+    batches = [np.ascontiguousarray(synth.make_images(4, 3, 160, 160, 100 + k)) for k in range(3)]
+    want = [net.detect_batch(b, 160, 160, .3, .45) for b in batches]
+    out = (dn.B200_DET * 100000)()
+    counts = (ctypes.c_int * 4)()
+    dn.lib.b200_submit_batch(net.ptr, batches[0].ctypes.data_as(ctypes.c_void_p))
+    for k in range(3):
+        nxt = batches[k + 1].ctypes.data_as(ctypes.c_void_p) if k < 2 else None
+        n = dn.lib.b200_detect_submitted(net.ptr, nxt, 160, 160, .3, .45, 1, out, 100000, counts)
+        rec = np.ctypeslib.as_array(out)[:n].copy()
+        ref, ref_counts = want[k]
+        assert n == len(ref) and list(counts) == ref_counts.tolist()
+        key = lambda r: np.lexsort((r["cls"], r["box_id"], r["image"]))
+        assert rec[key(rec)].tobytes() == ref[key(ref)].tobytes()
+
+
 def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
     net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
     x = synth.make_images(2, 3, 160, 160, 41)

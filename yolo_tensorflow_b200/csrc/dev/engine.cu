@@ -45,6 +45,9 @@ struct b200_engine {
     cudaEvent_t copy_done[8];
     std::vector<DevLayer> L;
     float *d_input;            // fp32 NCHW network input [cap][inputs]
+    float *d_input_next;       // spare input buffer: b200_submit_batch copies batch k+1 here while batch k computes
+    cudaEvent_t submit_done;
+    int submitted;
     TView in_view;             // NHWC copy of the input (only when layer 0 is not a stem conv)
     unsigned char *arena;      // parameters
     size_t arena_bytes;
@@ -148,6 +151,9 @@ static void build_engine_device_state(b200_engine *e, network *net)
     auto cons = consumers_of(net);
 
     e->d_input = (float *)dev_alloc((size_t)e->cap * net->inputs * sizeof(float));
+    e->d_input_next = nullptr;                                    // allocated on the first b200_submit_batch
+    B200_CHECK(cudaEventCreateWithFlags(&e->submit_done, cudaEventDisableTiming));
+    e->submitted = 0;
     size_t max_floats = (size_t)e->cap * net->inputs;
 
     // ---- shortcut fusion: conv -> shortcut pairs whose add can ride in the conv epilogue --------------
@@ -362,7 +368,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->L.resize(net->n);
     for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; }
     e->fusion = b200_get_default_fusion();
-    e->stream = nullptr; e->d_input = nullptr; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
+    e->stream = nullptr; e->d_input = nullptr; e->d_input_next = nullptr; e->submitted = 0; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
     memset(&e->cand, 0, sizeof e->cand); e->cand_slots = 0;
     memset(&e->nms_scratch, 0, sizeof e->nms_scratch);
@@ -397,7 +403,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
             cudaFree(d.stem_cols);
             if (d.head_out && d.type != DROPOUT) cudaFree(d.head_out);
         }
-        cudaFree(e->d_input); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
+        cudaFree(e->d_input); cudaFree(e->d_input_next); cudaEventDestroy(e->submit_done); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
         cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
         cudaFree(e->cand.flags); cudaFree(e->cand.offsets); cudaFree(e->cand.cls_count);
         cudaFree(e->nms_scratch.mask); cudaFree(e->d_records); cudaFree(e->d_record_count);
@@ -853,13 +859,10 @@ extern "C" int b200_engine_decode_image(b200_engine *e, network *net, int image,
 
 extern "C" int b200_engine_classes(b200_engine *e) { return e->classes; }
 
-extern "C" int b200_detect_batch(network *net, const float *input, int w, int h, float thresh, float nms_thresh,
-                                 int relative, b200_det *out, int max_out, int *counts)
+static int detect_core(b200_engine *e, network *net, int first, int w, int h, float thresh, float nms_thresh, int relative,
+                       b200_det *out, int max_out, int *counts)
 {
-    b200_engine *e = b200_engine_of(net);
-    need_device(e, "b200_detect_batch");
     int batch = logical_batch(e, net);
-    const int first = input ? stage_input(e, net, input) : 0;
     // with head sync off nobody reads l.output of the heads: skip forward_yolo_layer and decode from the head convolutions'
     // fp32 logits (identical arithmetic: the logistic is evaluated on the fly for the objectness test and for survivors)
     const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
@@ -889,6 +892,42 @@ extern "C" int b200_detect_batch(network *net, const float *input, int w, int h,
         B200_CHECK(cudaStreamSynchronize(e->stream));
     }
     return n;
+}
+
+extern "C" int b200_detect_batch(network *net, const float *input, int w, int h, float thresh, float nms_thresh,
+                                 int relative, b200_det *out, int max_out, int *counts)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_detect_batch");
+    const int first = input ? stage_input(e, net, input) : 0;
+    return detect_core(e, net, first, w, h, thresh, nms_thresh, relative, out, max_out, counts);
+}
+
+// double-buffered serving loop: submit(k+1) ; detect_submitted(k) ; submit(k+2) ; ...  The H2D of the next batch runs on
+// the copy stream into the spare input buffer while the current batch computes.
+extern "C" void b200_submit_batch(network *net, const float *input)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_submit_batch");
+    if (e->submitted) { fprintf(stderr, "b200-darknet: b200_submit_batch called twice without b200_detect_submitted\n"); abort(); }
+    int batch = logical_batch(e, net);
+    if (!e->d_input_next) e->d_input_next = (float *)dev_alloc((size_t)e->cap * net->inputs * sizeof(float));
+    B200_CHECK(cudaMemcpyAsync(e->d_input_next, input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    B200_CHECK(cudaEventRecord(e->submit_done, e->copy_stream));
+    e->submitted = 1;
+}
+
+extern "C" int b200_detect_submitted(network *net, const float *next_input, int w, int h, float thresh, float nms_thresh,
+                                     int relative, b200_det *out, int max_out, int *counts)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_detect_submitted");
+    if (!e->submitted) { fprintf(stderr, "b200-darknet: b200_detect_submitted without a submitted batch\n"); abort(); }
+    float *t = e->d_input; e->d_input = e->d_input_next; e->d_input_next = t;      // the submitted batch becomes current
+    e->submitted = 0;
+    B200_CHECK(cudaStreamWaitEvent(e->stream, e->submit_done, 0));
+    if (next_input) b200_submit_batch(net, next_input);                              // prefetch the following batch under this compute
+    return detect_core(e, net, 0, w, h, thresh, nms_thresh, relative, out, max_out, counts);
 }
 
 // device NMS on caller-provided host arrays (the kernel behind do_nms_sort / do_nms_obj)

@@ -102,6 +102,9 @@ lib.get_network_boxes_batch.argtypes = [c_void_p, c_int, c_int, c_int, c_float, 
 lib.get_network_boxes_batch.restype = POINTER(DETECTION)
 lib.b200_detect_batch.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(B200_DET), c_int, POINTER(c_int)]
 lib.b200_detect_batch.restype = c_int
+lib.b200_submit_batch.argtypes = [c_void_p, c_void_p]
+lib.b200_detect_submitted.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(B200_DET), c_int, POINTER(c_int)]
+lib.b200_detect_submitted.restype = c_int
 lib.b200_nms_sort_arrays.argtypes = [POINTER(c_float), POINTER(c_float), c_int, c_int, c_float]
 lib.b200_nms_obj_arrays.argtypes = [POINTER(c_float), POINTER(c_float), c_int, c_float, POINTER(c_ubyte)]
 
