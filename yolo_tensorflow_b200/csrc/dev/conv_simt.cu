@@ -127,6 +127,129 @@ conv_stem_fast_kernel(const float *__restrict__ in, int N, int H, int W, T *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Constant-bank variant of the first-layer kernel.  The shared-memory version above is bound by the LSU: one broadcast
+// LDS.128 returns 512 bytes to a warp (4 cycles of the 128 B/clk shared-memory pipe) per 4 FMAs, and the four SM
+// sub-partitions share that pipe.  Here the [K][COUT] fp32 weights sit in __constant__ memory, so every FMA takes its
+// weight as a constant-bank operand (FFMA R, R, c[bank][imm], R): no load instructions at all in the inner loop.
+// The bank holds ONE stem at a time; it is refilled (3.4 KB for YOLOv3) whenever a different weight pointer is launched.
+// ---------------------------------------------------------------------------------------------------
+#define STEM_CONST_MAX (147 * 64)
+__constant__ float c_stem_w[STEM_CONST_MAX];
+__constant__ float c_stem_scale[64];
+__constant__ float c_stem_shift[64];
+
+template <typename T, bool EXACT, int SIZE, int CIN, int COUT, int C0, int PIX>
+__device__ __forceinline__ void conv_stem_const_body(const float *__restrict__ in, int N, int H, int W, T *__restrict__ out, int OH,
+                                                     int OW, int ldo, int stride, int pad, int act)
+{
+    // one thread = PIX horizontally adjacent output pixels x CH filters: each constant-bank weight feeds PIX FMAs and the
+    // input columns the pixels share are loaded once
+    constexpr int CH = COUT < 32 ? COUT : 32;               // filters per thread
+    constexpr int c0 = C0;                                  // compile-time, so every weight is an immediate constant-bank operand
+    constexpr int MAXS = 2;                                 // strides 1 and 2 are supported
+    constexpr int COLS = SIZE + (PIX - 1) * MAXS;
+    const int groups_x = (OW + PIX - 1) / PIX;
+    const long long total = (long long)N * OH * groups_x;
+    const size_t plane = (size_t)H * W;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int gx = (int)(g % groups_x), oy = (int)((g / groups_x) % OH), n = (int)(g / ((long long)groups_x * OH));
+        const int ox0 = gx * PIX;
+        const float *img = in + (size_t)n * CIN * plane;
+        float acc[PIX][CH];
+#pragma unroll
+        for (int p = 0; p < PIX; ++p)
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[p][j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < SIZE; ++ky) {
+            const int y = oy * stride + ky - pad;
+            const bool yok = y >= 0 && y < H;
+            float v[COLS * CIN];
+#pragma unroll
+            for (int cx = 0; cx < COLS; ++cx) {
+                const int x = ox0 * stride + cx - pad;
+                const bool ok = yok && x >= 0 && x < W && cx < SIZE + (PIX - 1) * stride;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) v[cx * CIN + c] = ok ? __ldg(img + c * plane + (size_t)y * W + x) : 0.f;
+            }
+#pragma unroll
+            for (int kx = 0; kx < SIZE; ++kx)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) {
+                    const float *wrow = c_stem_w + ((ky * SIZE + kx) * CIN + c) * COUT + c0;
+                    float xin[PIX];
+#pragma unroll
+                    for (int p = 0; p < PIX; ++p) xin[p] = stride == 1 ? v[(kx + p) * CIN + c] : v[(kx + 2 * p) * CIN + c];
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+#pragma unroll
+                        for (int p = 0; p < PIX; ++p) acc[p][j] = fmaf(xin[p], wrow[j], acc[p][j]);
+                }
+        }
+        constexpr int V = Elem<T>::VEC;
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) {
+            if (ox0 + p >= OW) break;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[p][j] = apply_act<EXACT>(fmaf(acc[p][j], c_stem_scale[c0 + j], c_stem_shift[c0 + j]), act);
+            T *dst = out + ((size_t)(n * OH + oy) * OW + ox0 + p) * ldo + c0;
+#pragma unroll
+            for (int j = 0; j < CH; j += V) store_vec<T>(dst + j, acc[p] + j);
+        }
+    }
+}
+
+template <typename T, bool EXACT, int SIZE, int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+conv_stem_const_kernel(const float *__restrict__ in, int N, int H, int W, T *__restrict__ out, int OH, int OW, int ldo,
+                       int stride, int pad, int act)
+{
+    constexpr int PIX = 1;      // 2 pixels per thread measured slower (0.76 vs 0.66 ms on YOLOv3-416 b64): register pressure
+    if (COUT <= 32 || blockIdx.y == 0) conv_stem_const_body<T, EXACT, SIZE, CIN, COUT, 0, PIX>(in, N, H, W, out, OH, OW, ldo, stride, pad, act);
+    else conv_stem_const_body<T, EXACT, SIZE, CIN, COUT, (COUT > 32 ? 32 : 0), PIX>(in, N, H, W, out, OH, OW, ldo, stride, pad, act);
+}
+
+template <typename T>
+__global__ void stem_weights_to_f32_kernel(const T *__restrict__ wt, int K, int Cout, float *__restrict__ dst)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * Cout; i += gridDim.x * blockDim.x) {
+        int k = i / Cout, co = i % Cout;
+        dst[i] = Elem<T>::load(wt + (size_t)co * K + k);       // [Cout][K] -> [K][Cout]
+    }
+}
+
+static const void *g_stem_bank_owner = nullptr;
+static float *g_stem_scratch = nullptr;
+void conv_stem_invalidate_bank() { g_stem_bank_owner = nullptr; }
+
+template <typename T, bool EXACT>
+static bool try_stem_const(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
+{
+    if (getenv("B200_STEM_SMEM")) return false;
+    const int K = p.size * p.size * c;
+    // 3x3 stems only: the 7x7 YOLOv1 stem measured slower from the constant bank (3.6 vs 2.9 ms) than from shared memory
+    if (c != 3 || p.size != 3 || (p.stride != 1 && p.stride != 2) || (out.c != 16 && out.c != 32 && out.c != 64)) return false;
+    if (out.ld % Elem<T>::VEC != 0 || ((uintptr_t)out.p & 15)) return false;
+    if (g_stem_bank_owner != p.w) {                          // (re)fill the constant bank for this network's stem
+        if (!g_stem_scratch) B200_CHECK(cudaMalloc((void **)&g_stem_scratch, STEM_CONST_MAX * sizeof(float)));
+        stem_weights_to_f32_kernel<T><<<8, 256, 0, s>>>((const T *)p.w, K, out.c, g_stem_scratch);
+        B200_LAUNCHED();
+        B200_CHECK(cudaMemcpyToSymbolAsync(c_stem_w, g_stem_scratch, (size_t)K * out.c * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
+        B200_CHECK(cudaMemcpyToSymbolAsync(c_stem_scale, p.scale, out.c * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
+        B200_CHECK(cudaMemcpyToSymbolAsync(c_stem_shift, p.shift, out.c * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
+        g_stem_bank_owner = p.w;
+    }
+    long long groups = (long long)n * out.h * out.w;
+    int gx = (int)((groups + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid(gx, out.c > 32 ? out.c / 32 : 1);
+#define STEM_CONST_LAUNCH(SZ, CO) conv_stem_const_kernel<T, EXACT, SZ, 3, CO><<<grid, 256, 0, s>>>(in_nchw, n, h, w, (T *)out.p, out.h, out.w, out.ld, p.stride, p.pad, p.act)
+    if (out.c == 16) STEM_CONST_LAUNCH(3, 16); else if (out.c == 32) STEM_CONST_LAUNCH(3, 32); else STEM_CONST_LAUNCH(3, 64);
+#undef STEM_CONST_LAUNCH
+    return true;
+}
+
 template <typename T, bool EXACT>
 static bool try_stem_fast(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
 {
@@ -147,6 +270,11 @@ static bool try_stem_fast(const float *in_nchw, int n, int h, int w, int c, TVie
 
 void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
 {
+    if (out.dtype == DT_F32 ? try_stem_const<float, true>(in_nchw, n, h, w, c, out, p, s)
+                            : try_stem_const<bf16, false>(in_nchw, n, h, w, c, out, p, s)) {
+        B200_LAUNCHED();
+        return;
+    }
     if (out.dtype == DT_F32 ? try_stem_fast<float, true>(in_nchw, n, h, w, c, out, p, s)
                             : try_stem_fast<bf16, false>(in_nchw, n, h, w, c, out, p, s)) {
         B200_LAUNCHED();

@@ -483,6 +483,7 @@ extern "C" void b200_engine_upload_weights(b200_engine *e, network *net)
             fold_bn(l, l.outputs, (float *)(host.data() + d.scale_off), (float *)(host.data() + d.shift_off));
         }
     }
+    conv_stem_invalidate_bank();
     B200_CHECK(cudaMemcpyAsync(e->arena, host.data(), e->arena_bytes, cudaMemcpyHostToDevice, e->stream));
     B200_CHECK(cudaStreamSynchronize(e->stream));
 }

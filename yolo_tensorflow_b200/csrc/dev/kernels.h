@@ -38,6 +38,7 @@ struct ConvParams {
 };
 // first-layer kernel: reads the fp32 NCHW network input directly (fuses the layout/precision conversion)
 void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);
+void conv_stem_invalidate_bank();      // call after the stem's weights changed in place (load_weights)
 // CUDA-core implicit-GEMM (fp32 accumulate); the fp32-exact path and the fallback for odd shapes
 void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
 // tcgen05/TMEM/TMA implicit-GEMM (bf16 in, fp32 accumulate).  Plans live in conv_tc.cu.
