@@ -189,6 +189,8 @@ struct ConvTcArgs {
     int tmem_cols;
     int act;
     int resident_b;          // 1: the whole [block_n x K] weight slab stays in shared memory for the CTA's lifetime
+    int halo_P, halo_TWv, halo_THv;   // mode 2 (halo patch): row pitch of the patch (TW + size - 1) and the valid tile width / height
+    int a_stage_bytes, b_stages;      // mode 2: bytes per patch stage, depth of the separate weight ring
     int acc_stages;          // TMEM accumulator buffers (2..8): small filter tiles let the MMA run many tiles ahead of the epilogue
     int staged;              // 1: epilogue goes TMEM -> registers -> swizzled smem tile -> TMA store (and TMA-loads the residual)
     int pair;                // 1: cta_group::2 kernel (two CTAs share one 256 x block_n accumulator tile and its weights)
@@ -303,6 +305,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
     int acc = 0; uint32_t acc_phase = 0, rphase = 0;
     int rx = 0, ry = 0, rn = 0;                            // row -> position inside the pixel tile (tile independent)
     if (args.mode == 1) { rx = row % args.TW; ry = (row / args.TW) % args.TH; rn = row / (args.TW * args.TH); }
+    if (args.mode == 2) { rx = row % args.halo_P; ry = row / args.halo_P; }      // position inside the patch-pitched tile
     const bool hoist = args.n_tiles == 1;                  // one filter tile: its constants are staged once
     if (hoist) {
         for (int c = ep_tid; c < args.block_n; c += 128) {
@@ -329,17 +332,30 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         int tx = 0, ty = 0, tn = 0;
-        if (args.mode == 1) { tx = m_tile % args.tiles_x; ty = (m_tile / args.tiles_x) % args.tiles_y; tn = m_tile / (args.tiles_x * args.tiles_y); }
+        if (args.mode >= 1) { tx = m_tile % args.tiles_x; ty = (m_tile / args.tiles_x) % args.tiles_y; tn = m_tile / (args.tiles_x * args.tiles_y); }
+        // mode 2: image rows of this tile that exist (each is one TMA box of the staged epilogue)
+        int rows_here = 0;
+        if (args.mode == 2 && m_tile < args.m_tiles) { rows_here = args.OH - ty * args.halo_THv; if (rows_here > args.halo_THv) rows_here = args.halo_THv; }
         OutT *orow = nullptr;
         const bf16 *rrow = nullptr;
         if (staged) {
             if (ep_tid == 0) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's stores are done reading sC
                 if (has_res) {                                                      // residual tile -> sC while the mainloop runs
-                    mbar_expect_tx(rfull, (uint32_t)(args.a_rows * args.block_n * 2));
-                    for (int q = 0; q < n_sub; ++q) {
-                        if (args.mode == 0) tma_load_2d(&maps.r, sC + q * 16384, rfull, col0 + 64 * q, m_tile * 128);
-                        else tma_load_4d(&maps.r, sC + q * 16384, rfull, col0 + 64 * q, tx * args.TW, ty * args.TH, tn * args.TN);
+                    if (args.mode == 2 && rows_here == 0) {
+                        // phantom tile of an odd pair: nothing to load, nothing will be waited for
+                    } else if (args.mode == 2) {
+                        mbar_expect_tx(rfull, (uint32_t)(rows_here * args.halo_TWv * 128 * n_sub));
+                        for (int q = 0; q < n_sub; ++q)
+                            for (int yy = 0; yy < rows_here; ++yy)
+                                tma_load_4d(&maps.r, sC + q * 16384 + yy * args.halo_P * 128, rfull, col0 + 64 * q, tx * args.halo_TWv,
+                                            ty * args.halo_THv + yy, tn);
+                    } else {
+                        mbar_expect_tx(rfull, (uint32_t)(args.a_rows * args.block_n * 2));
+                        for (int q = 0; q < n_sub; ++q) {
+                            if (args.mode == 0) tma_load_2d(&maps.r, sC + q * 16384, rfull, col0 + 64 * q, m_tile * 128);
+                            else tma_load_4d(&maps.r, sC + q * 16384, rfull, col0 + 64 * q, tx * args.TW, ty * args.TH, tn * args.TN);
+                        }
                     }
                 }
             }
@@ -350,9 +366,13 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
                 if (args.mode == 0) {
                     long long p = (long long)m_tile * 128 + row;
                     if (p < args.npix) pix = p;
-                } else {
+                } else if (args.mode == 1) {
                     int ox = tx * args.TW + rx, oy = ty * args.TH + ry, n = tn * args.TN + rn;
                     if (row < args.a_rows && ox < args.OW && oy < args.OH && n < args.batch) pix = ((long long)n * args.OH + oy) * args.OW + ox;
+                } else {
+                    int ox = tx * args.halo_TWv + rx, oy = ty * args.halo_THv + ry;
+                    if (rx < args.halo_TWv && ry < args.halo_THv && ox < args.OW && oy < args.OH && tn < args.batch)
+                        pix = ((long long)tn * args.OH + oy) * args.OW + ox;
                 }
             }
             orow = pix >= 0 ? (OutT *)args.out + pix * args.ldo + col0 : nullptr;
@@ -362,7 +382,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
 
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        if (staged && has_res) { mbar_wait(rfull, rphase); rphase ^= 1; }
+        if (staged && has_res && !(args.mode == 2 && rows_here == 0)) { mbar_wait(rfull, rphase); rphase ^= 1; }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
         const float *sc = s_scale + (hoist ? 0 : acc * 256), *sh = s_shift + (hoist ? 0 : acc * 256);
         int c0 = 0;
@@ -396,7 +416,11 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
             if (ep_tid == 0) {
                 for (int q = 0; q < n_sub; ++q) {
                     if (args.mode == 0) tma_store_2d(&maps.c, sC + q * 16384, col0 + 64 * q, m_tile * 128);
-                    else tma_store_4d(&maps.c, sC + q * 16384, col0 + 64 * q, tx * args.TW, ty * args.TH, tn * args.TN);
+                    else if (args.mode == 1) tma_store_4d(&maps.c, sC + q * 16384, col0 + 64 * q, tx * args.TW, ty * args.TH, tn * args.TN);
+                    else
+                        for (int yy = 0; yy < rows_here; ++yy)        // one box per image row: the tile is patch-pitched in smem
+                            tma_store_4d(&maps.c, sC + q * 16384 + yy * args.halo_P * 128, col0 + 64 * q, tx * args.halo_TWv,
+                                         ty * args.halo_THv + yy, tn);
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -657,6 +681,137 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Halo-patch variant of the CTA-pair kernel for stride-1 size x size convolutions (mode 2).
+// The 1-tap-per-TMA-box scheme above re-reads every activation row size^2 times; measured, the TMA engine retires about
+// one <=128-byte row per ~3 SM cycles, and that row rate — not the MMA — bounds the kernel.  Here each CTA loads, once per
+// 64-channel block, the (TH+size-1) x (TW+size-1)-pixel input patch of its output tile (ONE 4-D TMA box, zero-filled at
+// the borders).  Shared-memory swizzling is a pure function of the address (verified on B200 with
+// scripts/desc_shift_probe.cu), so filter tap (ky,kx) is simply the SAME patch read through a descriptor whose start is
+// shifted by ky*P + kx rows (P = patch pitch).  GEMM row m then stands for patch position (m / P, m % P); positions in
+// the size-1 rightmost columns of every patch row are computed but never stored.  Activation rows per 64-channel block drop
+// from size^2 * 128 to (TH+size-1) * P (~216 for a 2 x 52 tile); the weight tiles stream through their own ring.
+// ---------------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_halo_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
+{
+    constexpr int BLOCK_K = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_stages = args.stages, b_stages = args.b_stages;
+    uint8_t *sA = smem;                                              // a_stages patches
+    uint8_t *sB = sA + (size_t)a_stages * args.a_stage_bytes;        // b_stages half weight tiles
+    uint8_t *sC = sB + (size_t)b_stages * args.b_stage_bytes;
+    uint8_t *aux = sC + (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0);
+    uint64_t *afull = (uint64_t *)aux;                               // [<=4]
+    uint64_t *aempty = afull + 4;                                    // [<=4]
+    uint64_t *bfull = aempty + 4;                                    // [<=8]
+    uint64_t *bempty = bfull + 8;                                    // [<=8]
+    uint64_t *tfull = bempty + 8;                                    // [2]
+    uint64_t *tempty = tfull + 8;                                    // [2]
+    uint64_t *rfull = tempty + 9;
+    uint32_t *tmem_slot = (uint32_t *)(rfull + 1);
+    float *s_scale = (float *)(aux + 512);
+    float *s_shift = s_scale + 512;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int m_pairs = (args.m_tiles + 1) / 2;
+    const int num_tiles = m_pairs * args.n_tiles;
+    const int taps = args.size * args.size;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a_stages; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < b_stages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        mbar_init(rfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(args.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int half_n = args.block_n / 2;
+    const int patch_rows = (args.halo_THv + args.size - 1) * args.halo_P;
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs) =========================
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            const uint32_t a_tx = 2u * (uint32_t)(patch_rows * BLOCK_K * 2);
+            const uint32_t b_tx = 2u * (uint32_t)(half_n * BLOCK_K * 2);
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                const int n_tile = tile % args.n_tiles, m_tile = 2 * (tile / args.n_tiles) + (int)rank;
+                const int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
+                for (int cb = 0; cb < args.cin_blocks; ++cb) {
+                    mbar_wait(&aempty[sa], pa ^ 1);
+                    if (leader) mbar_expect_tx(&afull[sa], a_tx);
+                    tma2_load_4d(&maps.a[0], sA + (size_t)sa * args.a_stage_bytes, &afull[sa], cb * BLOCK_K,
+                                 tx * args.halo_TWv - args.pad, ty * args.halo_THv - args.pad, tn);
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&bempty[sb], pb ^ 1);
+                        if (leader) mbar_expect_tx(&bfull[sb], b_tx);
+                        tma2_load_2d(&maps.b, sB + (size_t)sb * args.b_stage_bytes, &bfull[sb], (tap * args.cin_blocks + cb) * BLOCK_K,
+                                     n_tile * args.block_n + (int)rank * half_n);
+                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.block_n >> 3) << 17) | ((256u >> 4) << 24);
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * args.block_n);
+                for (int cb = 0; cb < args.cin_blocks; ++cb) {
+                    mbar_wait(&afull[sa], pa);
+                    tc_fence_after();
+                    const uint32_t patch = smem_u32(sA + (size_t)sa * args.a_stage_bytes);
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&bfull[sb], pb);
+                        tc_fence_after();
+                        const int ky = tap / args.size, kx = tap - ky * args.size;
+                        const uint64_t adesc = make_desc<BLOCK_K>(patch + (uint32_t)(ky * args.halo_P + kx) * 128u);   // row-shifted view
+                        const uint64_t bdesc = make_desc<BLOCK_K>(smem_u32(sB + (size_t)sb * args.b_stage_bytes));
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; ++k)
+                            tc2_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                        tc2_commit_both(&bempty[sb]);
+                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
+                    }
+                    tc2_commit_both(&aempty[sa]);
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                }
+                tc2_commit_both(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        run_epilogue<OutT, true>(maps, args, tfull, tempty, rfull, s_scale, s_shift, sC, tmem_base, pair_id, num_pairs, num_tiles, (int)rank);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(args.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -708,6 +863,7 @@ static void encode_tile_view(CUtensorMap *map, const TView &t, int channels, con
         cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
         cuuint64_t strides[3] = {(cuuint64_t)t.ld * esz, (cuuint64_t)t.w * t.ld * esz, (cuuint64_t)t.h * t.w * t.ld * esz};
         cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, (cuuint32_t)a.TN};
+        if (a.mode == 2) { box[1] = (cuuint32_t)a.halo_TWv; box[2] = 1; box[3] = 1; }      // one image row of the tile per box
         encode(map, t.p, 4, dims, strides, box, 64);
     }
 }
@@ -750,8 +906,33 @@ template <int BLOCK_K, typename OutT> static void launch_pair_variant(ConvTcPlan
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<BLOCK_K, OutT>, p->maps, p->args));
 }
 
+template <typename OutT> static void launch_halo_variant(ConvTcPlan *p, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_halo_pair_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p->grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = p->smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    B200_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_halo_pair_kernel<OutT>, p->maps, p->args));
+}
+
 void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
 {
+    if (p->args.mode == 2) {
+        if (p->out_dtype == DT_BF16) launch_halo_variant<bf16>(p, s);
+        else launch_halo_variant<float>(p, s);
+        B200_LAUNCHED();
+        return;
+    }
     if (p->args.pair) {
         if (p->out_dtype == DT_BF16) {
             if (p->block_k == 64) launch_pair_variant<64, bf16>(p, s);
@@ -868,6 +1049,45 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                 }
         }
     }
+    // ---- halo-patch mode (mode 2): stride-1 odd-size convolutions, one patch load per 64-channel block -----------------
+    // cost model: per 64-channel block a CTA is bound by max(MMA cycles, ~3 cycles per TMA row); compare cycles per VALID
+    // output pixel of the tap-per-box pair kernel with those of the patch kernel
+    // MEASURED (YOLOv3-416 b64, ncu): the patch kernel keeps the tensor pipe 61 % busy versus 56 % for the tap-per-box
+    // kernel, but only ~81 % of its MMA rows are valid outputs, so it ends up 5-20 % slower on every layer; the L2/TMA row
+    // rate is therefore NOT the binding limit of the pair kernel (shared-memory bandwidth / MMA issue is).  The mode stays
+    // available for experiments (B200_HALO=1 picks it by the cost model, B200_FORCE_HALO=1 always) but is off by default.
+    if (a.mode == 1 && (getenv("B200_HALO") || getenv("B200_FORCE_HALO")) && cp.stride == 1 && (cp.size & 1) && cp.size >= 3 && cp.pad == cp.size / 2 &&
+        block_k == 64 && a.block_n % 32 == 0 && a.block_n >= 64 && out.dtype == DT_BF16) {
+        const int halo = cp.size - 1, taps = cp.size * cp.size;
+        int tiles_x = div_up(out.w + halo, 128) > 1 ? div_up(out.w, 128 - halo) : 1;
+        int TWv = div_up(out.w, tiles_x);
+        int P = TWv + halo;
+        int TH = 128 / P; if (TH < 1) TH = 1; if (TH > out.h) TH = out.h;
+        int tiles_y = div_up(out.h, TH);
+        TH = div_up(out.h, tiles_y);
+        const int half_n = a.block_n / 2;
+        const int patch_rows = (TH + halo) * P;
+        const double mma_cycles = (double)taps * 4.0 * (a.block_n / 2.0);                     // cta_group::2, M=256: N/2 cycles per K=16 step
+        const double rows_tap = (double)taps * (128 + half_n), rows_halo = patch_rows + (double)taps * half_n;
+        const double eff1 = (double)a.npix / ((double)a.m_tiles * 128.0);
+        const double valid_halo = (double)out.w * out.h / ((double)tiles_x * tiles_y);
+        const double cost_tap = (mma_cycles > 3.0 * rows_tap ? mma_cycles : 3.0 * rows_tap) / (128.0 * eff1);
+        const double cost_halo = (mma_cycles > 3.0 * rows_halo ? mma_cycles : 3.0 * rows_halo) / valid_halo;
+        if (P <= 256 && TH + halo <= 256 && (cost_halo < 0.95 * cost_tap || getenv("B200_FORCE_HALO")) &&
+            (long long)tiles_x * tiles_y * in.n >= 2) {
+            a.mode = 2;
+            a.halo_P = P; a.halo_TWv = TWv; a.halo_THv = TH;
+            a.TW = TWv; a.TH = TH; a.TN = 1;
+            a.tiles_x = tiles_x; a.tiles_y = tiles_y;
+            a.m_tiles = tiles_x * tiles_y * in.n;
+            a.a_rows = TH * P;
+            cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+            cuuint64_t strides[3] = {(cuuint64_t)in.ld * esz, (cuuint64_t)in.w * in.ld * esz, (cuuint64_t)in.h * in.w * in.ld * esz};
+            cuuint32_t box[4] = {64, (cuuint32_t)P, (cuuint32_t)(TH + halo), 1};
+            encode(&p->maps.a[0], in.p, 4, dims, strides, box, 64);
+            a.a_stage_bytes = ((128 + halo * P + halo) * 128 + 1023) / 1024 * 1024;
+        }
+    }
     // ---- epilogue staging / weight residency / CTA pairing -------------------------------------------------
     // staged epilogue (TMEM -> registers -> swizzled smem tile -> TMA store, residual TMA-loaded into the same tile) is used
     // where a shortcut is fused: the per-row residual reads of the direct epilogue are what made fused layers slow.
@@ -878,6 +1098,42 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     const long long slab_ = (long long)a.num_kblocks * ((a.block_n * block_k * 2 + 1023) / 1024 * 1024);
     const bool could_reside = a.n_tiles == 1 && !getenv("B200_NO_RESIDENT_B") &&
                               slab_ + (want_staged ? 3LL * a_bytes_ + sc_bytes : 4LL * a_bytes_) <= budget_all;
+    if (a.mode == 2) {
+        // the patch kernel always runs as a CTA pair with its own smem budget (patch ring + weight ring + staging tile)
+        a.pair = 1; a.resident_b = 0;
+        a.b_stage_bytes = ((a.block_n / 2) * block_k * 2 + 1023) / 1024 * 1024;
+        int budget2 = 227 * 1024 - 1024 - (512 + 4096);
+        a.staged = (want_staged && sc_bytes + 2 * a.a_stage_bytes + 3 * a.b_stage_bytes <= budget2) ? 1 : 0;
+        if (a.staged) budget2 -= sc_bytes;
+        int a_st = 2;
+        int b_st = (budget2 - a_st * a.a_stage_bytes) / a.b_stage_bytes;
+        if (b_st > 8) { b_st = 8; int extra = (budget2 - b_st * a.b_stage_bytes) / a.a_stage_bytes; a_st = extra > 4 ? 4 : extra; }
+        if (b_st < 3) { delete p; return nullptr; }
+        a.stages = a_st; a.b_stages = b_st;
+        p->smem_bytes = (size_t)a_st * a.a_stage_bytes + (size_t)b_st * a.b_stage_bytes + (a.staged ? sc_bytes : 0) + (512 + 4096) + 1024;
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cp.cout_pad};
+            cuuint64_t strides[1] = {(cuuint64_t)K * esz};
+            cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)(a.block_n / 2)};
+            encode(&p->maps.b, (void *)cp.w, 2, dims, strides, box, block_k);
+        }
+        if (a.staged) {
+            encode_tile_view(&p->maps.c, out, cp.cout_pad, a);
+            if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a);
+        }
+        a.acc_stages = 2;
+        int cols2 = 2 * a.block_n;
+        a.tmem_cols = cols2 <= 32 ? 32 : (cols2 <= 64 ? 64 : (cols2 <= 128 ? 128 : (cols2 <= 256 ? 256 : 512)));
+        int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+        p->grid = 2 * (pair_tiles < 74 ? pair_tiles : 74);
+        p->flops = 2.0 * (double)a.npix * out.c * K;
+        char buf2[320];
+        snprintf(buf2, sizeof buf2, "conv_tc HALO k64 n%d tile %dx%d (pitch %d) m_tiles %d n_tiles %d patch-stages %d weight-stages %d smem %zu grid %d PAIR(cta_group::2)%s%s",
+                 a.block_n, a.halo_TWv, a.halo_THv, a.halo_P, a.m_tiles, a.n_tiles, a_st, b_st, p->smem_bytes, p->grid,
+                 a.res ? " +residual" : "", a.staged ? " stagedEpilogue" : "");
+        p->desc = buf2;
+        return p;
+    }
     a.pair = (!getenv("B200_NO_PAIR") && !could_reside && a.block_n % 32 == 0 && a.block_n >= 64 && a.m_tiles >= 2 &&
               (long long)a.num_kblocks * a.block_n >= 4 * 256) ? 1 : 0;
     // ---- B view ----
