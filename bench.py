@@ -278,9 +278,18 @@ def main_engine(args):
         for i in range(net.n):
             by_kernel[net.kernel(i)] = by_kernel.get(net.kernel(i), 0.0) + float(per_layer[i])
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+        traffic = None                      # DRAM bytes moved by the conv_tc family per step, from the committed ncu capture
+        tpath = os.path.join(REPO, "profiles", "r1_conv_tc_dram_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_total")
         roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % n_conv,
                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                    "traffic": None, "peak_source": pk["source"], "conv_ms_per_step": conv_ms,
+                    "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write summed over the conv_tc launches of one step (profiles/r1_conv_tc_dram_traffic.json); "
+                                    "algorithmic activation+weight bytes of those layers at bf16: %.2f GB" % (
+                                        sum((L["c"] * L["h"] * L["w"] + L["out_c"] * L["out_h"] * L["out_w"]) * 2.0 * BATCH + L["nweights"] * 2.0
+                                            for i, L in enumerate(net.layers) if is_tc[i]) / 1e9),
+                    "peak_source": pk["source"], "conv_ms_per_step": conv_ms,
                     "ms_per_step_by_kernel": {k: round(v, 4) for k, v in by_kernel.items()},
                     "whole_step_tflops": FLOP_PER_IMAGE * BATCH * args.steps / (ms / 1000.0) / 1e12 / max(world, 1)}
         cpu = None
