@@ -43,6 +43,7 @@ b200_engine *b200_engine_of(const network *net);
 b200_engine *b200_engine_create(network *net, int precision);   /* plans buffers from the layer array      */
 void b200_engine_destroy(b200_engine *e);
 void b200_engine_upload_weights(b200_engine *e, network *net);    /* BN folding + repack (+ bf16 cast) + H2D */
+b200_engine *b200_engine_recreate(b200_engine *old, network *net); /* resize_network: re-plan, keep settings, re-upload */
 
 /* forward_network replacement (network.c:188-211).  `input` is HOST fp32 NCHW, batch*inputs floats. */
 void b200_engine_forward(b200_engine *e, network *net, const float *input);

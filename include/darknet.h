@@ -146,7 +146,7 @@ int    network_width(network *net);                                         /* r
 int    network_height(network *net);                                        /* ref :742 */
 layer  get_network_output_layer(network *net);                              /* ref :717  network.c:699 */
 float *network_predict_image(network *net, image im);                       /* ref :743  network.c:579 */
-int    resize_network(network *net, int w, int h);                          /* ref :704  (re-plans the device engine) */
+int    resize_network(network *net, int w, int h);                          /* ref :704  network.c:358 (re-plans the device engine) */
 void   cuda_set_device(int n);                                              /* ref :631  cuda.c:13,176 */
 double what_time_is_it_now(void);                                           /* utils.c:27 */
 

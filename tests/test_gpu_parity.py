@@ -402,6 +402,28 @@ def test_double_buffered_serving_loop_matches_synchronous_call(dn, workdir):
         assert rec[key(rec)].tobytes() == ref[key(ref)].tobytes()
 
 
+@pytest.mark.parametrize("model,prec", [("yolov3", "fp32"), ("yolov3", "bf16"), ("yolov2", "bf16")])
+def test_resize_network_matches_fresh_parse(dn, model, prec, workdir):
+    """resize_network (network.c:358): after re-planning for a new size the same weights must give exactly what a
+    network parsed at that size gives (multi-scale inference, detector.c:96 / the `random` cfg key)."""
+    p = dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16
+    net, _, _ = open_net(dn, model, 2, 160, workdir, p)
+    x160 = synth.make_images(2, 3, 160, 160, 77)
+    before = net.detect_batch(x160, 160, 160, .3, .45)
+    assert net.resize(224, 224) == 0 and (net.w, net.h) == (224, 224)
+    fresh, _, _ = open_net(dn, model, 2, 224, workdir, p)
+    x = synth.make_images(2, 3, 224, 224, 78)
+    a, b = net.predict(x), fresh.predict(x)
+    assert a.shape == b.shape and np.array_equal(a, b)
+    ra, ca = net.detect_batch(x, 224, 224, .3, .45)
+    rb, cb = fresh.detect_batch(x, 224, 224, .3, .45)
+    assert len(ra) > 0 and np.array_equal(ca, cb) and ra.tobytes() == rb.tobytes()
+    assert net.resize(160, 160) == 0                       # and back: identical to the first run
+    again = net.detect_batch(x160, 160, 160, .3, .45)
+    assert again[0].tobytes() == before[0].tobytes() and np.array_equal(again[1], before[1])
+    net.close(); fresh.close()
+
+
 def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
     net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
     x = synth.make_images(2, 3, 160, 160, 41)

@@ -62,6 +62,68 @@ def test_shapes_and_weight_counts_yolov3():
     assert layers[86][:4] == ["ROUTE", "26", "26", "768"]
 
 
+RESIZE = textwrap.dedent("""
+    import sys
+    sys.path.insert(0, %r)
+    from yolo_tensorflow_b200 import darknet as dn
+    net = dn.Network(sys.argv[1])
+    rc = net.resize(int(sys.argv[2]), int(sys.argv[2]))
+    print(rc, net.w, net.h)
+    for L in net.layers:
+        print(L["type_name"], L["w"], L["h"], L["out_w"], L["out_h"], L["out_c"], L["inputs"], L["outputs"])
+    net.close()
+""" % REPO)
+
+
+@pytest.mark.parametrize("model,size", [("yolov3", 608), ("yolov3", 320), ("yolov2", 608), ("yolov3-tiny", 352)])
+def test_resize_network_geometry(model, size, tmp_path):
+    """resize_network (network.c:358-438) must leave the layer table as a fresh parse at that size would, and as the
+    reference's own resize leaves it."""
+    sys.path.insert(0, REPO)
+    from yolo_tensorflow_b200 import synth
+    cfg = os.path.join(REPO, "cfg", model + ".cfg")
+    r = subprocess.run([sys.executable, "-c", RESIZE, cfg, str(size)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = r.stdout.splitlines()
+    assert rows[0] == "0 %d %d" % (size, size)
+    fresh = synth.make_cfg(model, str(tmp_path), batch=1, width=size, height=size)
+    f = subprocess.run([sys.executable, "-c", RESIZE, fresh, str(size)], capture_output=True, text=True)
+    assert f.stdout == r.stdout
+    from oracle import ref_darknet as R
+    if not R.available():
+        return
+    code = textwrap.dedent("""
+        import ctypes, sys
+        sys.path.insert(0, %r)
+        from oracle import ref_darknet as R
+        net = R.RefNet(sys.argv[1])
+        net.lib.resize_network.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        with R._quiet():
+            rc = net.lib.resize_network(net.ptr, int(sys.argv[2]), int(sys.argv[2]))
+        print(rc)
+        for i in range(net.n):
+            s = net.layer_shape(i)
+            print(s["out_w"], s["out_h"], s["out_c"], s["outputs"])
+    """ % REPO)
+    ref = subprocess.run([sys.executable, "-c", code, cfg, str(size)], capture_output=True, text=True)
+    assert ref.returncode == 0, ref.stderr
+    ours = ["0"] + [" ".join(x.split()[3:6] + x.split()[7:8]) for x in rows[1:]]
+    theirs = ref.stdout.splitlines()
+    for i, row in enumerate(rows[1:], 1):
+        if row.split()[0] in ("YOLO", "REGION"):
+            # resize_yolo_layer/resize_region_layer (yolo_layer.c:63, region_layer.c:56) update w/h/outputs but leave the
+            # stale out_w/out_h behind; here they follow the new size like a fresh parse.  Compare what both define.
+            ours[i] = ours[i].split()[-1]
+            theirs[i] = theirs[i].split()[-1]
+    assert theirs == ours
+
+
+def test_resize_network_refuses_fixed_size_layers():
+    r = subprocess.run([sys.executable, "-c", RESIZE, os.path.join(REPO, "cfg", "yolov1.cfg"), "224"], capture_output=True, text=True)
+    assert r.stdout.splitlines()[0].split()[0] == "-1"       # local/connected/detection: network.c:428
+    assert "Cannot resize this type of layer" in r.stderr
+
+
 def test_batch_and_subdivisions(tmp_path):
     cfg = tmp_path / "b.cfg"
     text = open(os.path.join(REPO, "cfg", "yolov3-tiny.cfg")).read().replace("batch=1", "batch=8").replace("subdivisions=1", "subdivisions=4")

@@ -488,6 +488,21 @@ extern "C" void b200_engine_upload_weights(b200_engine *e, network *net)
     B200_CHECK(cudaStreamSynchronize(e->stream));
 }
 
+// resize_network: drop the plan built for the old geometry and build one for the layer table as it stands now, keeping
+// the engine's settings; the parameters come from the host fp32 copies load_weights filled.
+extern "C" b200_engine *b200_engine_recreate(b200_engine *old, network *net)
+{
+    const int precision = old->precision, fusion = old->fusion, head_sync = old->head_sync;
+    b200_engine_destroy(old);
+    const int default_fusion = b200_get_default_fusion();
+    b200_set_default_fusion(fusion);
+    b200_engine *e = b200_engine_create(net, precision);
+    b200_set_default_fusion(default_fusion);
+    e->head_sync = head_sync;
+    if (e->device >= 0) b200_engine_upload_weights(e, net);
+    return e;
+}
+
 extern "C" void *b200_weights_arena(network *net, size_t *bytes)
 {
     b200_engine *e = b200_engine_of(net);

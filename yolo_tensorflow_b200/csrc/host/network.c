@@ -231,11 +231,90 @@ float *network_predict_image(network *net, image im)
     return p;
 }
 
+/* resize_network (network.c:358-438): re-derive every layer's geometry for a new input size, re-allocate the host
+ * outputs, and re-plan the device engine (buffers, TMA descriptors, tiling) around the parameters already loaded. */
+static float *regrow(float *p, size_t n)
+{
+    free(p);
+    return calloc(n ? n : 1, sizeof(float));
+}
+
 int resize_network(network *net, int w, int h)
 {
-    (void)net; (void)w; (void)h;
-    fprintf(stderr, "b200-darknet: resize_network is not implemented yet (SURVEY.md §8f-3); re-parse the cfg with the new size\n");
-    return -1;
+    network_box *nb = (network_box *)net;
+    int cw = w, ch = h, cc = net->c;
+    for (int i = 0; i < net->n; ++i) {
+        layer *l = &net->layers[i];
+        switch (l->type) {
+        case CONVOLUTIONAL:
+            l->w = cw; l->h = ch;
+            l->out_w = (l->w + 2 * l->pad - l->size) / l->stride + 1;
+            l->out_h = (l->h + 2 * l->pad - l->size) / l->stride + 1;
+            break;
+        case MAXPOOL:
+            l->w = cw; l->h = ch;
+            l->out_w = (l->w + 2 * l->pad) / l->stride;
+            l->out_h = (l->h + 2 * l->pad) / l->stride;
+            break;
+        case UPSAMPLE:
+            l->w = cw; l->h = ch;
+            l->out_w = cw * l->stride; l->out_h = ch * l->stride;
+            break;
+        case REORG:
+            l->w = cw; l->h = ch;
+            l->out_w = cw / l->stride; l->out_h = ch / l->stride;
+            break;
+        case SHORTCUT: {
+            const layer *src = &net->layers[l->index];
+            l->w = src->out_w; l->h = src->out_h;
+            l->out_w = cw; l->out_h = ch;
+            break;
+        }
+        case ROUTE: {
+            const layer *first = &net->layers[l->input_layers[0]];
+            l->out_w = first->out_w; l->out_h = first->out_h; l->out_c = first->out_c;
+            l->outputs = 0;
+            for (int j = 0; j < l->n; ++j) {
+                const layer *in = &net->layers[l->input_layers[j]];
+                l->input_sizes[j] = in->outputs;
+                l->outputs += in->outputs;
+                if (j > 0) {
+                    if (in->out_w == first->out_w && in->out_h == first->out_h) l->out_c += in->out_c;
+                    else l->out_w = l->out_h = l->out_c = 0;
+                }
+            }
+            l->w = l->out_w; l->h = l->out_h; l->c = l->out_c;
+            l->inputs = l->outputs;
+            break;
+        }
+        case YOLO: case REGION:
+            l->w = l->out_w = cw; l->h = l->out_h = ch;
+            break;
+        case DROPOUT:
+            l->w = l->out_w = cw; l->h = l->out_h = ch;
+            break;
+        default:
+            fprintf(stderr, "Cannot resize this type of layer\n");      /* network.c:428 (local/connected/detection) */
+            return -1;
+        }
+        if (l->type != ROUTE) {
+            l->inputs = l->w * l->h * l->c;
+            l->outputs = l->out_w * l->out_h * l->out_c;
+            if (l->type == SHORTCUT) l->inputs = l->outputs;
+            if (l->type == DROPOUT) l->inputs = l->outputs = cw * ch * cc;
+        }
+        if (l->type == DROPOUT) l->output = net->layers[i - 1].output;
+        else l->output = regrow(l->output, (size_t)l->batch * l->outputs);
+        cw = l->out_w; ch = l->out_h; cc = l->out_c;
+    }
+    net->w = w; net->h = h;
+    net->inputs = w * h * net->c;
+    layer out = get_network_output_layer(net);
+    net->outputs = out.outputs;
+    net->output = out.output;
+    net->input = regrow(net->input, (size_t)net->inputs * net->batch);
+    nb->engine = b200_engine_recreate(nb->engine, net);
+    return 0;
 }
 
 void free_layer(layer l) { release_layer_host(l); }

@@ -88,6 +88,7 @@ lib.b200_layer_kernel.argtypes = [c_void_p, c_int]; lib.b200_layer_kernel.restyp
 lib.b200_launch_count.restype = c_ulonglong
 lib.b200_layer_plan.argtypes = [c_void_p, c_int]; lib.b200_layer_plan.restype = c_char_p
 lib.b200_network_layers.argtypes = [c_void_p]; lib.b200_network_layers.restype = c_int
+lib.resize_network.argtypes = [c_void_p, c_int, c_int]; lib.resize_network.restype = c_int
 lib.b200_layer_info.argtypes = [c_void_p, c_int, POINTER(c_int)]; lib.b200_layer_info.restype = c_int
 lib.b200_layer_output_host.argtypes = [c_void_p, c_int]; lib.b200_layer_output_host.restype = POINTER(c_float)
 lib.b200_weights_arena.argtypes = [c_void_p, POINTER(c_size_t)]; lib.b200_weights_arena.restype = c_void_p
@@ -138,6 +139,13 @@ class Network:
         self.w, self.h = lib.network_width(self.ptr), lib.network_height(self.ptr)
         self.layers = [self.layer_info(i) for i in range(self.n)]
         self.batch = self.layers[0]["batch"]
+
+    def resize(self, w, h):
+        """resize_network (network.c:358): new input size, same parameters; returns 0, or -1 for unresizable layers."""
+        rc = lib.resize_network(self.ptr, int(w), int(h))
+        self.w, self.h = lib.network_width(self.ptr), lib.network_height(self.ptr)
+        self.layers = [self.layer_info(i) for i in range(self.n)]
+        return rc
 
     def close(self):
         if self.ptr:
