@@ -211,23 +211,35 @@ SHAPES = [  # h, w, c, filters, size, stride, batch
     (9, 9, 256, 1024, 1, 1, 4),      # four filter tiles
     (16, 16, 64, 48, 5, 1, 2),       # 5x5 taps
     (7, 7, 1024, 425, 1, 1, 3),      # YOLOv2 head shape: 425 filters -> 432 padded, ragged last filter tile
+    (40, 56, 32, 64, 3, 1, 3),       # patch kernel, stride 1, C=32 (64-byte rows), ragged right/bottom tiles
+    (33, 44, 32, 64, 3, 2, 2),       # patch kernel, stride 2 on pixel-pair rows, odd height
+    (21, 37, 32, 128, 3, 1, 2),      # patch kernel, stride 1, 128 filters (two 64-channel sub-tiles), odd sizes
+    (40, 56, 32, 64, 3, 1, 3, "tap"),    # the same shapes through the tap-per-box kernels (B200_NO_PATCH)
+    (26, 26, 32, 64, 3, 2, 3, "tap"),
 ]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
 def test_conv_tc_shape(dn, shape, tmp_path):
-    h, w, c, filters, size, stride, batch = shape
+    h, w, c, filters, size, stride, batch = shape[:7]
+    tap_only = len(shape) > 7
     cfg = str(tmp_path / "one.cfg")
     act = "linear" if filters in (255, 425) else "leaky"
     single_conv_cfg(cfg, h, w, c, filters, size, stride, batch, bn=0 if act == "linear" else 1, act=act)
     wpath = str(tmp_path / "one.weights")
     synth.write_weights(cfg, wpath, seed=3, damp_heads=False)
     fd = os.dup(2); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 2)
+    if tap_only:
+        os.environ["B200_NO_PATCH"] = "1"
     try:
         net = dn.Network(cfg, wpath, precision=dn.PREC_BF16)
     finally:
+        os.environ.pop("B200_NO_PATCH", None)
         os.dup2(fd, 2); os.close(fd); os.close(devnull)
     assert net.kernel(1) == "conv_tc"
+    plan = dn.lib.b200_layer_plan(net.ptr, 1).decode()
+    patchable = size == 3 and c == 32 and filters in (64, 128) and (stride == 1 or (stride == 2 and w % 2 == 0))
+    assert ("PATCH" in plan) == (patchable and not tap_only), plan
     port = P.Net(cfg, wpath)
     x = synth.make_images(batch, 3, h, w, 5)
     outs = port.forward(x)
@@ -417,10 +429,11 @@ def test_resize_network_matches_fresh_parse(dn, model, prec, workdir):
     assert a.shape == b.shape and np.array_equal(a, b)
     ra, ca = net.detect_batch(x, 224, 224, .3, .45)
     rb, cb = fresh.detect_batch(x, 224, 224, .3, .45)
-    assert len(ra) > 0 and np.array_equal(ca, cb) and ra.tobytes() == rb.tobytes()
+    order = lambda r: r[np.lexsort((r["cls"], r["box_id"], r["image"]))]
+    assert len(ra) > 0 and np.array_equal(ca, cb) and order(ra).tobytes() == order(rb).tobytes()
     assert net.resize(160, 160) == 0                       # and back: identical to the first run
     again = net.detect_batch(x160, 160, 160, .3, .45)
-    assert again[0].tobytes() == before[0].tobytes() and np.array_equal(again[1], before[1])
+    assert order(again[0]).tobytes() == order(before[0]).tobytes() and np.array_equal(again[1], before[1])
     net.close(); fresh.close()
 
 

@@ -194,6 +194,14 @@ struct ConvTcArgs {
     int acc_stages;          // TMEM accumulator buffers (2..8): small filter tiles let the MMA run many tiles ahead of the epilogue
     int staged;              // 1: epilogue goes TMEM -> registers -> swizzled smem tile -> TMA store (and TMA-loads the residual)
     int pair;                // 1: cta_group::2 kernel (two CTAs share one 256 x block_n accumulator tile and its weights)
+    // single-CTA patch kernel (mode 2, pair 0): one K pass per tile over resident weights
+    int np;                  // activation patches per tile (1: stride 1; 2: stride 2 on pixel-pair rows)
+    int patch_map[4], patch_off[4], patch_dx[4], patch_dy[4];     // tensor map, byte offset in the stage, box origin relative to the tile
+    int stage_tx;            // bytes all patch boxes of a tile deliver
+    int a_k, b_k;            // elements per smem row of the patches / of the weight tiles (-> swizzle mode)
+    int nb, b_koff[12];      // resident weight tiles: K offset of each [block_n x b_k] box
+    int nseg, seg_a[12], seg_b[12], seg_k[12];   // K segments: patch byte offset (row shift), weight byte offset, K/16 steps
+    int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
     long long npix;
     const float *scale, *shift;
     void *out;
@@ -812,6 +820,297 @@ conv_tc_halo_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcAr
 }
 
 // ---------------------------------------------------------------------------------------------------
+// single-CTA patch kernel for the layers with few input channels (Cin = 32 / 64, 3x3).  The tap-per-box kernels above
+// pull size^2 activation rows per output pixel through TMA (64-byte rows when Cin = 32) and are bound by the TMA row
+// rate (~3 cycles a row), not by the tensor pipe.  Here a tile's input arrives ONCE as a halo patch, every tap's A
+// operand is a row-shifted descriptor into it (see the CTA-pair patch kernel), and ALL weights stay resident, so a
+// tile costs ~1.5 activation rows per output pixel and the layer becomes HBM-bound.
+//   stride 1: one patch [(TH+2) x (TW+2)] pixels, 9 K-segments of Cin.
+//   stride 2, Cin = 32: the input is viewed as rows of PIXEL PAIRS (2 x 32 channels = 128 bytes) of one row parity;
+//   taps kx = 1,2 are one K = 64 segment of pair ox, tap kx = 0 is the upper half (K = 32) of pair ox - 1.
+// The segment table is built by the host (ConvTcArgs::seg_*).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc_rt(uint32_t smem_addr, int k)
+{
+    const uint64_t layout = k == 64 ? 2 : (k == 32 ? 4 : 6);
+    const uint64_t sbo = (uint64_t)(8 * k * 2) >> 4;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// Whole-warp (convergent) issue: every lane runs the role's loop and ONE elected lane issues the tensor-core instruction.
+// Issuing from inside `if (lane == 0)` makes the compiler wrap each UTCHMMA in a move-to-uniform + elect loop (~13
+// instructions, ~80 cycles of dependent issue per MMA), which bounds a short K pass; here the operands stay in uniform registers.
+__device__ __forceinline__ void tc_mma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t *bar)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// persistent-tile walker: tile = first, first + step, ... decoded into (tx, ty, tn) without a division per tile
+struct TileWalk {
+    int tx, ty, tn, sx, sy, sn;
+    __device__ __forceinline__ void init(int first, int step, int tiles_x, int tiles_y)
+    {
+        tx = first % tiles_x; ty = (first / tiles_x) % tiles_y; tn = first / (tiles_x * tiles_y);
+        sx = step % tiles_x;  sy = (step / tiles_x) % tiles_y;  sn = step / (tiles_x * tiles_y);
+    }
+    __device__ __forceinline__ void next(int tiles_x, int tiles_y)
+    {
+        tx += sx; if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+        ty += sy; if (ty >= tiles_y) { ty -= tiles_y; ++tn; }
+        tn += sn;
+    }
+};
+
+template <int PENDING> __device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+__device__ __forceinline__ void group_sync(int group)            // the 128 threads of one epilogue group
+{
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+// Warp roles: warp 0 = TMA producer (patches + residual tiles), warp 1 = MMA issuer, warp 2 = TMA store warp, then
+// `ep_groups` groups of four epilogue warps that take alternate tiles.  The output leaves through a ring of `c_bufs`
+// swizzled tiles: a tile's residual is TMA-loaded into its ring slot tiles ahead of time, the epilogue adds the activation
+// in place, the store warp TMA-stores the slot and frees it once the store engine has read it.  With a K pass this short
+// (18 MMAs) everything else on a tile's path has to be off the critical path: no role waits on a DRAM round trip or on
+// another role's bookkeeping, and the roles talk through mbarriers only.
+// mbar_wait as a macro: the spin shows up at the CALL SITE's line in profiler source views (which wait is the hot one)
+#define MBAR_WAIT_HERE(bar, parity)                                                                                      \
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"        \
+                 "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"((uint32_t)(parity)) : "memory")
+
+template <int NSUB, int NSEG, int KS0, int KS1>       // K segment s issues (s odd ? KS1 : KS0) K=16 steps
+__global__ void __launch_bounds__(352, 1)
+conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
+{
+    constexpr int N = NSUB * 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stages = args.stages;
+    uint8_t *sA = smem;                                              // patch ring
+    uint8_t *sB = sA + (size_t)stages * args.a_stage_bytes;          // nb resident weight tiles
+    uint8_t *sC = sB + (size_t)args.nb * args.b_stage_bytes;         // output ring: c_bufs x NSUB x 16 KB
+    uint8_t *aux = sC + (size_t)args.c_bufs * NSUB * 16384;
+    uint64_t *full = (uint64_t *)aux;                                // [8]
+    uint64_t *empty = full + 8;                                      // [8]
+    uint64_t *tfull = empty + 8;                                     // [8]
+    uint64_t *tempty = tfull + 8;                                    // [8]
+    uint64_t *cfull = tempty + 8;                                    // [8] residual landed in ring slot
+    uint64_t *cempty = cfull + 8;                                    // [8] ring slot read out by its store
+    uint64_t *cwritten = cempty + 8;                                 // [8] ring slot written by the four epilogue warps
+    uint64_t *wfull = cwritten + 8;
+    uint32_t *tmem_slot = (uint32_t *)(wfull + 1);
+    float *s_scale = (float *)(aux + 512);
+    float *s_shift = s_scale + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = args.m_tiles;
+    const int G = args.ep_groups, NBUF = args.c_bufs;
+    const bool has_res = args.res != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < args.acc_stages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&cfull[i], 1); mbar_init(&cempty[i], 1); mbar_init(&cwritten[i], 4); }
+        mbar_init(wfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(args.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0 && (int)blockIdx.x < num_tiles) {
+            mbar_expect_tx(wfull, (uint32_t)(args.nb * N * args.b_k * 2));
+            for (int i = 0; i < args.nb; ++i) tma_load_2d(&maps.b, sB + (size_t)i * args.b_stage_bytes, wfull, args.b_koff[i], 0);
+            int stage = 0; uint32_t phase = 0;
+            int cb = 0; uint32_t cphase = 0;
+            TileWalk t; t.init(blockIdx.x, gridDim.x, args.tiles_x, args.tiles_y);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, t.next(args.tiles_x, args.tiles_y)) {
+                const int ox0 = t.tx * args.halo_TWv, oy0 = t.ty * args.halo_THv;
+                MBAR_WAIT_HERE(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], (uint32_t)args.stage_tx);
+                uint8_t *dst = sA + (size_t)stage * args.a_stage_bytes;
+                for (int q = 0; q < args.np; ++q)
+                    tma_load_4d(&maps.a[args.patch_map[q]], dst + args.patch_off[q], &full[stage], 0, ox0 + args.patch_dx[q], oy0 + args.patch_dy[q], t.tn);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+                if (has_res) {
+                    int rows_here = args.OH - oy0; if (rows_here > args.halo_THv) rows_here = args.halo_THv;
+                    MBAR_WAIT_HERE(&cempty[cb], cphase ^ 1);
+                    mbar_expect_tx(&cfull[cb], (uint32_t)(rows_here * args.halo_TWv * 128 * NSUB));
+                    uint8_t *cdst = sC + (size_t)cb * NSUB * 16384;
+                    for (int q = 0; q < NSUB; ++q)
+                        for (int yy = 0; yy < rows_here; ++yy)
+                            tma_load_4d(&maps.r, cdst + q * 16384 + yy * args.halo_P * 128, &cfull[cb], 64 * q, ox0, oy0 + yy, t.tn);
+                    if (++cb == NBUF) { cb = 0; cphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if ((int)blockIdx.x < num_tiles) {                 // all 32 lanes walk the loop; one elected lane issues
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            // every descriptor is a constant offset from the stage's base descriptor: keep the offsets in registers and
+            // unroll the whole K pass, so issuing a tile is 18 back-to-back MMAs with no loads or address math between them
+            uint32_t a_off[NSEG]; uint64_t bdesc[NSEG];
+#pragma unroll
+            for (int sgm = 0; sgm < NSEG; ++sgm) {
+                a_off[sgm] = (uint32_t)args.seg_a[sgm] >> 4;
+                bdesc[sgm] = make_desc_rt(smem_u32(sB) + (uint32_t)args.seg_b[sgm], args.b_k);
+            }
+            const uint64_t adesc0 = make_desc_rt(smem_u32(sA), args.a_k);
+            const uint32_t stage_step = (uint32_t)args.a_stage_bytes >> 4;
+            MBAR_WAIT_HERE(wfull, 0);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                MBAR_WAIT_HERE(&tempty[acc], acc_phase ^ 1);
+                MBAR_WAIT_HERE(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)stage * stage_step);
+#pragma unroll
+                for (int sgm = 0; sgm < NSEG; ++sgm) {
+#pragma unroll
+                    for (int k = 0; k < ((sgm & 1) ? KS1 : KS0); ++k)
+                        tc_mma_bf16_elect(d_tmem, adesc + (uint64_t)(a_off[sgm] + 2 * k), bdesc[sgm] + (uint64_t)(2 * k), idesc, (sgm | k) != 0 ? 1u : 0u);
+                }
+                tc_commit_elect(&empty[stage]);
+                tc_commit_elect(&tfull[acc]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+                if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================== store warp =======================================
+        // takes a ring slot once the four epilogue warps have written it, TMA-stores it (one box per image row: the tile
+        // is patch-pitched in smem) and frees the slot when the store engine has read it
+        if (lane == 0) {
+            TileWalk t; t.init(blockIdx.x, gridDim.x, args.tiles_x, args.tiles_y);
+            int cb = 0; uint32_t cphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, t.next(args.tiles_x, args.tiles_y)) {
+                const int ox0 = t.tx * args.halo_TWv, oy0 = t.ty * args.halo_THv;
+                int rows_here = args.OH - oy0; if (rows_here > args.halo_THv) rows_here = args.halo_THv;
+                const uint8_t *src = sC + (size_t)cb * NSUB * 16384;
+                MBAR_WAIT_HERE(&cwritten[cb], cphase);
+                for (int q = 0; q < NSUB; ++q)
+                    for (int yy = 0; yy < rows_here; ++yy)
+                        tma_store_4d(&maps.c, src + q * 16384 + yy * args.halo_P * 128, 64 * q, ox0, oy0 + yy, t.tn);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                bulk_wait_read<0>();
+                mbar_arrive(&cempty[cb]);
+                if (++cb == NBUF) { cb = 0; cphase ^= 1; }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else {
+        // ===================================== epilogue groups ==================================
+        const int g = (warp - 3) >> 2;
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+        const int row = quarter * 32 + lane;
+        const int ep_tid = threadIdx.x - 96 - 128 * g;
+        for (int c = ep_tid; c < N; c += 128) { s_scale[c] = args.scale[c]; s_shift[c] = args.shift[c]; }   // every group writes the same values
+        group_sync(g);
+        const bool leaky = args.act == ACT_LEAKY;
+        const float alpha = args.res_alpha, beta = args.res_beta;
+        const uint32_t scale_addr = smem_u32(s_scale), shift_addr = smem_u32(s_shift);
+        const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
+        int i = g;                                         // CTA-local tile counter
+        for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += G * gridDim.x, i += G) {
+            const int acc = i % args.acc_stages;
+            const uint32_t acc_phase = (uint32_t)(i / args.acc_stages) & 1u;
+            const int cb = i % NBUF;
+            const uint32_t cphase = (uint32_t)(i / NBUF) & 1u;
+            const uint32_t slot = smem_u32(sC + (size_t)cb * NSUB * 16384);
+            if (has_res) MBAR_WAIT_HERE(&cfull[cb], cphase);          // residual landed (the producer waited for the slot)
+            else MBAR_WAIT_HERE(&cempty[cb], cphase ^ 1);             // slot free
+            MBAR_WAIT_HERE(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll
+            for (int c0 = 0; c0 < N; c0 += 64) {
+                uint32_t r[64];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld32(taddr + c0 + 32, r + 32);
+                tmem_ld_wait();
+                if (c0 + 64 == N) {                        // accumulator fully read: hand it back before the math
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+#pragma unroll
+                for (int j = 0; j < 64; j += 8) {
+                    const uint32_t addr = slot + (uint32_t)(c0 >> 6) * 16384u + row_off + ((((uint32_t)j >> 3) ^ row_x) << 4);
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q += 4) {
+                        const uint4 s4 = lds128(scale_addr + (uint32_t)(c0 + j + q) * 4u);
+                        const uint4 h4 = lds128(shift_addr + (uint32_t)(c0 + j + q) * 4u);
+                        v[q + 0] = fmaf(__uint_as_float(r[j + q + 0]), __uint_as_float(s4.x), __uint_as_float(h4.x));
+                        v[q + 1] = fmaf(__uint_as_float(r[j + q + 1]), __uint_as_float(s4.y), __uint_as_float(h4.y));
+                        v[q + 2] = fmaf(__uint_as_float(r[j + q + 2]), __uint_as_float(s4.z), __uint_as_float(h4.z));
+                        v[q + 3] = fmaf(__uint_as_float(r[j + q + 3]), __uint_as_float(s4.w), __uint_as_float(h4.w));
+                    }
+                    if (leaky) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : 0.1f * v[q];
+                    }
+                    if (has_res) {
+                        const uint4 rr = lds128(addr);
+                        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __bfloat1622float2(h[q]);
+                            v[2 * q] = fmaf(alpha, v[2 * q], beta * f.x);
+                            v[2 * q + 1] = fmaf(alpha, v[2 * q + 1], beta * f.y);
+                        }
+                    }
+                    uint4 o;
+                    __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                    sts128(addr, o);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cwritten[cb]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(args.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -925,8 +1224,31 @@ template <typename OutT> static void launch_halo_variant(ConvTcPlan *p, cudaStre
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_halo_pair_kernel<OutT>, p->maps, p->args));
 }
 
+template <int NSUB, int NSEG, int KS0, int KS1> static void launch_patch_variant(ConvTcPlan *p, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_patch_kernel<NSUB, NSEG, KS0, KS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    conv_tc_patch_kernel<NSUB, NSEG, KS0, KS1><<<p->grid, 96 + 128 * p->args.ep_groups, p->smem_bytes, s>>>(p->maps, p->args);
+}
+template <int NSUB> static void launch_patch(ConvTcPlan *p, cudaStream_t s)
+{
+    const ConvTcArgs &a = p->args;
+    if (a.nseg == 6) launch_patch_variant<NSUB, 6, 4, 2>(p, s);                 // stride 2 on pixel-pair rows
+    else if (a.seg_k[0] == 2) launch_patch_variant<NSUB, 9, 2, 2>(p, s);        // stride 1, 32 channels
+    else launch_patch_variant<NSUB, 9, 4, 4>(p, s);                             // stride 1, 64 channels
+}
+
 void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
 {
+    if (p->args.mode == 2 && !p->args.pair) {
+        if (p->args.block_n == 64) launch_patch<1>(p, s);
+        else launch_patch<2>(p, s);
+        B200_LAUNCHED();
+        return;
+    }
     if (p->args.mode == 2) {
         if (p->out_dtype == DT_BF16) launch_halo_variant<bf16>(p, s);
         else launch_halo_variant<float>(p, s);
@@ -1047,6 +1369,119 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                     void *base = (unsigned char *)in.p + ((size_t)py * in.w + px) * in.ld * esz;
                     encode(&p->maps.a[py * 2 + px], base, 4, dims, strides, box, block_k);
                 }
+        }
+    }
+    // ---- single-CTA patch kernel (mode 2, pair 0): few input channels, all weights resident ----------------------------
+    if (a.mode == 1 && !getenv("B200_NO_PATCH") && cp.size == 3 && cp.pad == 1 && out.dtype == DT_BF16 && a.n_tiles == 1 &&
+        (cp.cout_pad == 64 || cp.cout_pad == 128) && out.c == cp.cout_pad &&
+        ((cp.stride == 1 && (C == 32 || C == 64)) || (cp.stride == 2 && C == 32 && in.ld == 32 && in.w % 2 == 0))) {
+        const bool s2 = cp.stride == 2;
+        const int a_k = s2 ? 64 : C, b_k = a_k, row_bytes = a_k * 2;
+        const int halo_x = s2 ? 1 : 2;
+        const int N = a.block_n;
+        const int nb = s2 ? 6 : 9;
+        const int b_tile = (N * b_k * 2 + 1023) / 1024 * 1024;
+        int groups = 2;
+        if (getenv("B200_PATCH_GROUPS")) groups = atoi(getenv("B200_PATCH_GROUPS")) == 1 ? 1 : 2;
+        const int aux_bytes = 512 + 2 * 512 * 4, slot_bytes = (N / 64) * 16384;
+        const int np = s2 ? 2 : 1;
+        auto stage_bytes_for = [&](int P) {
+            const int max_shift = s2 ? P + 1 : 2 * P + 2;
+            return np * (((max_shift + 128) * row_bytes + 1023) / 1024 * 1024);
+        };
+        const int room = 227 * 1024 - 1024 - aux_bytes - nb * b_tile;         // patch ring + output ring share this
+        // tile: P = TW + halo_x patch columns, TH = 128 / P rows.  MEASURED (YOLOv3 layers 1 and 3): a tile costs about
+        // 4 cycles per TMA row moved (patch + store + residual rows) plus ~38 cycles per TMA instruction.
+        double best = 1e30; int bTW = 0;
+        for (int tw = 4; tw <= out.w && tw + halo_x <= 128; ++tw) {
+            int P = tw + halo_x, th = 128 / P; if (th > out.h) th = out.h;
+            if (3 * stage_bytes_for(P) + 2 * slot_bytes > room) continue;
+            double tiles = (double)div_up(out.w, tw) * div_up(out.h, th);
+            double rows = (s2 ? (2.0 * th + 1) * P : (th + 2.0) * P) + (residual ? 2.0 : 1.0) * th * tw * (N / 64);
+            double ops = np + (residual ? 2.0 : 1.0) * th * (N / 64);
+            double cost = tiles * (4.0 * rows + 38.0 * ops);
+            if (cost < best) { best = cost; bTW = tw; }
+        }
+        if (getenv("B200_PATCH_TW")) { int f = atoi(getenv("B200_PATCH_TW")); if (f >= 1 && f <= out.w && 3 * stage_bytes_for(f + halo_x) + 2 * slot_bytes <= room) bTW = f; }
+        if (bTW) {
+            const int TWv = bTW, P = TWv + halo_x;
+            int TH = 128 / P; if (TH > out.h) TH = out.h;
+            const int stage_bytes = stage_bytes_for(P), patch_bytes = stage_bytes / np;
+            // output ring: a fused residual is prefetched into its slot tiles ahead of the epilogue, so it wants the deeper
+            // ring; whatever is left goes to patch stages (3 are enough to cover the load latency, more do not help)
+            int c_bufs = residual ? 6 : 3;      // measured on YOLOv3 layer 3: 6 slots + 6 stages beat 8 + 4 and 4 + 8
+            while (c_bufs > 2 && 3 * stage_bytes + c_bufs * slot_bytes > room) --c_bufs;
+            if (getenv("B200_PATCH_CBUFS")) { int f = atoi(getenv("B200_PATCH_CBUFS")); if (f >= 2 && f <= 8 && 2 * stage_bytes + f * slot_bytes <= room) c_bufs = f; }
+            const int sc_bytes = c_bufs * slot_bytes;
+            int st = (room - sc_bytes) / stage_bytes; if (st > 8) st = 8;
+            if (getenv("B200_PATCH_STAGES")) { int f = atoi(getenv("B200_PATCH_STAGES")); if (f >= 2 && f < st) st = f; }
+            if (st >= 2) {
+                a.mode = 2; a.pair = 0; a.resident_b = 1; a.staged = 1;
+                a.halo_P = P; a.halo_TWv = TWv; a.halo_THv = TH;
+                a.TW = TWv; a.TH = TH; a.TN = 1;
+                a.tiles_x = div_up(out.w, TWv); a.tiles_y = div_up(out.h, TH);
+                a.m_tiles = a.tiles_x * a.tiles_y * in.n;
+                a.a_rows = TH * P;
+                a.np = np; a.a_k = a_k; a.b_k = b_k; a.nb = nb;
+                a.ep_groups = groups; a.c_bufs = c_bufs;
+                a.a_stage_bytes = stage_bytes; a.b_stage_bytes = b_tile; a.stages = st;
+                if (!s2) {
+                    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+                    cuuint64_t strides[3] = {(cuuint64_t)in.ld * esz, (cuuint64_t)in.w * in.ld * esz, (cuuint64_t)in.h * in.w * in.ld * esz};
+                    cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)P, (cuuint32_t)(TH + 2), 1};
+                    encode(&p->maps.a[0], in.p, 4, dims, strides, box, a_k);
+                    a.patch_map[0] = 0; a.patch_off[0] = 0; a.patch_dx[0] = -1; a.patch_dy[0] = -1;
+                    a.stage_tx = (TH + 2) * P * row_bytes;
+                    a.nseg = 9;
+                    for (int t = 0; t < 9; ++t) {
+                        a.b_koff[t] = t * C;
+                        a.seg_a[t] = ((t / 3) * P + (t % 3)) * row_bytes;
+                        a.seg_b[t] = t * b_tile;
+                        a.seg_k[t] = C / 16;
+                    }
+                } else {
+                    // rows of pixel pairs of one row parity: dims {64, W/2, rows of that parity, N}
+                    for (int py = 0; py < 2; ++py) {
+                        const int ph = (in.h - py + 1) / 2;
+                        cuuint64_t dims[4] = {64, (cuuint64_t)(in.w / 2), (cuuint64_t)(ph < 1 ? 1 : ph), (cuuint64_t)in.n};
+                        cuuint64_t strides[3] = {(cuuint64_t)128, (cuuint64_t)2 * in.w * 64, (cuuint64_t)in.h * in.w * 64};
+                        cuuint32_t box[4] = {64, (cuuint32_t)P, (cuuint32_t)(py ? TH + 1 : TH), 1};
+                        encode(&p->maps.a[py], (unsigned char *)in.p + (size_t)py * in.w * 64, 4, dims, strides, box, 64);
+                    }
+                    // patch 0 = odd input rows (taps ky = 0, 2), patch 1 = even input rows (tap ky = 1)
+                    a.patch_map[0] = 1; a.patch_off[0] = 0;           a.patch_dx[0] = -1; a.patch_dy[0] = -1;
+                    a.patch_map[1] = 0; a.patch_off[1] = patch_bytes; a.patch_dx[1] = -1; a.patch_dy[1] = 0;
+                    a.stage_tx = ((TH + 1) + TH) * P * row_bytes;
+                    a.nseg = 6;
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int base = (ky == 1 ? patch_bytes : 0) + (ky == 2 ? P : 0) * row_bytes;
+                        a.b_koff[2 * ky] = ky * 96 + 32;  a.b_koff[2 * ky + 1] = ky * 96;
+                        a.seg_a[2 * ky] = base + row_bytes;   a.seg_b[2 * ky] = (2 * ky) * b_tile;         a.seg_k[2 * ky] = 4;      // kx = 1,2: pair ox
+                        a.seg_a[2 * ky + 1] = base + 64;      a.seg_b[2 * ky + 1] = (2 * ky + 1) * b_tile; a.seg_k[2 * ky + 1] = 2;  // kx = 0: upper half of pair ox-1
+                    }
+                }
+                {
+                    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cp.cout_pad};
+                    cuuint64_t strides[1] = {(cuuint64_t)K * esz};
+                    cuuint32_t box[2] = {(cuuint32_t)b_k, (cuuint32_t)N};
+                    encode(&p->maps.b, (void *)cp.w, 2, dims, strides, box, b_k);
+                }
+                encode_tile_view(&p->maps.c, out, cp.cout_pad, a);
+                if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a);
+                int fit = 512 / N;
+                a.acc_stages = fit >= 8 ? 8 : (fit >= 4 ? 4 : 2);
+                if (getenv("B200_PATCH_ACC")) { int f = atoi(getenv("B200_PATCH_ACC")); if (f >= 1 && f < a.acc_stages) a.acc_stages = f; }
+                int cols = a.acc_stages * N;
+                a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+                p->grid = a.m_tiles < 148 ? a.m_tiles : 148;
+                p->smem_bytes = (size_t)st * stage_bytes + (size_t)nb * b_tile + sc_bytes + aux_bytes + 1024;
+                p->flops = 2.0 * (double)a.npix * out.c * K;
+                char buf3[320];
+                snprintf(buf3, sizeof buf3, "conv_tc PATCH s%d k%d n%d tile %dx%d (pitch %d) m_tiles %d patches %d segs %d stages %d acc %d ring %d groups %d smem %zu grid %d residentB%s stagedEpilogue",
+                         cp.stride, a_k, N, TWv, TH, P, a.m_tiles, np, a.nseg, st, a.acc_stages, c_bufs, groups, p->smem_bytes, p->grid, a.res ? " +residual" : "");
+                p->desc = buf3;
+                return p;
+            }
         }
     }
     // ---- halo-patch mode (mode 2): stride-1 odd-size convolutions, one patch load per 64-channel block -----------------
