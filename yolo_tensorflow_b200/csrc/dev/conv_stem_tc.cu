@@ -1,0 +1,462 @@
+// conv_stem_tc.cu — the network's first convolution (3 input channels, 3x3, stride 1, 16 or 32 filters) on tcgen05.
+//
+// What it replaces: forward_convolutional_layer for layer 0 (convolutional_layer.c:445-485: im2col_cpu + gemm_nn +
+// batch-norm + leaky) fused with the input's layout / precision conversion.  The CUDA-core stem spends 27 x C_out FMAs
+// per pixel and is FMA-bound (0.74 ms for 64 x 416 x 416, 26 TFLOP/s); the layer's traffic (133 MB fp32 in, 709 MB bf16
+// out) is worth ~0.13 ms of HBM time.  Here the 27-tap window of every pixel is gathered straight from the fp32 NCHW input
+// into a K-major, 64B-swizzled [128 pixels x 32] bf16 tile in shared memory (K = 27 padded to 32: an im2col that never
+// leaves the SM), ONE pair of tcgen05.mma (M = 128, N = C_out, K = 2 x 16) per tile does the arithmetic, and the epilogue
+// applies folded batch-norm + leaky and writes NHWC bf16.
+//
+// Warp roles (416 threads, persistent over 16 x 8 pixel tiles): warp 0 = MMA issuer + TMEM owner, warps 1-8 = two
+// gather groups taking alternate tiles (hides the global-load latency of the window gather), warps 9-12 = epilogue.
+// Everything is handed over through mbarriers: gather -> afull -> MMA -> (aempty, tfull) -> epilogue -> tempty.
+//
+// Roofline: HBM.  Algorithmic bytes per pixel = 3 x 4 (fp32 in) + C_out x 2 (bf16 out).
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int kTW = 16, kTH = 8;            // pixel tile (128 GEMM rows)
+constexpr int kSlots = 4;                   // A-tile ring
+constexpr int kAcc = 4;                     // TMEM accumulator ring
+constexpr int kThreads = 13 * 32;
+
+struct StemTcArgs {
+    const float *in;                        // fp32 NCHW
+    bf16 *out;                              // bf16 NHWC, row pitch ldo
+    const bf16 *w;                          // [NOUT][27], K order (ky, kx, c)
+    const float *scale, *shift;
+    int N, H, W, ldo, act;
+    int tiles_x, tiles_y, num_tiles;
+};
+
+struct Walk {                               // tile = first, first + step, ... -> (tx, ty, n) without a division per tile
+    int tx, ty, tn, sx, sy, sn;
+    __device__ __forceinline__ void init(int first, int step, int tiles_x, int tiles_y)
+    {
+        tx = first % tiles_x; ty = (first / tiles_x) % tiles_y; tn = first / (tiles_x * tiles_y);
+        sx = step % tiles_x;  sy = (step / tiles_x) % tiles_y;  sn = step / (tiles_x * tiles_y);
+    }
+    __device__ __forceinline__ void next(int tiles_x, int tiles_y)
+    {
+        tx += sx; if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+        ty += sy; if (ty >= tiles_y) { ty -= tiles_y; ++tn; }
+        tn += sn;
+    }
+};
+
+#define STEM_WAIT(bar, parity)                                                                                          \
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"        \
+                 "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"((uint32_t)(parity)) : "memory")
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+template <int NOUT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stem_tc_kernel(const StemTcArgs a)
+{
+    __shared__ __align__(1024) uint8_t sA[kSlots][128 * 64];        // [128 rows][32 K] bf16, 64B-swizzled
+    __shared__ __align__(1024) uint8_t sB[NOUT * 64];               // [NOUT rows][32 K] bf16, 64B-swizzled
+    __shared__ uint64_t afull[kSlots], aempty[kSlots], tfull[kAcc], tempty[kAcc];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = a.num_tiles;
+
+    // weights -> swizzled B tile (K padded 27 -> 32 with zeros)
+    for (int idx = threadIdx.x; idx < NOUT * 32; idx += kThreads) {
+        const int co = idx >> 5, k = idx & 31;
+        const bf16 v = k < 27 ? a.w[co * 27 + k] : __float2bfloat16(0.f);
+        *reinterpret_cast<bf16 *>(sB + co * 64 + ((((k >> 3) ^ ((co >> 1) & 3))) << 4) + (k & 7) * 2) = v;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the generic-proxy writes of sB -> visible to the tensor core
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kAcc * 32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== MMA issuer (whole warp, one elected lane issues) =====================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bdesc = make_desc<32>(smem_u32(sB));
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int slot = i % kSlots, acc = i % kAcc;
+            STEM_WAIT(&tempty[acc], ((i / kAcc) & 1) ^ 1);
+            STEM_WAIT(&afull[slot], (i / kSlots) & 1);
+            tc_fence_after();
+            const uint64_t adesc = make_desc<32>(smem_u32(sA[slot]));
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
+            tc_mma_bf16_elect(d_tmem, adesc, bdesc, idesc, 0u);
+            tc_mma_bf16_elect(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            tc_commit_elect(&aempty[slot]);
+            tc_commit_elect(&tfull[acc]);
+        }
+    } else if (warp <= 8) {
+        // ===================================== window gather (two groups of 4 warps) ================================
+        const int g = (warp - 1) >> 2;
+        const int r = ((warp - 1) & 3) * 32 + lane;              // GEMM row = pixel of the tile
+        const int px = r % kTW, py = r / kTW;
+        const size_t plane = (size_t)a.H * a.W;
+        Walk t; t.init(blockIdx.x + g * gridDim.x, 2 * gridDim.x, a.tiles_x, a.tiles_y);
+        int i = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2, t.next(a.tiles_x, a.tiles_y)) {
+            const int slot = i % kSlots;
+            const int x = t.tx * kTW + px, y = t.ty * kTH + py;
+            const bool valid = x < a.W && y < a.H;
+            const float *img = a.in + (size_t)t.tn * 3 * plane;
+            float v[28];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = y + ky - 1;
+                const bool yok = valid && yy >= 0 && yy < a.H;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = x + kx - 1;
+                    const bool ok = yok && xx >= 0 && xx < a.W;
+                    const float *p = img + (size_t)(ok ? yy : 0) * a.W + (ok ? xx : 0);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float val = __ldg(p + c * plane);
+                        v[(ky * 3 + kx) * 3 + c] = ok ? val : 0.f;
+                    }
+                }
+            }
+            v[27] = 0.f;
+            STEM_WAIT(&aempty[slot], ((i / kSlots) & 1) ^ 1);     // loads are already in flight while we wait for the slot
+            const uint32_t row_addr = smem_u32(sA[slot]) + (uint32_t)r * 64u;
+            const uint32_t sw = (uint32_t)(r >> 1) & 3u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                if (j < 3) {
+                    q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]); q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                    q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                } else {
+                    q.x = pack_bf16(v[24], v[25]); q.y = pack_bf16(v[26], v[27]); q.z = 0u; q.w = 0u;
+                }
+                sts128(row_addr + (((uint32_t)j ^ sw) << 4), q);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[slot]);
+        }
+    } else {
+        // ===================================== epilogue (warps 9..12) ===============================================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int px = r % kTW, py = r / kTW;
+        float sc[NOUT], sh[NOUT];
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) { sc[c] = a.scale[c]; sh[c] = a.shift[c]; }
+        const bool leaky = a.act == ACT_LEAKY;
+        Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
+            const int acc = i % kAcc;
+            STEM_WAIT(&tfull[acc], (i / kAcc) & 1);
+            tc_fence_after();
+            uint32_t d[NOUT];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32);
+            if constexpr (NOUT == 32) tmem_ld32(taddr, d); else tmem_ld16(taddr, d);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            const int x = t.tx * kTW + px, y = t.ty * kTH + py;
+            if (x < a.W && y < a.H) {
+                bf16 *dst = a.out + (((size_t)t.tn * a.H + y) * a.W + x) * a.ldo;
+#pragma unroll
+                for (int c = 0; c < NOUT; c += 8) {
+                    float o[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        o[q] = fmaf(__uint_as_float(d[c + q]), sc[c + q], sh[c + q]);
+                        if (leaky) o[q] = o[q] > 0.f ? o[q] : 0.1f * o[q];
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+                    *reinterpret_cast<uint4 *>(dst + c) = pk;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc * 32) : "memory");
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// TMA-fed variant (image width a multiple of 4): the tile's fp32 window source arrives as ONE 4-D TMA box
+// [3 channels][10 rows][24 columns] (out-of-bounds = zero = the convolution's padding, so the gather needs no predicates
+// and reads shared memory instead of global), and the output tile leaves as ONE TMA store from a swizzled staging tile.
+// Warp roles (480 threads): 0 = MMA, 1 = TMA loads, 2 = TMA stores, 3-10 = two gather groups, 11-14 = epilogue.
+// ---------------------------------------------------------------------------------------------------
+// patch box: rows y0-1 .. y0+8, columns x0-4 .. x0+19.  An un-swizzled TMA box must START on a 16-byte boundary in
+// dimension 0 (scripts/tma_f32_probe.cu: x0-1 raises an illegal-instruction error), hence the 4-column left margin.
+constexpr int kPW = 24, kPH = 10, kPX = 4;
+constexpr int kPatchBytes = 3 * kPH * kPW * 4;    // 2880
+constexpr int kPatchPitch = 2944;                 // ring pitch (128-byte aligned TMA destinations)
+constexpr int kPatches = 6;
+constexpr int kOutSlots = 3;
+constexpr int kThreads2 = 15 * 32;
+
+struct alignas(64) StemTcMaps { CUtensorMap in, out; };
+
+template <int NOUT>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArgs a)
+{
+    constexpr int ROWB = NOUT * 2;                                   // bytes per pixel row of the output tile (= its swizzle span)
+    extern __shared__ uint8_t stem_smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)stem_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t (*sA)[128 * 64] = reinterpret_cast<uint8_t (*)[128 * 64]>(base);                               // kSlots x 8 KB
+    uint8_t (*sC)[128 * ROWB] = reinterpret_cast<uint8_t (*)[128 * ROWB]>(base + kSlots * 8192);           // kOutSlots tiles
+    uint8_t *sB = base + kSlots * 8192 + kOutSlots * 8192;                                                 // 2 KB, 1024-aligned
+    uint8_t (*sP)[kPatchPitch] = reinterpret_cast<uint8_t (*)[kPatchPitch]>(base + kSlots * 8192 + kOutSlots * 8192 + 2048);
+    __shared__ uint64_t pfull[kPatches], pempty[kPatches], afull[kSlots], aempty[kSlots], tfull[kAcc], tempty[kAcc],
+                        cwritten[kOutSlots], cempty[kOutSlots];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = a.num_tiles;
+
+    for (int idx = threadIdx.x; idx < NOUT * 32; idx += kThreads2) {
+        const int co = idx >> 5, k = idx & 31;
+        const bf16 v = k < 27 ? a.w[co * 27 + k] : __float2bfloat16(0.f);
+        *reinterpret_cast<bf16 *>(sB + co * 64 + ((((k >> 3) ^ ((co >> 1) & 3))) << 4) + (k & 7) * 2) = v;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPatches; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 4); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < kOutSlots; ++i) { mbar_init(&cwritten[i], 4); mbar_init(&cempty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kAcc * 32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== MMA issuer ===========================================================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bdesc = make_desc<32>(smem_u32(sB));
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int slot = i % kSlots, acc = i % kAcc;
+            STEM_WAIT(&tempty[acc], ((i / kAcc) & 1) ^ 1);
+            STEM_WAIT(&afull[slot], (i / kSlots) & 1);
+            tc_fence_after();
+            const uint64_t adesc = make_desc<32>(smem_u32(sA[slot]));
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
+            tc_mma_bf16_elect(d_tmem, adesc, bdesc, idesc, 0u);
+            tc_mma_bf16_elect(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            tc_commit_elect(&aempty[slot]);
+            tc_commit_elect(&tfull[acc]);
+        }
+    } else if (warp == 1) {
+        // ===================================== TMA loads: one fp32 window-source box per tile =======================
+        if (lane == 0) {
+            Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
+            int i = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
+                const int ps = i % kPatches;
+                STEM_WAIT(&pempty[ps], ((i / kPatches) & 1) ^ 1);
+                mbar_expect_tx(&pfull[ps], kPatchBytes);
+                tma_load_4d(&maps.in, sP[ps], &pfull[ps], t.tx * kTW - kPX, t.ty * kTH - 1, 0, t.tn);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================== TMA stores ============================================================
+        if (lane == 0) {
+            Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
+            int i = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
+                const int cs = i % kOutSlots;
+                STEM_WAIT(&cwritten[cs], (i / kOutSlots) & 1);
+                tma_store_4d(&maps.out, sC[cs], 0, t.tx * kTW, t.ty * kTH, t.tn);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(&cempty[cs]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp <= 10) {
+        // ===================================== window gather (two groups of 4 warps) ================================
+        const int g = (warp - 3) >> 2;
+        const int r = ((warp - 3) & 3) * 32 + lane;
+        const int px = r % kTW, py = r / kTW;
+        const uint32_t sw = (uint32_t)(r >> 1) & 3u;
+        int i = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2) {
+            const int slot = i % kSlots, ps = i % kPatches;
+            STEM_WAIT(&pfull[ps], (i / kPatches) & 1);
+            const float *P = reinterpret_cast<const float *>(sP[ps]) + py * kPW + px + (kPX - 1);
+            float v[28];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = P[c * (kPH * kPW) + ky * kPW + kx];
+            v[27] = 0.f;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pempty[ps]);              // values are in registers: the patch slot can be refilled
+            STEM_WAIT(&aempty[slot], ((i / kSlots) & 1) ^ 1);
+            const uint32_t row_addr = smem_u32(sA[slot]) + (uint32_t)r * 64u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                if (j < 3) {
+                    q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]); q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                    q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                } else {
+                    q.x = pack_bf16(v[24], v[25]); q.y = pack_bf16(v[26], v[27]); q.z = 0u; q.w = 0u;
+                }
+                sts128(row_addr + (((uint32_t)j ^ sw) << 4), q);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[slot]);
+        }
+    } else {
+        // ===================================== epilogue (warps 11..14) ==============================================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        float sc[NOUT], sh[NOUT];
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) { sc[c] = a.scale[c]; sh[c] = a.shift[c]; }
+        const bool leaky = a.act == ACT_LEAKY;
+        // output tile rows are NOUT*2 bytes = the swizzle span: 16-byte chunk j of row r sits at chunk j ^ f(r)
+        const uint32_t swz = NOUT == 32 ? ((uint32_t)(r >> 1) & 3u) : ((uint32_t)(r >> 2) & 1u);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int acc = i % kAcc, cs = i % kOutSlots;
+            STEM_WAIT(&tfull[acc], (i / kAcc) & 1);
+            tc_fence_after();
+            uint32_t d[NOUT];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32);
+            if constexpr (NOUT == 32) tmem_ld32(taddr, d); else tmem_ld16(taddr, d);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            STEM_WAIT(&cempty[cs], ((i / kOutSlots) & 1) ^ 1);
+            const uint32_t row_addr = smem_u32(sC[cs]) + (uint32_t)r * ROWB;
+#pragma unroll
+            for (int c = 0; c < NOUT; c += 8) {
+                float o[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    o[q] = fmaf(__uint_as_float(d[c + q]), sc[c + q], sh[c + q]);
+                    if (leaky) o[q] = o[q] > 0.f ? o[q] : 0.1f * o[q];
+                }
+                uint4 pk;
+                pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+                sts128(row_addr + (((uint32_t)(c >> 3) ^ swz) << 4), pk);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cwritten[cs]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc * 32) : "memory");
+    }
+}
+
+// tensor maps depend on the buffers only: cache the last few (the chunked H2D path launches the stem per chunk)
+struct MapCacheEntry { const void *in; void *out; int n, h, w, c, ld; StemTcMaps maps; };
+static MapCacheEntry g_maps[16];
+static int g_maps_used = 0, g_maps_next = 0;
+
+static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView out)
+{
+    for (int i = 0; i < g_maps_used; ++i) {
+        const MapCacheEntry &e = g_maps[i];
+        if (e.in == in && e.out == out.p && e.n == n && e.h == h && e.w == w && e.c == out.c && e.ld == out.ld) return &e.maps;
+    }
+    MapCacheEntry &e = g_maps[g_maps_next];
+    g_maps_next = (g_maps_next + 1) % 16;
+    if (g_maps_used < 16) ++g_maps_used;
+    e.in = in; e.out = out.p; e.n = n; e.h = h; e.w = w; e.c = out.c; e.ld = out.ld;
+    {
+        unsigned long long dims[4] = {(unsigned long long)w, (unsigned long long)h, 3ull, (unsigned long long)n};
+        unsigned long long strides[3] = {(unsigned long long)w * 4, (unsigned long long)h * w * 4, (unsigned long long)3 * h * w * 4};
+        unsigned box[4] = {kPW, kPH, 3, 1};
+        tc_encode_tiled(&e.maps.in, 1, 4, (void *)in, dims, strides, box, 0);
+    }
+    {
+        unsigned long long dims[4] = {(unsigned long long)out.c, (unsigned long long)w, (unsigned long long)h, (unsigned long long)n};
+        unsigned long long strides[3] = {(unsigned long long)out.ld * 2, (unsigned long long)w * out.ld * 2, (unsigned long long)h * w * out.ld * 2};
+        unsigned box[4] = {(unsigned)out.c, kTW, kTH, 1};
+        tc_encode_tiled(&e.maps.out, 0, 4, out.p, dims, strides, box, out.c * 2);
+    }
+    return &e.maps;
+}
+
+}  // namespace
+
+// true when the layer was launched here; false -> caller uses the CUDA-core stem
+bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
+{
+    if (getenv("B200_STEM_SIMT")) return false;
+    if (out.dtype != DT_BF16 || c != 3 || p.size != 3 || p.stride != 1 || p.pad != 1) return false;
+    if (out.c != p.cout_pad || (out.c != 16 && out.c != 32) || out.h != h || out.w != w) return false;
+    if (out.ld % 8 != 0 || ((uintptr_t)out.p & 15)) return false;
+    if (p.act != ACT_LEAKY && p.act != ACT_LINEAR) return false;
+    StemTcArgs a;
+    a.in = in_nchw; a.out = (bf16 *)out.p; a.w = (const bf16 *)p.w; a.scale = p.scale; a.shift = p.shift;
+    a.N = n; a.H = h; a.W = w; a.ldo = out.ld; a.act = p.act;
+    a.tiles_x = div_up(w, kTW); a.tiles_y = div_up(h, kTH);
+    const long long tiles = (long long)a.tiles_x * a.tiles_y * n;
+    if (tiles > 0x7fffffff) return false;
+    a.num_tiles = (int)tiles;
+    const int grid = a.num_tiles < 148 ? a.num_tiles : 148;
+    if (w % 4 == 0 && ((uintptr_t)in_nchw & 15) == 0 && !getenv("B200_STEM_LDG")) {
+        const StemTcMaps *maps = stem_maps(in_nchw, n, h, w, out);
+        const size_t smem = 1024 + kSlots * 8192 + kOutSlots * 8192 + kPatches * kPatchPitch + 2048;
+        static bool configured = false;
+        if (!configured) {
+            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        if (out.c == 32) conv_stem_tc_tma_kernel<32><<<grid, kThreads2, smem, s>>>(*maps, a);
+        else conv_stem_tc_tma_kernel<16><<<grid, kThreads2, smem, s>>>(*maps, a);
+        return true;
+    }
+    if (out.c == 32) conv_stem_tc_kernel<32><<<grid, kThreads, 0, s>>>(a);
+    else conv_stem_tc_kernel<16><<<grid, kThreads, 0, s>>>(a);
+    return true;
+}

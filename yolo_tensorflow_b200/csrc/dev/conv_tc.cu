@@ -26,147 +26,7 @@
 #include <cuda.h>
 #include <string>
 
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ---- TMA tile stores + swizzled shared-memory staging (epilogue) ---------------------------------------
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
-{
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// ---- cta_group::2 (CTA pair) flavours ----------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA loads issued by EITHER CTA of the pair; completion bytes are credited to the LEADER's mbarrier (peer bit cleared)
-__device__ __forceinline__ void tma2_load_2d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(const CUtensorMap *map, void *dst, uint64_t *bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc2_commit_both(uint64_t *bar)      // arrives on `bar` in BOTH CTAs of the pair
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tc2_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)   // arrive on the copy of `bar` that lives in CTA rank 0
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 remote;\n\t"
-        "mapa.shared::cluster.u32 remote, %0, 0;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t"
-        "}" ::"r"(smem_u32(bar)) : "memory");
-}
+#include "tc_ptx.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // kernel arguments
@@ -211,14 +71,6 @@ struct ConvTcArgs {
 };
 
 static constexpr int kTcThreads = 192;
-
-// shared-memory descriptor for a K-major operand tile whose rows are BLOCK_K*2 bytes (= the swizzle span)
-template <int BLOCK_K> __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
-{
-    constexpr uint64_t layout = BLOCK_K == 64 ? 2 : (BLOCK_K == 32 ? 4 : 6);      // SWIZZLE_128B / 64B / 32B
-    constexpr uint64_t sbo = (8 * BLOCK_K * 2) >> 4;                                // 8 rows
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
 
 // epilogue math for NC accumulator columns of one pixel row: folded-BN scale/shift, activation, optional
 // residual, cast, 16-byte stores.  `sc`/`sh` point at the tile's per-filter constants in shared memory.
@@ -830,36 +682,6 @@ conv_tc_halo_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcAr
 //   taps kx = 1,2 are one K = 64 segment of pair ox, tap kx = 0 is the upper half (K = 32) of pair ox - 1.
 // The segment table is built by the host (ConvTcArgs::seg_*).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t make_desc_rt(uint32_t smem_addr, int k)
-{
-    const uint64_t layout = k == 64 ? 2 : (k == 32 ? 4 : 6);
-    const uint64_t sbo = (uint64_t)(8 * k * 2) >> 4;
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-// Whole-warp (convergent) issue: every lane runs the role's loop and ONE elected lane issues the tensor-core instruction.
-// Issuing from inside `if (lane == 0)` makes the compiler wrap each UTCHMMA in a move-to-uniform + elect loop (~13
-// instructions, ~80 cycles of dependent issue per MMA), which bounds a short K pass; here the operands stay in uniform registers.
-__device__ __forceinline__ void tc_mma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, e;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_commit_elect(uint64_t *bar)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-        "}" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // persistent-tile walker: tile = first, first + step, ... decoded into (tx, ty, tn) without a division per tile
 struct TileWalk {
     int tx, ty, tn, sx, sy, sn;
@@ -1150,6 +972,21 @@ static void encode(CUtensorMap *map, void *base, int rank, const cuuint64_t *dim
 }
 
 // 64-channel x pixel-tile boxes of an NHWC bf16 tensor, 128B-swizzled: the staged epilogue's store / residual-load view
+// generic form for the other tcgen05 translation units (conv_stem_tc.cu): dtype 0 = bf16, 1 = fp32; swizzle_bytes 0/32/64/128
+void tc_encode_tiled(void *map, int dtype, int rank, void *base, const unsigned long long *dims, const unsigned long long *strides_bytes,
+                     const unsigned *box, int swizzle_bytes)
+{
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    cuuint64_t d[5], st[5]; cuuint32_t b[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; if (i < rank - 1) st[i] = strides_bytes[i]; }
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = encode_fn()((CUtensorMap *)map, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base,
+                             d, st, b, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "b200-darknet: cuTensorMapEncodeTiled failed (%d)\n", (int)r); abort(); }
+}
+
 static void encode_tile_view(CUtensorMap *map, const TView &t, int channels, const ConvTcArgs &a)
 {
     const size_t esz = 2;

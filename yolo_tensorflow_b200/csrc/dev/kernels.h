@@ -38,6 +38,7 @@ struct ConvParams {
 };
 // first-layer kernel: reads the fp32 NCHW network input directly (fuses the layout/precision conversion)
 void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);
+bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);   // false: shape not covered
 void conv_stem_invalidate_bank();      // call after the stem's weights changed in place (load_weights)
 // CUDA-core implicit-GEMM (fp32 accumulate); the fp32-exact path and the fallback for odd shapes
 void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
@@ -48,6 +49,9 @@ void conv_tc_plan_destroy(ConvTcPlan *plan);
 bool conv_tc_shape_supported(int cin, int stride, int act);
 void launch_conv_tc(ConvTcPlan *plan, cudaStream_t s);
 const char *conv_tc_plan_desc(ConvTcPlan *plan);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (dtype 0 = bf16, 1 = fp32; swizzle_bytes 0/32/64/128)
+void tc_encode_tiled(void *map, int dtype, int rank, void *base, const unsigned long long *dims, const unsigned long long *strides_bytes,
+                     const unsigned *box, int swizzle_bytes);
 
 // YOLOv1 dense layers (dense.cu)
 void launch_local(TView in, TView out, const void *w, const float *bias, int size, int stride, int pad, int act, cudaStream_t s);
