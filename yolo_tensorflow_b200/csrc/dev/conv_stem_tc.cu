@@ -210,16 +210,17 @@ conv_stem_tc_kernel(const StemTcArgs a)
 // TMA-fed variant (image width a multiple of 4): the tile's fp32 window source arrives as ONE 4-D TMA box
 // [3 channels][10 rows][24 columns] (out-of-bounds = zero = the convolution's padding, so the gather needs no predicates
 // and reads shared memory instead of global), and the output tile leaves as ONE TMA store from a swizzled staging tile.
-// Warp roles (480 threads): 0 = MMA, 1 = TMA loads, 2 = TMA stores, 3-10 = two gather groups, 11-14 = epilogue.
+// Warp roles (608 threads): 0 = MMA, 1 = TMA loads, 2 = TMA stores, 3-10 = two gather groups, 11-18 = two epilogue groups
+// (gather and epilogue groups take alternate tiles: one warp per scheduler cannot issue a tile's epilogue fast enough).
 // ---------------------------------------------------------------------------------------------------
 // patch box: rows y0-1 .. y0+8, columns x0-4 .. x0+19.  An un-swizzled TMA box must START on a 16-byte boundary in
 // dimension 0 (scripts/tma_f32_probe.cu: x0-1 raises an illegal-instruction error), hence the 4-column left margin.
 constexpr int kPW = 24, kPH = 10, kPX = 4;
 constexpr int kPatchBytes = 3 * kPH * kPW * 4;    // 2880
 constexpr int kPatchPitch = 2944;                 // ring pitch (128-byte aligned TMA destinations)
-constexpr int kPatches = 6;
+constexpr int kPatches = 16;
 constexpr int kOutSlots = 3;
-constexpr int kThreads2 = 15 * 32;
+constexpr int kThreads2 = 19 * 32;
 
 struct alignas(64) StemTcMaps { CUtensorMap in, out; };
 
@@ -237,6 +238,8 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
     __shared__ uint64_t pfull[kPatches], pempty[kPatches], afull[kSlots], aempty[kSlots], tfull[kAcc], tempty[kAcc],
                         cwritten[kOutSlots], cempty[kOutSlots];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_scale[NOUT], s_shift[NOUT];
+    if (threadIdx.x < NOUT) { s_scale[threadIdx.x] = a.scale[threadIdx.x]; s_shift[threadIdx.x] = a.shift[threadIdx.x]; }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = a.num_tiles;
@@ -346,17 +349,16 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
             if (lane == 0) mbar_arrive(&afull[slot]);
         }
     } else {
-        // ===================================== epilogue (warps 11..14) ==============================================
+        // ===================================== epilogue (two groups of 4 warps) =====================================
+        const int g = (warp - 11) >> 2;
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
-        float sc[NOUT], sh[NOUT];
-#pragma unroll
-        for (int c = 0; c < NOUT; ++c) { sc[c] = a.scale[c]; sh[c] = a.shift[c]; }
         const bool leaky = a.act == ACT_LEAKY;
+        const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
         // output tile rows are NOUT*2 bytes = the swizzle span: 16-byte chunk j of row r sits at chunk j ^ f(r)
         const uint32_t swz = NOUT == 32 ? ((uint32_t)(r >> 1) & 3u) : ((uint32_t)(r >> 2) & 1u);
-        int i = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        int i = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2) {
             const int acc = i % kAcc, cs = i % kOutSlots;
             STEM_WAIT(&tfull[acc], (i / kAcc) & 1);
             tc_fence_after();
@@ -373,9 +375,16 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
             for (int c = 0; c < NOUT; c += 8) {
                 float o[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    o[q] = fmaf(__uint_as_float(d[c + q]), sc[c + q], sh[c + q]);
-                    if (leaky) o[q] = o[q] > 0.f ? o[q] : 0.1f * o[q];
+                for (int q = 0; q < 8; q += 4) {
+                    const uint4 s4 = lds128(sc_addr + (uint32_t)(c + q) * 4u), h4 = lds128(sh_addr + (uint32_t)(c + q) * 4u);
+                    o[q + 0] = fmaf(__uint_as_float(d[c + q + 0]), __uint_as_float(s4.x), __uint_as_float(h4.x));
+                    o[q + 1] = fmaf(__uint_as_float(d[c + q + 1]), __uint_as_float(s4.y), __uint_as_float(h4.y));
+                    o[q + 2] = fmaf(__uint_as_float(d[c + q + 2]), __uint_as_float(s4.z), __uint_as_float(h4.z));
+                    o[q + 3] = fmaf(__uint_as_float(d[c + q + 3]), __uint_as_float(s4.w), __uint_as_float(h4.w));
+                }
+                if (leaky) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = fmaxf(o[q], 0.1f * o[q]);
                 }
                 uint4 pk;
                 pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
