@@ -61,6 +61,7 @@ struct ConvTcArgs {
     int a_k, b_k;            // elements per smem row of the patches / of the weight tiles (-> swizzle mode)
     int nb, b_koff[12];      // resident weight tiles: K offset of each [block_n x b_k] box
     int nseg, seg_a[12], seg_b[12], seg_k[12];   // K segments: patch byte offset (row shift), weight byte offset, K/16 steps
+    int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
     int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
     long long npix;
     const float *scale, *shift;
@@ -745,6 +746,10 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = args.m_tiles;
     const int G = args.ep_groups, NBUF = args.c_bufs;
+    // filter split: CTA b computes filters [ch0, ch0 + N) of pixel tiles vb, vb + vgrid, ...; neighbouring CTAs take the
+    // filter slices of the SAME pixel tile at the same time, so the second read of its patch is an L2 hit
+    const int vb = (int)blockIdx.x / args.n_split, vgrid = (int)gridDim.x / args.n_split;
+    const int ch0 = ((int)blockIdx.x % args.n_split) * N;
     const bool has_res = args.res != nullptr;
 
     if (threadIdx.x == 0) {
@@ -766,13 +771,13 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0 && (int)blockIdx.x < num_tiles) {
+        if (lane == 0 && vb < num_tiles) {
             mbar_expect_tx(wfull, (uint32_t)(args.nb * N * args.b_k * 2));
-            for (int i = 0; i < args.nb; ++i) tma_load_2d(&maps.b, sB + (size_t)i * args.b_stage_bytes, wfull, args.b_koff[i], 0);
+            for (int i = 0; i < args.nb; ++i) tma_load_2d(&maps.b, sB + (size_t)i * args.b_stage_bytes, wfull, args.b_koff[i], ch0);
             int stage = 0; uint32_t phase = 0;
             int cb = 0; uint32_t cphase = 0;
-            TileWalk t; t.init(blockIdx.x, gridDim.x, args.tiles_x, args.tiles_y);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, t.next(args.tiles_x, args.tiles_y)) {
+            TileWalk t; t.init(vb, vgrid, args.tiles_x, args.tiles_y);
+            for (int tile = vb; tile < num_tiles; tile += vgrid, t.next(args.tiles_x, args.tiles_y)) {
                 const int ox0 = t.tx * args.halo_TWv, oy0 = t.ty * args.halo_THv;
                 MBAR_WAIT_HERE(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], (uint32_t)args.stage_tx);
@@ -787,14 +792,14 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
                     uint8_t *cdst = sC + (size_t)cb * NSUB * 16384;
                     for (int q = 0; q < NSUB; ++q)
                         for (int yy = 0; yy < rows_here; ++yy)
-                            tma_load_4d(&maps.r, cdst + q * 16384 + yy * args.halo_P * 128, &cfull[cb], 64 * q, ox0, oy0 + yy, t.tn);
+                            tma_load_4d(&maps.r, cdst + q * 16384 + yy * args.halo_P * 128, &cfull[cb], ch0 + 64 * q, ox0, oy0 + yy, t.tn);
                     if (++cb == NBUF) { cb = 0; cphase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if ((int)blockIdx.x < num_tiles) {                 // all 32 lanes walk the loop; one elected lane issues
+        if (vb < num_tiles) {                 // all 32 lanes walk the loop; one elected lane issues
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -809,7 +814,7 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
             const uint64_t adesc0 = make_desc_rt(smem_u32(sA), args.a_k);
             const uint32_t stage_step = (uint32_t)args.a_stage_bytes >> 4;
             MBAR_WAIT_HERE(wfull, 0);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = vb; tile < num_tiles; tile += vgrid) {
                 MBAR_WAIT_HERE(&tempty[acc], acc_phase ^ 1);
                 MBAR_WAIT_HERE(&full[stage], phase);
                 tc_fence_after();
@@ -832,16 +837,16 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
         // takes a ring slot once the four epilogue warps have written it, TMA-stores it (one box per image row: the tile
         // is patch-pitched in smem) and frees the slot when the store engine has read it
         if (lane == 0) {
-            TileWalk t; t.init(blockIdx.x, gridDim.x, args.tiles_x, args.tiles_y);
+            TileWalk t; t.init(vb, vgrid, args.tiles_x, args.tiles_y);
             int cb = 0; uint32_t cphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, t.next(args.tiles_x, args.tiles_y)) {
+            for (int tile = vb; tile < num_tiles; tile += vgrid, t.next(args.tiles_x, args.tiles_y)) {
                 const int ox0 = t.tx * args.halo_TWv, oy0 = t.ty * args.halo_THv;
                 int rows_here = args.OH - oy0; if (rows_here > args.halo_THv) rows_here = args.halo_THv;
                 const uint8_t *src = sC + (size_t)cb * NSUB * 16384;
                 MBAR_WAIT_HERE(&cwritten[cb], cphase);
                 for (int q = 0; q < NSUB; ++q)
                     for (int yy = 0; yy < rows_here; ++yy)
-                        tma_store_4d(&maps.c, src + q * 16384 + yy * args.halo_P * 128, 64 * q, ox0, oy0 + yy, t.tn);
+                        tma_store_4d(&maps.c, src + q * 16384 + yy * args.halo_P * 128, ch0 + 64 * q, ox0, oy0 + yy, t.tn);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 bulk_wait_read<0>();
                 mbar_arrive(&cempty[cb]);
@@ -855,14 +860,14 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
         const int row = quarter * 32 + lane;
         const int ep_tid = threadIdx.x - 96 - 128 * g;
-        for (int c = ep_tid; c < N; c += 128) { s_scale[c] = args.scale[c]; s_shift[c] = args.shift[c]; }   // every group writes the same values
+        for (int c = ep_tid; c < N; c += 128) { s_scale[c] = args.scale[ch0 + c]; s_shift[c] = args.shift[ch0 + c]; }   // every group writes the same values
         group_sync(g);
         const bool leaky = args.act == ACT_LEAKY;
         const float alpha = args.res_alpha, beta = args.res_beta;
         const uint32_t scale_addr = smem_u32(s_scale), shift_addr = smem_u32(s_shift);
         const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
         int i = g;                                         // CTA-local tile counter
-        for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += G * gridDim.x, i += G) {
+        for (int tile = vb + g * vgrid; tile < num_tiles; tile += G * vgrid, i += G) {
             const int acc = i % args.acc_stages;
             const uint32_t acc_phase = (uint32_t)(i / args.acc_stages) & 1u;
             const int cb = i % NBUF;
@@ -1210,12 +1215,18 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     }
     // ---- single-CTA patch kernel (mode 2, pair 0): few input channels, all weights resident ----------------------------
     if (a.mode == 1 && !getenv("B200_NO_PATCH") && cp.size == 3 && cp.pad == 1 && out.dtype == DT_BF16 && a.n_tiles == 1 &&
-        (cp.cout_pad == 64 || cp.cout_pad == 128) && out.c == cp.cout_pad &&
+        (cp.cout_pad == 64 || cp.cout_pad == 128 || cp.cout_pad == 256) && out.c == cp.cout_pad &&
         ((cp.stride == 1 && (C == 32 || C == 64)) || (cp.stride == 2 && C == 32 && in.ld == 32 && in.w % 2 == 0))) {
         const bool s2 = cp.stride == 2;
         const int a_k = s2 ? 64 : C, b_k = a_k, row_bytes = a_k * 2;
         const int halo_x = s2 ? 1 : 2;
-        const int N = a.block_n;
+        // filters per CTA: all of them while the resident weights leave room for the rings, else 64-filter slices
+        // handled by neighbouring CTAs (the patch is then read n_split times, all but the first from L2)
+        int N = cp.cout_pad <= 128 ? cp.cout_pad : 64;
+        if ((s2 ? 6 : 9) * N * b_k * 2 > 80 * 1024) N = 64;
+        if (getenv("B200_PATCH_SPLIT")) N = 64;
+        const int n_split = cp.cout_pad / N;
+        if (148 % n_split != 0) N = 0;
         const int nb = s2 ? 6 : 9;
         const int b_tile = (N * b_k * 2 + 1023) / 1024 * 1024;
         int groups = 2;
@@ -1240,6 +1251,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
             if (cost < best) { best = cost; bTW = tw; }
         }
         if (getenv("B200_PATCH_TW")) { int f = atoi(getenv("B200_PATCH_TW")); if (f >= 1 && f <= out.w && 3 * stage_bytes_for(f + halo_x) + 2 * slot_bytes <= room) bTW = f; }
+        if (N == 0) bTW = 0;
         if (bTW) {
             const int TWv = bTW, P = TWv + halo_x;
             int TH = 128 / P; if (TH > out.h) TH = out.h;
@@ -1260,7 +1272,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                 a.m_tiles = a.tiles_x * a.tiles_y * in.n;
                 a.a_rows = TH * P;
                 a.np = np; a.a_k = a_k; a.b_k = b_k; a.nb = nb;
-                a.ep_groups = groups; a.c_bufs = c_bufs;
+                a.ep_groups = groups; a.c_bufs = c_bufs; a.n_split = n_split; a.block_n = N;
                 a.a_stage_bytes = stage_bytes; a.b_stage_bytes = b_tile; a.stages = st;
                 if (!s2) {
                     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
@@ -1310,12 +1322,12 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                 if (getenv("B200_PATCH_ACC")) { int f = atoi(getenv("B200_PATCH_ACC")); if (f >= 1 && f < a.acc_stages) a.acc_stages = f; }
                 int cols = a.acc_stages * N;
                 a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
-                p->grid = a.m_tiles < 148 ? a.m_tiles : 148;
+                p->grid = n_split * (a.m_tiles < 148 / n_split ? a.m_tiles : 148 / n_split);
                 p->smem_bytes = (size_t)st * stage_bytes + (size_t)nb * b_tile + sc_bytes + aux_bytes + 1024;
                 p->flops = 2.0 * (double)a.npix * out.c * K;
                 char buf3[320];
-                snprintf(buf3, sizeof buf3, "conv_tc PATCH s%d k%d n%d tile %dx%d (pitch %d) m_tiles %d patches %d segs %d stages %d acc %d ring %d groups %d smem %zu grid %d residentB%s stagedEpilogue",
-                         cp.stride, a_k, N, TWv, TH, P, a.m_tiles, np, a.nseg, st, a.acc_stages, c_bufs, groups, p->smem_bytes, p->grid, a.res ? " +residual" : "");
+                snprintf(buf3, sizeof buf3, "conv_tc PATCH s%d k%d n%d x%d tile %dx%d (pitch %d) m_tiles %d patches %d segs %d stages %d acc %d ring %d groups %d smem %zu grid %d residentB%s stagedEpilogue",
+                         cp.stride, a_k, N, n_split, TWv, TH, P, a.m_tiles, np, a.nseg, st, a.acc_stages, c_bufs, groups, p->smem_bytes, p->grid, a.res ? " +residual" : "");
                 p->desc = buf3;
                 return p;
             }
