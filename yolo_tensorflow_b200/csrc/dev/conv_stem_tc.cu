@@ -89,6 +89,7 @@ conv_stem_tc_kernel(const StemTcArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================================== MMA issuer (whole warp, one elected lane issues) =====================
@@ -113,6 +114,7 @@ conv_stem_tc_kernel(const StemTcArgs a)
         const int r = ((warp - 1) & 3) * 32 + lane;              // GEMM row = pixel of the tile
         const int px = r % kTW, py = r / kTW;
         const size_t plane = (size_t)a.H * a.W;
+        pdl_wait();
         Walk t; t.init(blockIdx.x + g * gridDim.x, 2 * gridDim.x, a.tiles_x, a.tiles_y);
         int i = g;
         for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2, t.next(a.tiles_x, a.tiles_y)) {
@@ -165,6 +167,7 @@ conv_stem_tc_kernel(const StemTcArgs a)
 #pragma unroll
         for (int c = 0; c < NOUT; ++c) { sc[c] = a.scale[c]; sh[c] = a.shift[c]; }
         const bool leaky = a.act == ACT_LEAKY;
+        pdl_wait();
         Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
         int i = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
@@ -265,6 +268,7 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================================== MMA issuer ===========================================================
@@ -286,6 +290,7 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
     } else if (warp == 1) {
         // ===================================== TMA loads: one fp32 window-source box per tile =======================
         if (lane == 0) {
+            pdl_wait();
             Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
             int i = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
@@ -298,6 +303,7 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
     } else if (warp == 2) {
         // ===================================== TMA stores ============================================================
         if (lane == 0) {
+            pdl_wait();
             Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
             int i = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
@@ -461,8 +467,14 @@ bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView
             B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
-        if (out.c == 32) conv_stem_tc_tma_kernel<32><<<grid, kThreads2, smem, s>>>(*maps, a);
-        else conv_stem_tc_tma_kernel<16><<<grid, kThreads2, smem, s>>>(*maps, a);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = getenv("B200_NO_PDL") ? 0 : 1;
+        if (out.c == 32) B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<32>, *maps, a));
+        else B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<16>, *maps, a));
         return true;
     }
     if (out.c == 32) conv_stem_tc_kernel<32><<<grid, kThreads, 0, s>>>(a);

@@ -175,6 +175,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    pdl_wait();                                            // first residual read / output write comes after this
     const bool leaky = args.act == ACT_LEAKY;
     const bool staged = sizeof(OutT) == 2 && args.staged;
     const bool has_res = args.res != nullptr;
@@ -333,6 +334,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -345,6 +347,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
                 for (int kb = 0; kb < args.num_kblocks; ++kb)
                     tma_load_2d(&maps.b, sB + (size_t)kb * args.b_stage_bytes, wfull, kb * BLOCK_K, 0);
             }
+            pdl_wait();                                   // weights may load early; activations only after the previous layer is done
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % args.n_tiles, m_tile = tile / args.n_tiles;
                 int ox0 = 0, oy0 = 0, n0 = 0;
@@ -465,6 +468,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
     cluster_sync_all();                                             // peer barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
     const int half_n = args.block_n / 2;
 
     if (warp == 0) {
@@ -472,6 +476,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = 2u * (uint32_t)(args.a_rows * BLOCK_K * 2 + half_n * BLOCK_K * 2);
+            pdl_wait();
             for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
                 const int n_tile = tile % args.n_tiles, m_tile = 2 * (tile / args.n_tiles) + (int)rank;
                 int ox0 = 0, oy0 = 0, n0 = 0;
@@ -599,6 +604,7 @@ conv_tc_halo_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcAr
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
     const int half_n = args.block_n / 2;
     const int patch_rows = (args.halo_THv + args.size - 1) * args.halo_P;
 
@@ -608,6 +614,7 @@ conv_tc_halo_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcAr
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             const uint32_t a_tx = 2u * (uint32_t)(patch_rows * BLOCK_K * 2);
             const uint32_t b_tx = 2u * (uint32_t)(half_n * BLOCK_K * 2);
+            pdl_wait();
             for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
                 const int n_tile = tile % args.n_tiles, m_tile = 2 * (tile / args.n_tiles) + (int)rank;
                 const int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
@@ -768,12 +775,14 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0 && vb < num_tiles) {
             mbar_expect_tx(wfull, (uint32_t)(args.nb * N * args.b_k * 2));
             for (int i = 0; i < args.nb; ++i) tma_load_2d(&maps.b, sB + (size_t)i * args.b_stage_bytes, wfull, args.b_koff[i], ch0);
+            pdl_wait();                                   // weights load early; activations only after the previous layer is done
             int stage = 0; uint32_t phase = 0;
             int cb = 0; uint32_t cphase = 0;
             TileWalk t; t.init(vb, vgrid, args.tiles_x, args.tiles_y);
@@ -837,6 +846,7 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
         // takes a ring slot once the four epilogue warps have written it, TMA-stores it (one box per image row: the tile
         // is patch-pitched in smem) and frees the slot when the store engine has read it
         if (lane == 0) {
+            pdl_wait();
             TileWalk t; t.init(vb, vgrid, args.tiles_x, args.tiles_y);
             int cb = 0; uint32_t cphase = 0;
             for (int tile = vb; tile < num_tiles; tile += vgrid, t.next(args.tiles_x, args.tiles_y)) {
@@ -1018,6 +1028,32 @@ struct ConvTcPlan {
     std::string desc;
 };
 
+// every tcgen05 convolution is launched with programmatic stream serialization (see pdl_wait in tc_ptx.cuh)
+template <typename Kernel> static void launch_pdl(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t s, int cluster,
+                                                  const ConvTcMaps &maps, const ConvTcArgs &args)
+{
+    static const bool no_pdl = getenv("B200_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (!no_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    B200_CHECK(cudaLaunchKernelEx(&cfg, kernel, maps, args));
+}
+
 template <int BLOCK_K, typename OutT> static void launch_variant(ConvTcPlan *p, cudaStream_t s)
 {
     static bool configured = false;
@@ -1025,7 +1061,7 @@ template <int BLOCK_K, typename OutT> static void launch_variant(ConvTcPlan *p, 
         B200_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_K, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    conv_tc_kernel<BLOCK_K, OutT><<<p->grid, kTcThreads, p->smem_bytes, s>>>(p->maps, p->args);
+    launch_pdl(conv_tc_kernel<BLOCK_K, OutT>, p->grid, kTcThreads, p->smem_bytes, s, 1, p->maps, p->args);
 }
 
 template <int BLOCK_K, typename OutT> static void launch_pair_variant(ConvTcPlan *p, cudaStream_t s)
@@ -1035,16 +1071,7 @@ template <int BLOCK_K, typename OutT> static void launch_pair_variant(ConvTcPlan
         B200_CHECK(cudaFuncSetAttribute(conv_tc_pair_kernel<BLOCK_K, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p->grid);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = p->smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    B200_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<BLOCK_K, OutT>, p->maps, p->args));
+    launch_pdl(conv_tc_pair_kernel<BLOCK_K, OutT>, p->grid, kTcThreads, p->smem_bytes, s, 2, p->maps, p->args);
 }
 
 template <typename OutT> static void launch_halo_variant(ConvTcPlan *p, cudaStream_t s)
@@ -1054,16 +1081,7 @@ template <typename OutT> static void launch_halo_variant(ConvTcPlan *p, cudaStre
         B200_CHECK(cudaFuncSetAttribute(conv_tc_halo_pair_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p->grid);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = p->smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    B200_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_halo_pair_kernel<OutT>, p->maps, p->args));
+    launch_pdl(conv_tc_halo_pair_kernel<OutT>, p->grid, kTcThreads, p->smem_bytes, s, 2, p->maps, p->args);
 }
 
 template <int NSUB, int NSEG, int KS0, int KS1> static void launch_patch_variant(ConvTcPlan *p, cudaStream_t s)
@@ -1073,7 +1091,7 @@ template <int NSUB, int NSEG, int KS0, int KS1> static void launch_patch_variant
         B200_CHECK(cudaFuncSetAttribute(conv_tc_patch_kernel<NSUB, NSEG, KS0, KS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    conv_tc_patch_kernel<NSUB, NSEG, KS0, KS1><<<p->grid, 96 + 128 * p->args.ep_groups, p->smem_bytes, s>>>(p->maps, p->args);
+    launch_pdl(conv_tc_patch_kernel<NSUB, NSEG, KS0, KS1>, p->grid, 96 + 128 * p->args.ep_groups, p->smem_bytes, s, 1, p->maps, p->args);
 }
 template <int NSUB> static void launch_patch(ConvTcPlan *p, cudaStream_t s)
 {

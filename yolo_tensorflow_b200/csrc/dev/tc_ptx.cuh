@@ -147,6 +147,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)   // arrive on
 }
 
 
+// ---- programmatic dependent launch -------------------------------------------------------------------------
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while the previous kernel
+// of the stream is still draining: everything before pdl_wait() (barrier init, TMEM allocation, loads of WEIGHTS, which no
+// kernel writes) overlaps the predecessor's tail; pdl_wait() must precede the first read of an activation and the first
+// global write.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- UMMA shared-memory descriptors ------------------------------------------------------------------
 // shared-memory descriptor for a K-major operand tile whose rows are BLOCK_K*2 bytes (= the swizzle span)
 template <int BLOCK_K> __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
