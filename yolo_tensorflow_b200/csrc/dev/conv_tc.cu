@@ -61,6 +61,7 @@ struct ConvTcArgs {
     int a_k, b_k;            // elements per smem row of the patches / of the weight tiles (-> swizzle mode)
     int nb, b_koff[12];      // resident weight tiles: K offset of each [block_n x b_k] box
     int nseg, seg_a[12], seg_b[12], seg_k[12];   // K segments: patch byte offset (row shift), weight byte offset, K/16 steps
+    int ring;                // 1: ring epilogue (ring_roles) with 384 threads; c_bufs = ring depth (<= 4)
     int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
     int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
     long long npix;
@@ -72,6 +73,7 @@ struct ConvTcArgs {
 };
 
 static constexpr int kTcThreads = 192;
+static constexpr int kTcRingThreads = 384;      // ring epilogue: + store warp, residual loader, second epilogue group
 
 // epilogue math for NC accumulator columns of one pixel row: folded-BN scale/shift, activation, optional
 // residual, cast, 16-byte stores.  `sc`/`sh` point at the tile's per-filter constants in shared memory.
@@ -292,8 +294,182 @@ __device__ __forceinline__ void run_epilogue(const ConvTcMaps &maps, const ConvT
     if (staged && ep_tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int BLOCK_K, typename OutT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// mbar_wait as a macro: the spin shows up at the CALL SITE's line in profiler source views (which wait is the hot one)
+#define MBAR_WAIT_HERE(bar, parity)                                                                                      \
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"        \
+                 "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"((uint32_t)(parity)) : "memory")
+
+template <int PENDING> __device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Ring epilogue (args.ring): the tile leaves TMEM in 64-filter sub-tiles through a ring of swizzled 16 KB slots.
+//   warp 2      store warp: slot written -> TMA store -> slot free once the store engine has read it
+//   warp 3      residual loader (fused shortcut): slot free -> TMA load of the residual sub-tile, tiles ahead of the math
+//   warps 4-11  two epilogue groups (even / odd sub-tiles): TMEM -> scale/shift/leaky (+ residual, in place) -> slot
+// Nothing in a tile's epilogue waits on a DRAM round trip or on another role's bookkeeping; the roles only meet at
+// mbarriers.  With the serial epilogue (run_epilogue) a fused shortcut cost the 52x52 layers 18 % (990 vs 1200 TFLOP/s).
+// ---------------------------------------------------------------------------------------------------
+struct RingTile {
+    int n_tile, m_tile, col0, tx, ty, tn, rows_here;
+    bool real;
+};
+template <bool PAIR>
+__device__ __forceinline__ RingTile ring_tile(const ConvTcArgs &args, int tile, int rank)
+{
+    RingTile t;
+    t.n_tile = tile % args.n_tiles;
+    t.m_tile = PAIR ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
+    t.col0 = t.n_tile * args.block_n;
+    t.tx = t.ty = t.tn = 0; t.rows_here = 0;
+    t.real = t.m_tile < args.m_tiles;                       // an odd tile count leaves the pair's second CTA a phantom tile
+    if (args.mode >= 1) { t.tx = t.m_tile % args.tiles_x; t.ty = (t.m_tile / args.tiles_x) % args.tiles_y; t.tn = t.m_tile / (args.tiles_x * args.tiles_y); }
+    if (args.mode == 2) { t.rows_here = args.OH - t.ty * args.halo_THv; if (t.rows_here > args.halo_THv) t.rows_here = args.halo_THv; }
+    return t;
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcArgs &args, uint64_t *tfull, uint64_t *tempty,
+                                           uint64_t *ring_bars, uint8_t *sC, uint32_t tmem_base,
+                                           int first_tile, int tile_step, int num_tiles, int rank)
+{
+    uint64_t *cfull = ring_bars, *cempty = ring_bars + 4, *cwritten = ring_bars + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NSUB = args.block_n >> 6, NBUF = args.c_bufs;
+    const bool has_res = args.res != nullptr;
+    if (warp == 2) {
+        // ===================================== store warp =======================================
+        if (lane == 0) {
+            pdl_wait();
+            int j = 0;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                const RingTile t = ring_tile<PAIR>(args, tile, rank);
+                if (!t.real) continue;
+                for (int q = 0; q < NSUB; ++q, ++j) {
+                    const int slot = j % NBUF;
+                    const uint8_t *src = sC + (size_t)slot * 16384;
+                    MBAR_WAIT_HERE(&cwritten[slot], (j / NBUF) & 1);
+                    if (args.mode == 0) tma_store_2d(&maps.c, src, t.col0 + 64 * q, t.m_tile * 128);
+                    else if (args.mode == 1) tma_store_4d(&maps.c, src, t.col0 + 64 * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
+                    else
+                        for (int yy = 0; yy < t.rows_here; ++yy)
+                            tma_store_4d(&maps.c, src + yy * args.halo_P * 128, t.col0 + 64 * q, t.tx * args.halo_TWv, t.ty * args.halo_THv + yy, t.tn);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    bulk_wait_read<0>();
+                    mbar_arrive(&cempty[slot]);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp == 3) {
+        // ===================================== residual loader ==================================
+        if (lane == 0 && has_res) {
+            pdl_wait();
+            int j = 0;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                const RingTile t = ring_tile<PAIR>(args, tile, rank);
+                if (!t.real) continue;
+                for (int q = 0; q < NSUB; ++q, ++j) {
+                    const int slot = j % NBUF;
+                    uint8_t *dst = sC + (size_t)slot * 16384;
+                    MBAR_WAIT_HERE(&cempty[slot], ((j / NBUF) & 1) ^ 1);
+                    if (args.mode == 2) {
+                        mbar_expect_tx(&cfull[slot], (uint32_t)(t.rows_here * args.halo_TWv * 128));
+                        for (int yy = 0; yy < t.rows_here; ++yy)
+                            tma_load_4d(&maps.r, dst + yy * args.halo_P * 128, &cfull[slot], t.col0 + 64 * q, t.tx * args.halo_TWv, t.ty * args.halo_THv + yy, t.tn);
+                    } else {
+                        mbar_expect_tx(&cfull[slot], (uint32_t)(args.a_rows * 128));
+                        if (args.mode == 0) tma_load_2d(&maps.r, dst, &cfull[slot], t.col0 + 64 * q, t.m_tile * 128);
+                        else tma_load_4d(&maps.r, dst, &cfull[slot], t.col0 + 64 * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue groups ==================================
+        const int h = (warp - 4) >> 2;                     // group: sub-tiles q = h, h + 2, ...
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+        const int row = quarter * 32 + lane;
+        const bool leaky = args.act == ACT_LEAKY;
+        const float alpha = args.res_alpha, beta = args.res_beta;
+        const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
+        const uint32_t sC_addr = smem_u32(sC);
+        int acc = 0; uint32_t acc_phase = 0;
+        int jbase = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const RingTile t = ring_tile<PAIR>(args, tile, rank);
+            MBAR_WAIT_HERE(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
+            if (!t.real || h >= NSUB) {                    // nothing to emit: just hand the accumulator back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+            } else {
+                for (int q = h; q < NSUB; q += 2) {
+                    const int j = jbase + q, slot = j % NBUF;
+                    const uint32_t sphase = (uint32_t)(j / NBUF) & 1u;
+                    const uint32_t slot_addr = sC_addr + (uint32_t)slot * 16384u;
+                    uint32_t r[64];
+                    tmem_ld32(taddr + 64 * q, r);
+                    tmem_ld32(taddr + 64 * q + 32, r + 32);
+                    tmem_ld_wait();
+                    if (q + 2 >= NSUB) {                   // this group's last sub-tile: the accumulator can be reused
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+                    }
+                    if (has_res) MBAR_WAIT_HERE(&cfull[slot], sphase);
+                    else MBAR_WAIT_HERE(&cempty[slot], sphase ^ 1u);
+                    const float *gsc = args.scale + t.col0 + 64 * q, *gsh = args.shift + t.col0 + 64 * q;
+#pragma unroll
+                    for (int c = 0; c < 64; c += 8) {
+                        const uint32_t addr = slot_addr + row_off + ((((uint32_t)c >> 3) ^ row_x) << 4);
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u += 4) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(gsc + c + u));
+                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(gsh + c + u));
+                            v[u + 0] = fmaf(__uint_as_float(r[c + u + 0]), s4.x, h4.x);
+                            v[u + 1] = fmaf(__uint_as_float(r[c + u + 1]), s4.y, h4.y);
+                            v[u + 2] = fmaf(__uint_as_float(r[c + u + 2]), s4.z, h4.z);
+                            v[u + 3] = fmaf(__uint_as_float(r[c + u + 3]), s4.w, h4.w);
+                        }
+                        if (leaky) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) v[u] = v[u] > 0.f ? v[u] : 0.1f * v[u];
+                        }
+                        if (has_res) {
+                            const uint4 rr = lds128(addr);
+                            const __nv_bfloat162 *hh = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 f = __bfloat1622float2(hh[u]);
+                                v[2 * u] = fmaf(alpha, v[2 * u], beta * f.x);
+                                v[2 * u + 1] = fmaf(alpha, v[2 * u + 1], beta * f.y);
+                            }
+                        }
+                        uint4 o;
+                        __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) oh[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+                        sts128(addr, o);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&cwritten[slot]);
+                }
+            }
+            if (t.real) jbase += NSUB;
+            if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+}
+
+template <int BLOCK_K, typename OutT, bool RING>      // RING: ring epilogue roles (384 threads); else the serial epilogue (192)
+__global__ void __launch_bounds__(RING ? kTcRingThreads : kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -304,7 +480,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
     uint8_t *sB = smem + (size_t)stages * A_BYTES;
     const int b_slots = args.resident_b ? args.num_kblocks : stages;
     uint8_t *sC = sB + (size_t)b_slots * args.b_stage_bytes;       // staged-epilogue tile: (block_n/64) x 16 KB, 1024-aligned
-    uint8_t *aux = sC + (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0);
+    uint8_t *aux = sC + (args.ring ? (size_t)args.c_bufs * 16384 : (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0));
+    uint64_t *ring_bars = (uint64_t *)(aux + 384);     // ring epilogue: cfull[4], cempty[4], cwritten[4]
     uint64_t *full = (uint64_t *)aux;                 // [stages]
     uint64_t *empty = full + 8;                       // [stages]
     uint64_t *tfull = empty + 8;                      // [acc_stages <= 8]
@@ -320,7 +497,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < args.acc_stages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        const int ep_warps = args.ring ? 8 : 4;             // both ring groups hand the accumulator back, even an idle one
+        for (int i = 0; i < args.acc_stages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], ep_warps); }
+        if (args.ring)
+            for (int i = 0; i < 4; ++i) { mbar_init(&ring_bars[i], 1); mbar_init(&ring_bars[4 + i], 1); mbar_init(&ring_bars[8 + i], 4); }
         mbar_init(wfull, 1);
         mbar_init(rfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -407,7 +587,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
         }
     } else {
         // ===================================== epilogue (warps 2..5) ============================
-        run_epilogue<OutT, false>(maps, args, tfull, tempty, rfull, s_scale, s_shift, sC, tmem_base, blockIdx.x, gridDim.x, num_tiles, 0);
+        if constexpr (RING) ring_roles<false>(maps, args, tfull, tempty, ring_bars, sC, tmem_base, blockIdx.x, gridDim.x, num_tiles, 0);
+        else run_epilogue<OutT, false>(maps, args, tfull, tempty, rfull, s_scale, s_shift, sC, tmem_base, blockIdx.x, gridDim.x, num_tiles, 0);
     }
 
     tc_fence_before();
@@ -425,8 +606,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 // Barriers: full[s] lives in the leader and collects the TMA bytes of both CTAs; empty[s] / tfull[a] are signalled
 // in both CTAs by a multicast tcgen05.commit; tempty[a] lives in the leader and collects the 8 epilogue warps.
 // ---------------------------------------------------------------------------------------------------
-template <int BLOCK_K, typename OutT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BLOCK_K, typename OutT, bool RING>
+__global__ void __launch_bounds__(RING ? kTcRingThreads : kTcThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -436,7 +617,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)stages * A_BYTES;
     uint8_t *sC = sB + (size_t)stages * args.b_stage_bytes;        // b_stage_bytes = half tile here
-    uint8_t *aux = sC + (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0);
+    uint8_t *aux = sC + (args.ring ? (size_t)args.c_bufs * 16384 : (args.staged ? (size_t)(args.block_n >> 6) * 16384 : 0));
+    uint64_t *ring_bars = (uint64_t *)(aux + 384);     // ring epilogue: cfull[4], cempty[4], cwritten[4]
     uint64_t *full = (uint64_t *)aux;
     uint64_t *empty = full + 8;
     uint64_t *tfull = empty + 8;
@@ -455,7 +637,10 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < args.acc_stages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        const int ep_warps = args.ring ? 16 : 8;            // epilogue warps of both CTAs
+        for (int i = 0; i < args.acc_stages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], ep_warps); }
+        if (args.ring)
+            for (int i = 0; i < 4; ++i) { mbar_init(&ring_bars[i], 1); mbar_init(&ring_bars[4 + i], 1); mbar_init(&ring_bars[8 + i], 4); }
         mbar_init(rfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -535,7 +720,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
         }
     } else {
         // ===================================== epilogue (warps 2..5, both CTAs) =================
-        run_epilogue<OutT, true>(maps, args, tfull, tempty, rfull, s_scale, s_shift, sC, tmem_base, pair_id, num_pairs, num_tiles, (int)rank);
+        if constexpr (RING) ring_roles<true>(maps, args, tfull, tempty, ring_bars, sC, tmem_base, pair_id, num_pairs, num_tiles, (int)rank);
+        else run_epilogue<OutT, true>(maps, args, tfull, tempty, rfull, s_scale, s_shift, sC, tmem_base, pair_id, num_pairs, num_tiles, (int)rank);
     }
 
     tc_fence_before();
@@ -706,10 +892,6 @@ struct TileWalk {
     }
 };
 
-template <int PENDING> __device__ __forceinline__ void bulk_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
-}
 __device__ __forceinline__ void group_sync(int group)            // the 128 threads of one epilogue group
 {
     asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
@@ -721,11 +903,6 @@ __device__ __forceinline__ void group_sync(int group)            // the 128 thre
 // in place, the store warp TMA-stores the slot and frees it once the store engine has read it.  With a K pass this short
 // (18 MMAs) everything else on a tile's path has to be off the critical path: no role waits on a DRAM round trip or on
 // another role's bookkeeping, and the roles talk through mbarriers only.
-// mbar_wait as a macro: the spin shows up at the CALL SITE's line in profiler source views (which wait is the hot one)
-#define MBAR_WAIT_HERE(bar, parity)                                                                                      \
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"        \
-                 "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"((uint32_t)(parity)) : "memory")
-
 template <int NSUB, int NSEG, int KS0, int KS1>       // K segment s issues (s odd ? KS1 : KS0) K=16 steps
 __global__ void __launch_bounds__(352, 1)
 conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
@@ -1058,20 +1235,24 @@ template <int BLOCK_K, typename OutT> static void launch_variant(ConvTcPlan *p, 
 {
     static bool configured = false;
     if (!configured) {
-        B200_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_K, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_K, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_K, bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    launch_pdl(conv_tc_kernel<BLOCK_K, OutT>, p->grid, kTcThreads, p->smem_bytes, s, 1, p->maps, p->args);
+    if (p->args.ring) launch_pdl(conv_tc_kernel<BLOCK_K, bf16, true>, p->grid, kTcRingThreads, p->smem_bytes, s, 1, p->maps, p->args);
+    else launch_pdl(conv_tc_kernel<BLOCK_K, OutT, false>, p->grid, kTcThreads, p->smem_bytes, s, 1, p->maps, p->args);
 }
 
 template <int BLOCK_K, typename OutT> static void launch_pair_variant(ConvTcPlan *p, cudaStream_t s)
 {
     static bool configured = false;
     if (!configured) {
-        B200_CHECK(cudaFuncSetAttribute(conv_tc_pair_kernel<BLOCK_K, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_pair_kernel<BLOCK_K, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(conv_tc_pair_kernel<BLOCK_K, bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    launch_pdl(conv_tc_pair_kernel<BLOCK_K, OutT>, p->grid, kTcThreads, p->smem_bytes, s, 2, p->maps, p->args);
+    if (p->args.ring) launch_pdl(conv_tc_pair_kernel<BLOCK_K, bf16, true>, p->grid, kTcRingThreads, p->smem_bytes, s, 2, p->maps, p->args);
+    else launch_pdl(conv_tc_pair_kernel<BLOCK_K, OutT, false>, p->grid, kTcThreads, p->smem_bytes, s, 2, p->maps, p->args);
 }
 
 template <typename OutT> static void launch_halo_variant(ConvTcPlan *p, cudaStream_t s)
@@ -1394,9 +1575,18 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     // staged epilogue (TMEM -> registers -> swizzled smem tile -> TMA store, residual TMA-loaded into the same tile) is used
     // where a shortcut is fused: the per-row residual reads of the direct epilogue are what made fused layers slow.
     const int a_bytes_ = 128 * block_k * 2;
-    const int sc_bytes = (a.block_n / 64) * 16384;
     const int budget_all = 227 * 1024 - 1024 - (512 + 4096);
-    const bool want_staged = residual && !getenv("B200_NO_STAGED") && out.dtype == DT_BF16 && a.block_n % 64 == 0 && cp.cout_pad % 64 == 0;
+    // staged epilogue = the ring epilogue (ring_roles) for the tap-per-box kernels, the serial staged path of run_epilogue
+    // for the (opt-in) halo pair kernel.
+    const bool stageable = out.dtype == DT_BF16 && a.block_n % 64 == 0 && cp.cout_pad % 64 == 0 && out.c == cp.cout_pad;
+    // MEASURED (YOLOv3-416 b64): the ring epilogue wins on every stageable layer (1x1 layers -10..-20 %, fused shortcuts
+    // -8 %) except the stride-2 3x3 layers without a residual, which lose the pipeline stage the ring's slots cost (+3 %).
+    const bool ring_pays = residual || !(cp.size == 3 && cp.stride == 2 && a.block_n == 256);
+    const bool want_staged = stageable && !getenv("B200_NO_STAGED") && (getenv("B200_RING_RESIDUAL_ONLY") ? residual != nullptr : ring_pays);
+    const bool use_ring = want_staged && a.mode != 2 && !getenv("B200_NO_RING");
+    int ring_slots = 3;                                  // measured: 3 slots beat 2 and 4 (a 4th costs a pipeline stage)
+    if (getenv("B200_RING_SLOTS")) { int f = atoi(getenv("B200_RING_SLOTS")); if (f >= 2 && f <= 4) ring_slots = f; }
+    const int sc_bytes = use_ring ? ring_slots * 16384 : (a.block_n / 64) * 16384;
     const long long slab_ = (long long)a.num_kblocks * ((a.block_n * block_k * 2 + 1023) / 1024 * 1024);
     const bool could_reside = a.n_tiles == 1 && !getenv("B200_NO_RESIDENT_B") &&
                               slab_ + (want_staged ? 3LL * a_bytes_ + sc_bytes : 4LL * a_bytes_) <= budget_all;
@@ -1455,6 +1645,8 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         const long long need = could_reside ? slab_ + 3LL * a_bytes : 3LL * (a_bytes + a.b_stage_bytes);
         if (need + sc_bytes <= budget) { a.staged = 1; budget -= sc_bytes; }
     }
+    a.ring = (a.staged && use_ring) ? 1 : 0;
+    a.c_bufs = ring_slots;
     // weight-stationary variant: when one filter tile covers all filters and its whole [block_n x K] slab fits next
     // to >= 4 activation stages, load it once per CTA and stream only activations (halves the TMA rows per k-block)
     const long long slab = (long long)a.num_kblocks * a.b_stage_bytes;
@@ -1497,6 +1689,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
              a.pair ? " PAIR(cta_group::2)" : (a.resident_b ? " residentB" : ""), a.res ? " +residual" : "");
 
     p->desc = buf;
-    if (a.staged) p->desc += " stagedEpilogue";
+    if (a.ring) p->desc += " ringEpilogue(" + std::to_string(a.c_bufs) + ")";
+    else if (a.staged) p->desc += " stagedEpilogue";
     return p;
 }
