@@ -561,10 +561,14 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
+        // the whole warp walks the loop and one elected lane issues (see tc_mma_bf16_elect): with N <= 128 an MMA is
+        // 32-64 cycles of tensor time, less than the ~80 cycles a lane-0-only issue sequence costs
+        {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.block_n >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            const uint64_t adesc0 = make_desc<BLOCK_K>(smem_u32(sA)), bdesc0 = make_desc<BLOCK_K>(smem_u32(sB));
+            const uint32_t a_step = (uint32_t)A_BYTES >> 4, b_step = (uint32_t)args.b_stage_bytes >> 4;
             if (args.resident_b && (int)blockIdx.x < num_tiles) mbar_wait(wfull, 0);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -573,15 +577,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
                 for (int kb = 0; kb < args.num_kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_desc<BLOCK_K>(smem_u32(sA + (size_t)stage * A_BYTES));
-                    const uint64_t bdesc = make_desc<BLOCK_K>(smem_u32(sB + (size_t)(args.resident_b ? kb : stage) * args.b_stage_bytes));
+                    const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)stage * a_step);
+                    const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(args.resident_b ? kb : stage) * b_step);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k)
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(&empty[stage]);                 // frees the smem slot once these MMAs have read it
+                        tc_mma_bf16_elect(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_elect(&empty[stage]);           // frees the smem slot once these MMAs have read it
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull[acc]);                       // accumulator complete -> epilogue
+                tc_commit_elect(&tfull[acc]);                 // accumulator complete -> epilogue
                 if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }
