@@ -172,6 +172,41 @@ static void build_engine_device_state(b200_engine *e, network *net)
         e->L[i + 1].fused_away = true;
     }
 
+    // ---- zero-copy concatenation: a route's inputs are produced straight into channel slices of the route's buffer ----
+    // (route_layer.c:80-95 copies every input; here only inputs that cannot be placed are copied).  An input is placed
+    // when its producer writes through a TView (row pitch = the route's channel count) and nothing needs it dense.
+    std::vector<int> place_route(net->n, -1), place_off(net->n, 0);
+    for (int r = 0; r < net->n && !getenv("B200_NO_ZERO_COPY_ROUTE"); ++r) {
+        const layer &rl = net->layers[r];
+        if (rl.type != ROUTE || rl.n < 2 || rl.out_c == 0) continue;
+        const int align = 16 / esize;                                   // slice starts stay 16-byte aligned
+        if (rl.out_c % align != 0) continue;
+        int coff = 0;
+        for (int j = 0; j < rl.n; ++j) {
+            const int sidx = rl.input_layers[j];
+            const layer &sl = net->layers[sidx];
+            bool ok = place_route[sidx] < 0 && coff % align == 0 && sl.out_c % 16 == 0 &&
+                      (sl.type == CONVOLUTIONAL || sl.type == UPSAMPLE || sl.type == SHORTCUT || sl.type == MAXPOOL || sl.type == REORG);
+            if (sl.type == CONVOLUTIONAL && (e->L[sidx].fused_into >= 0 || (sidx == 0 && e->L[0].stem_kpad))) ok = false;
+            for (int c : cons[sidx]) {
+                LAYER_TYPE ct = net->layers[c].type;
+                if (ct == CONNECTED || ct == YOLO || ct == REGION || ct == DETECTION) ok = false;     // these read dense buffers
+            }
+            if (ok) { place_route[sidx] = r; place_off[sidx] = coff; }
+            coff += sl.out_c;
+        }
+    }
+    auto concat_slice = [&](int sidx, const layer &sl, int dtype) -> TView {
+        const int r = place_route[sidx];
+        DevLayer &rd = e->L[r];
+        const layer &rl = net->layers[r];
+        if (!rd.out.p) {
+            rd.out = TView{dev_alloc((size_t)e->cap * rl.outputs * dt_size(dtype)), e->cap, rl.out_h, rl.out_w, rl.out_c, rl.out_c, dtype};
+            rd.owns_out = true;
+        }
+        return TView{(unsigned char *)rd.out.p + (size_t)place_off[sidx] * dt_size(dtype), e->cap, sl.out_h, sl.out_w, sl.out_c, rl.out_c, dtype};
+    };
+
     // ---- output views ------------------------------------------------------------------------------
     for (int i = 0; i < net->n; ++i) {
         const layer &l = net->layers[i];
@@ -192,17 +227,20 @@ static void build_engine_device_state(b200_engine *e, network *net)
                 d.owns_out = false;
                 break;
             }
+            if (place_route[i] >= 0 && dtype == e->act_dtype) { d.out = concat_slice(i, l, dtype); d.owns_out = false; break; }
             d.out = TView{dev_alloc((size_t)e->cap * l.out_h * l.out_w * ld * dt_size(dtype)), e->cap, l.out_h, l.out_w, l.out_c, ld, dtype};
             d.owns_out = true;
             break;
         }
         case MAXPOOL: case UPSAMPLE: case SHORTCUT: case REORG: case LOCAL:
+            if (place_route[i] >= 0 && l.type != LOCAL) { d.out = concat_slice(i, l, dtype); d.owns_out = false; break; }
             d.out = TView{dev_alloc(floats * dt_size(dtype)), e->cap, l.out_h, l.out_w, l.out_c, l.out_c, dtype};
             d.owns_out = true;
             break;
         case ROUTE:
             if (l.out_c == 0) { fprintf(stderr, "b200-darknet: route %d joins layers of different spatial size\n", i); abort(); }
             if (l.n == 1) { d.out = e->L[l.input_layers[0]].out; d.owns_out = false; }
+            else if (d.out.p) { /* allocated when its first placed input was planned */ }
             else {
                 int dt0 = e->L[l.input_layers[0]].out.dtype;
                 d.out = TView{dev_alloc(floats * dt_size(dt0)), e->cap, l.out_h, l.out_w, l.out_c, l.out_c, dt0};
@@ -311,7 +349,12 @@ static void build_engine_device_state(b200_engine *e, network *net)
         case UPSAMPLE: d.kernel = "upsample"; break;
         case SHORTCUT: d.kernel = d.fused_away ? "fused" : "shortcut"; break;
         case REORG: d.kernel = "reorg"; break;
-        case ROUTE: d.kernel = l.n == 1 ? "alias" : "route_copy"; break;
+        case ROUTE: {
+            bool all_placed = l.n > 1;
+            for (int j = 0; j < l.n && l.n > 1; ++j) if (place_route[l.input_layers[j]] != i) all_placed = false;
+            d.kernel = l.n == 1 ? "alias" : (all_placed ? "concat_in_place" : "route_copy");
+            break;
+        }
         case DROPOUT: d.kernel = "alias"; break;
         case LOCAL: d.kernel = "local"; break;
         case CONNECTED: d.kernel = "connected"; break;
@@ -548,7 +591,7 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
                 TView dst = out;
                 dst.p = (unsigned char *)out.p + (size_t)coff * dt_size(out.dtype);
                 dst.c = src.c;
-                launch_copy_channels(src, dst, s);
+                if (src.p != dst.p) launch_copy_channels(src, dst, s);      // placed inputs were produced in this slice
                 coff += src.c;
             }
         }
