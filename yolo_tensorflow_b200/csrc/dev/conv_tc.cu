@@ -61,6 +61,7 @@ struct ConvTcArgs {
     int a_k, b_k;            // elements per smem row of the patches / of the weight tiles (-> swizzle mode)
     int nb, b_koff[12];      // resident weight tiles: K offset of each [block_n x b_k] box
     int nseg, seg_a[12], seg_b[12], seg_k[12];   // K segments: patch byte offset (row shift), weight byte offset, K/16 steps
+    int sub_cols, out_f32;   // ring epilogue sub-tile: filters per slot (64 or 32), fp32 output rows
     int ring;                // 1: ring epilogue (ring_roles) with 384 threads; c_bufs = ring depth (<= 4)
     int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
     int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
@@ -330,6 +331,63 @@ __device__ __forceinline__ RingTile ring_tile(const ConvTcArgs &args, int tile, 
     return t;
 }
 
+// hand a TMEM accumulator back to the MMA issuer (the pair's barrier lives in the leader CTA)
+template <bool PAIR> __device__ __forceinline__ void ring_release(uint64_t *tempty, int acc, int lane)
+{
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+}
+
+// one pixel row of a sub-tile: SUBC accumulator columns -> scale/shift/leaky (+ residual, read from the slot) -> the slot.
+// Slot rows are SUBC * esz bytes (128 or 64) = the swizzle span: 16-byte chunk k of row r sits at chunk k ^ f(r).
+template <int SUBC, bool F32>
+__device__ __forceinline__ void ring_emit(const uint32_t *r, const float *gsc, const float *gsh, uint32_t slot_addr, int row,
+                                          bool leaky, bool has_res, float alpha, float beta)
+{
+    constexpr int RB = SUBC * (F32 ? 4 : 2);
+    const uint32_t row_addr = slot_addr + (uint32_t)row * RB;
+    const uint32_t swz = RB == 128 ? (uint32_t)(row & 7) : ((uint32_t)(row >> 1) & 3u);
+#pragma unroll
+    for (int c = 0; c < SUBC; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(gsc + c + u));
+            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(gsh + c + u));
+            v[u + 0] = fmaf(__uint_as_float(r[c + u + 0]), s4.x, h4.x);
+            v[u + 1] = fmaf(__uint_as_float(r[c + u + 1]), s4.y, h4.y);
+            v[u + 2] = fmaf(__uint_as_float(r[c + u + 2]), s4.z, h4.z);
+            v[u + 3] = fmaf(__uint_as_float(r[c + u + 3]), s4.w, h4.w);
+        }
+        if (leaky) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = v[u] > 0.f ? v[u] : 0.1f * v[u];
+        }
+        if constexpr (F32) {
+            sts128(row_addr + ((((uint32_t)c >> 2) ^ swz) << 4), make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+            sts128(row_addr + (((((uint32_t)c >> 2) + 1) ^ swz) << 4), make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+        } else {
+            const uint32_t addr = row_addr + ((((uint32_t)c >> 3) ^ swz) << 4);
+            if (has_res) {
+                const uint4 rr = lds128(addr);
+                const __nv_bfloat162 *hh = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 f = __bfloat1622float2(hh[u]);
+                    v[2 * u] = fmaf(alpha, v[2 * u], beta * f.x);
+                    v[2 * u + 1] = fmaf(alpha, v[2 * u + 1], beta * f.y);
+                }
+            }
+            uint4 o;
+            __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) oh[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+            sts128(addr, o);
+        }
+    }
+}
+
 template <bool PAIR>
 __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcArgs &args, uint64_t *tfull, uint64_t *tempty,
                                            uint64_t *ring_bars, uint8_t *sC, uint32_t tmem_base,
@@ -337,7 +395,9 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
 {
     uint64_t *cfull = ring_bars, *cempty = ring_bars + 4, *cwritten = ring_bars + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NSUB = args.block_n >> 6, NBUF = args.c_bufs;
+    const int SUBC = args.sub_cols;                        // filters per sub-tile: 64 (bf16) or 32 (bf16 / fp32 outputs)
+    const int NSUB = args.block_n / SUBC, NBUF = args.c_bufs;
+    const int row_bytes = SUBC * (args.out_f32 ? 4 : 2);   // 128 or 64: also the swizzle span of the slot
     const bool has_res = args.res != nullptr;
     if (warp == 2) {
         // ===================================== store warp =======================================
@@ -351,11 +411,11 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
                     const int slot = j % NBUF;
                     const uint8_t *src = sC + (size_t)slot * 16384;
                     MBAR_WAIT_HERE(&cwritten[slot], (j / NBUF) & 1);
-                    if (args.mode == 0) tma_store_2d(&maps.c, src, t.col0 + 64 * q, t.m_tile * 128);
-                    else if (args.mode == 1) tma_store_4d(&maps.c, src, t.col0 + 64 * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
+                    if (args.mode == 0) tma_store_2d(&maps.c, src, t.col0 + SUBC * q, t.m_tile * 128);
+                    else if (args.mode == 1) tma_store_4d(&maps.c, src, t.col0 + SUBC * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
                     else
                         for (int yy = 0; yy < t.rows_here; ++yy)
-                            tma_store_4d(&maps.c, src + yy * args.halo_P * 128, t.col0 + 64 * q, t.tx * args.halo_TWv, t.ty * args.halo_THv + yy, t.tn);
+                            tma_store_4d(&maps.c, src + yy * args.halo_P * row_bytes, t.col0 + SUBC * q, t.tx * args.halo_TWv, t.ty * args.halo_THv + yy, t.tn);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     bulk_wait_read<0>();
                     mbar_arrive(&cempty[slot]);
@@ -378,11 +438,11 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
                     if (args.mode == 2) {
                         mbar_expect_tx(&cfull[slot], (uint32_t)(t.rows_here * args.halo_TWv * 128));
                         for (int yy = 0; yy < t.rows_here; ++yy)
-                            tma_load_4d(&maps.r, dst + yy * args.halo_P * 128, &cfull[slot], t.col0 + 64 * q, t.tx * args.halo_TWv, t.ty * args.halo_THv + yy, t.tn);
+                            tma_load_4d(&maps.r, dst + yy * args.halo_P * row_bytes, &cfull[slot], t.col0 + SUBC * q, t.tx * args.halo_TWv, t.ty * args.halo_THv + yy, t.tn);
                     } else {
                         mbar_expect_tx(&cfull[slot], (uint32_t)(args.a_rows * 128));
-                        if (args.mode == 0) tma_load_2d(&maps.r, dst, &cfull[slot], t.col0 + 64 * q, t.m_tile * 128);
-                        else tma_load_4d(&maps.r, dst, &cfull[slot], t.col0 + 64 * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
+                        if (args.mode == 0) tma_load_2d(&maps.r, dst, &cfull[slot], t.col0 + SUBC * q, t.m_tile * 128);
+                        else tma_load_4d(&maps.r, dst, &cfull[slot], t.col0 + SUBC * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
                     }
                 }
             }
@@ -394,7 +454,6 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
         const int row = quarter * 32 + lane;
         const bool leaky = args.act == ACT_LEAKY;
         const float alpha = args.res_alpha, beta = args.res_beta;
-        const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
         const uint32_t sC_addr = smem_u32(sC);
         int acc = 0; uint32_t acc_phase = 0;
         int jbase = 0;
@@ -412,50 +471,25 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
                     const int j = jbase + q, slot = j % NBUF;
                     const uint32_t sphase = (uint32_t)(j / NBUF) & 1u;
                     const uint32_t slot_addr = sC_addr + (uint32_t)slot * 16384u;
-                    uint32_t r[64];
-                    tmem_ld32(taddr + 64 * q, r);
-                    tmem_ld32(taddr + 64 * q + 32, r + 32);
-                    tmem_ld_wait();
-                    if (q + 2 >= NSUB) {                   // this group's last sub-tile: the accumulator can be reused
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
-                    }
-                    if (has_res) MBAR_WAIT_HERE(&cfull[slot], sphase);
-                    else MBAR_WAIT_HERE(&cempty[slot], sphase ^ 1u);
-                    const float *gsc = args.scale + t.col0 + 64 * q, *gsh = args.shift + t.col0 + 64 * q;
-#pragma unroll
-                    for (int c = 0; c < 64; c += 8) {
-                        const uint32_t addr = slot_addr + row_off + ((((uint32_t)c >> 3) ^ row_x) << 4);
-                        float v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u += 4) {
-                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(gsc + c + u));
-                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(gsh + c + u));
-                            v[u + 0] = fmaf(__uint_as_float(r[c + u + 0]), s4.x, h4.x);
-                            v[u + 1] = fmaf(__uint_as_float(r[c + u + 1]), s4.y, h4.y);
-                            v[u + 2] = fmaf(__uint_as_float(r[c + u + 2]), s4.z, h4.z);
-                            v[u + 3] = fmaf(__uint_as_float(r[c + u + 3]), s4.w, h4.w);
-                        }
-                        if (leaky) {
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) v[u] = v[u] > 0.f ? v[u] : 0.1f * v[u];
-                        }
-                        if (has_res) {
-                            const uint4 rr = lds128(addr);
-                            const __nv_bfloat162 *hh = reinterpret_cast<const __nv_bfloat162 *>(&rr);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float2 f = __bfloat1622float2(hh[u]);
-                                v[2 * u] = fmaf(alpha, v[2 * u], beta * f.x);
-                                v[2 * u + 1] = fmaf(alpha, v[2 * u + 1], beta * f.y);
-                            }
-                        }
-                        uint4 o;
-                        __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) oh[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
-                        sts128(addr, o);
+                    const bool last = q + 2 >= NSUB;       // this group's last sub-tile: the accumulator can be reused after the load
+                    const float *gsc = args.scale + t.col0 + SUBC * q, *gsh = args.shift + t.col0 + SUBC * q;
+                    if (SUBC == 64) {
+                        uint32_t r[64];
+                        tmem_ld32(taddr + 64 * q, r);
+                        tmem_ld32(taddr + 64 * q + 32, r + 32);
+                        tmem_ld_wait();
+                        if (last) ring_release<PAIR>(tempty, acc, lane);
+                        if (has_res) MBAR_WAIT_HERE(&cfull[slot], sphase);
+                        else MBAR_WAIT_HERE(&cempty[slot], sphase ^ 1u);
+                        ring_emit<64, false>(r, gsc, gsh, slot_addr, row, leaky, has_res, alpha, beta);
+                    } else {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + 32 * q, r);
+                        tmem_ld_wait();
+                        if (last) ring_release<PAIR>(tempty, acc, lane);
+                        MBAR_WAIT_HERE(&cempty[slot], sphase ^ 1u);
+                        if (args.out_f32) ring_emit<32, true>(r, gsc, gsh, slot_addr, row, leaky, false, alpha, beta);
+                        else ring_emit<32, false>(r, gsc, gsh, slot_addr, row, leaky, false, alpha, beta);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -1183,20 +1217,26 @@ void tc_encode_tiled(void *map, int dtype, int rank, void *base, const unsigned 
     if (r != CUDA_SUCCESS) { fprintf(stderr, "b200-darknet: cuTensorMapEncodeTiled failed (%d)\n", (int)r); abort(); }
 }
 
-static void encode_tile_view(CUtensorMap *map, const TView &t, int channels, const ConvTcArgs &a)
+void tc_encode_tiled(void *map, int dtype, int rank, void *base, const unsigned long long *dims, const unsigned long long *strides_bytes,
+                     const unsigned *box, int swizzle_bytes);
+
+// output / residual tile view: boxes of `sub_cols` channels (rows of sub_cols * esz bytes = the swizzle span)
+static void encode_tile_view(CUtensorMap *map, const TView &t, int channels, const ConvTcArgs &a, int sub_cols = 64)
 {
-    const size_t esz = 2;
+    const unsigned long long esz = dt_size(t.dtype);
+    const int dtype = t.dtype == DT_F32 ? 1 : 0;
+    const int swz = (int)(sub_cols * esz);
     if (a.mode == 0) {
-        cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)a.npix};
-        cuuint64_t strides[1] = {(cuuint64_t)t.ld * esz};
-        cuuint32_t box[2] = {64, 128};
-        encode(map, t.p, 2, dims, strides, box, 64);
+        unsigned long long dims[2] = {(unsigned long long)channels, (unsigned long long)a.npix};
+        unsigned long long strides[1] = {(unsigned long long)t.ld * esz};
+        unsigned box[2] = {(unsigned)sub_cols, 128};
+        tc_encode_tiled(map, dtype, 2, t.p, dims, strides, box, swz);
     } else {
-        cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
-        cuuint64_t strides[3] = {(cuuint64_t)t.ld * esz, (cuuint64_t)t.w * t.ld * esz, (cuuint64_t)t.h * t.w * t.ld * esz};
-        cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, (cuuint32_t)a.TN};
-        if (a.mode == 2) { box[1] = (cuuint32_t)a.halo_TWv; box[2] = 1; box[3] = 1; }      // one image row of the tile per box
-        encode(map, t.p, 4, dims, strides, box, 64);
+        unsigned long long dims[4] = {(unsigned long long)channels, (unsigned long long)t.w, (unsigned long long)t.h, (unsigned long long)t.n};
+        unsigned long long strides[3] = {(unsigned long long)t.ld * esz, (unsigned long long)t.w * t.ld * esz, (unsigned long long)t.h * t.w * t.ld * esz};
+        unsigned box[4] = {(unsigned)sub_cols, (unsigned)a.TW, (unsigned)a.TH, (unsigned)a.TN};
+        if (a.mode == 2) { box[1] = (unsigned)a.halo_TWv; box[2] = 1; box[3] = 1; }      // one image row of the tile per box
+        tc_encode_tiled(map, dtype, 4, t.p, dims, strides, box, swz);
     }
 }
 
@@ -1582,7 +1622,12 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     const int budget_all = 227 * 1024 - 1024 - (512 + 4096);
     // staged epilogue = the ring epilogue (ring_roles) for the tap-per-box kernels, the serial staged path of run_epilogue
     // for the (opt-in) halo pair kernel.
-    const bool stageable = out.dtype == DT_BF16 && a.block_n % 64 == 0 && cp.cout_pad % 64 == 0 && out.c == cp.cout_pad;
+    const bool stageable64 = out.dtype == DT_BF16 && a.block_n % 64 == 0 && cp.cout_pad % 64 == 0 && out.c == cp.cout_pad;
+    // 32-filter sub-tiles: bf16 layers with 32 (mod 64) filters and the fp32 head convolutions (255 -> 256 padded filters:
+    // the pad column lands in the row's own padding, never in a neighbour's slice of a concat buffer)
+    const bool stageable32 = !residual && a.block_n % 32 == 0 && cp.cout_pad % 32 == 0 && (out.c == cp.cout_pad || out.ld == cp.cout_pad) &&
+                             a.mode != 2 && !getenv("B200_NO_RING32");
+    const bool stageable = stageable64 || stageable32;
     // MEASURED (YOLOv3-416 b64): the ring epilogue wins on every stageable layer (1x1 layers -10..-20 %, fused shortcuts
     // -8 %) except the stride-2 3x3 layers without a residual, which lose the pipeline stage the ring's slots cost (+3 %).
     const bool ring_pays = residual || !(cp.size == 3 && cp.stride == 2 && a.block_n == 256);
@@ -1599,7 +1644,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         a.pair = 1; a.resident_b = 0;
         a.b_stage_bytes = ((a.block_n / 2) * block_k * 2 + 1023) / 1024 * 1024;
         int budget2 = 227 * 1024 - 1024 - (512 + 4096);
-        a.staged = (want_staged && sc_bytes + 2 * a.a_stage_bytes + 3 * a.b_stage_bytes <= budget2) ? 1 : 0;
+        a.staged = (want_staged && stageable64 && sc_bytes + 2 * a.a_stage_bytes + 3 * a.b_stage_bytes <= budget2) ? 1 : 0;
         if (a.staged) budget2 -= sc_bytes;
         int a_st = 2;
         int b_st = (budget2 - a_st * a.a_stage_bytes) / a.b_stage_bytes;
@@ -1645,12 +1690,14 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     const int aux_bytes = 512 + 2 * 512 * 4;
     int budget = 227 * 1024 - 1024 - aux_bytes;
     a.staged = 0;
-    if (want_staged) {
+    if (want_staged && (use_ring || stageable64)) {
         const long long need = could_reside ? slab_ + 3LL * a_bytes : 3LL * (a_bytes + a.b_stage_bytes);
         if (need + sc_bytes <= budget) { a.staged = 1; budget -= sc_bytes; }
     }
     a.ring = (a.staged && use_ring) ? 1 : 0;
     a.c_bufs = ring_slots;
+    a.sub_cols = stageable64 ? 64 : 32;
+    a.out_f32 = out.dtype == DT_F32 ? 1 : 0;
     // weight-stationary variant: when one filter tile covers all filters and its whole [block_n x K] slab fits next
     // to >= 4 activation stages, load it once per CTA and stream only activations (halves the TMA rows per k-block)
     const long long slab = (long long)a.num_kblocks * a.b_stage_bytes;
@@ -1668,13 +1715,16 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     }
     a.stages = stages;
     if (a.staged) {
-        encode_tile_view(&p->maps.c, out, cp.cout_pad, a);
-        if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a);
+        encode_tile_view(&p->maps.c, out, cp.cout_pad, a, a.sub_cols);
+        if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a, a.sub_cols);
     }
     a.acc_stages = 2;
     // deeper accumulator rings were measured (YOLOv3-416 b64) to give no gain on the small-filter layers: they are bound
     // by the TMA row rate, not by the MMA->epilogue hand-off.  Kept switchable for experiments.
-    if (a.n_tiles == 1 && getenv("B200_DEEP_TMEM")) {   // per-tile constants are hoisted, so any number of buffers works
+    if (a.ring && !getenv("B200_NO_DEEP_TMEM")) {        // the ring epilogue takes its constants from global memory: any depth works,
+        int fit = 512 / a.block_n;                       // and short K passes (1x1 layers) need the MMA to run tiles ahead
+        a.acc_stages = fit >= 8 ? 8 : (fit >= 4 ? 4 : 2);
+    } else if (a.n_tiles == 1 && getenv("B200_DEEP_TMEM")) {   // per-tile constants are hoisted, so any number of buffers works
         int fit = 512 / a.block_n;
         a.acc_stages = fit >= 8 ? 8 : (fit >= 4 ? 4 : 2);
     }
