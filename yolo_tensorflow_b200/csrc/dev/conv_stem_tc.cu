@@ -19,8 +19,9 @@
 namespace {
 
 constexpr int kTW = 16, kTH = 8;            // pixel tile (128 GEMM rows)
-constexpr int kSlots = 4;                   // A-tile ring
-constexpr int kAcc = 4;                     // TMEM accumulator ring
+constexpr int kSlots = 8;                   // A-tile ring (TMA-fed kernel)
+constexpr int kAcc = 8;                     // TMEM accumulator ring (TMA-fed kernel)
+constexpr int kSlots1 = 4, kAcc1 = 4;       // the same for the LDG-gather fallback (static shared memory)
 constexpr int kThreads = 13 * 32;
 
 struct StemTcArgs {
@@ -30,6 +31,7 @@ struct StemTcArgs {
     const float *scale, *shift;
     int N, H, W, ldo, act;
     int tiles_x, tiles_y, num_tiles;
+    int pack;                               // TMA kernel: pixels per 128-byte output row (dense outputs), 1 = one pixel per row
 };
 
 struct Walk {                               // tile = first, first + step, ... -> (tx, ty, n) without a division per tile
@@ -61,9 +63,9 @@ template <int NOUT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stem_tc_kernel(const StemTcArgs a)
 {
-    __shared__ __align__(1024) uint8_t sA[kSlots][128 * 64];        // [128 rows][32 K] bf16, 64B-swizzled
+    __shared__ __align__(1024) uint8_t sA[kSlots1][128 * 64];        // [128 rows][32 K] bf16, 64B-swizzled
     __shared__ __align__(1024) uint8_t sB[NOUT * 64];               // [NOUT rows][32 K] bf16, 64B-swizzled
-    __shared__ uint64_t afull[kSlots], aempty[kSlots], tfull[kAcc], tempty[kAcc];
+    __shared__ uint64_t afull[kSlots1], aempty[kSlots1], tfull[kAcc1], tempty[kAcc1];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,13 +78,13 @@ conv_stem_tc_kernel(const StemTcArgs a)
         *reinterpret_cast<bf16 *>(sB + co * 64 + ((((k >> 3) ^ ((co >> 1) & 3))) << 4) + (k & 7) * 2) = v;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
-        for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < kSlots1; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < kAcc1; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the generic-proxy writes of sB -> visible to the tensor core
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kAcc * 32) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kAcc1 * 32) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -97,9 +99,9 @@ conv_stem_tc_kernel(const StemTcArgs a)
         const uint64_t bdesc = make_desc<32>(smem_u32(sB));
         int i = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
-            const int slot = i % kSlots, acc = i % kAcc;
-            STEM_WAIT(&tempty[acc], ((i / kAcc) & 1) ^ 1);
-            STEM_WAIT(&afull[slot], (i / kSlots) & 1);
+            const int slot = i % kSlots1, acc = i % kAcc1;
+            STEM_WAIT(&tempty[acc], ((i / kAcc1) & 1) ^ 1);
+            STEM_WAIT(&afull[slot], (i / kSlots1) & 1);
             tc_fence_after();
             const uint64_t adesc = make_desc<32>(smem_u32(sA[slot]));
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
@@ -118,7 +120,7 @@ conv_stem_tc_kernel(const StemTcArgs a)
         Walk t; t.init(blockIdx.x + g * gridDim.x, 2 * gridDim.x, a.tiles_x, a.tiles_y);
         int i = g;
         for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2, t.next(a.tiles_x, a.tiles_y)) {
-            const int slot = i % kSlots;
+            const int slot = i % kSlots1;
             const int x = t.tx * kTW + px, y = t.ty * kTH + py;
             const bool valid = x < a.W && y < a.H;
             const float *img = a.in + (size_t)t.tn * 3 * plane;
@@ -140,7 +142,7 @@ conv_stem_tc_kernel(const StemTcArgs a)
                 }
             }
             v[27] = 0.f;
-            STEM_WAIT(&aempty[slot], ((i / kSlots) & 1) ^ 1);     // loads are already in flight while we wait for the slot
+            STEM_WAIT(&aempty[slot], ((i / kSlots1) & 1) ^ 1);     // loads are already in flight while we wait for the slot
             const uint32_t row_addr = smem_u32(sA[slot]) + (uint32_t)r * 64u;
             const uint32_t sw = (uint32_t)(r >> 1) & 3u;
 #pragma unroll
@@ -171,8 +173,8 @@ conv_stem_tc_kernel(const StemTcArgs a)
         Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
         int i = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
-            const int acc = i % kAcc;
-            STEM_WAIT(&tfull[acc], (i / kAcc) & 1);
+            const int acc = i % kAcc1;
+            STEM_WAIT(&tfull[acc], (i / kAcc1) & 1);
             tc_fence_after();
             uint32_t d[NOUT];
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32);
@@ -204,7 +206,7 @@ conv_stem_tc_kernel(const StemTcArgs a)
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc * 32) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc1 * 32) : "memory");
     }
 }
 
@@ -222,7 +224,7 @@ constexpr int kPW = 24, kPH = 10, kPX = 4;
 constexpr int kPatchBytes = 3 * kPH * kPW * 4;    // 2880
 constexpr int kPatchPitch = 2944;                 // ring pitch (128-byte aligned TMA destinations)
 constexpr int kPatches = 16;
-constexpr int kOutSlots = 3;
+constexpr int kOutSlots = 4;
 constexpr int kThreads2 = 19 * 32;
 
 struct alignas(64) StemTcMaps { CUtensorMap in, out; };
@@ -309,7 +311,7 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
                 const int cs = i % kOutSlots;
                 STEM_WAIT(&cwritten[cs], (i / kOutSlots) & 1);
-                tma_store_4d(&maps.out, sC[cs], 0, t.tx * kTW, t.ty * kTH, t.tn);
+                tma_store_4d(&maps.out, sC[cs], 0, t.tx * kTW / a.pack, t.ty * kTH, t.tn);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 mbar_arrive(&cempty[cs]);
@@ -361,8 +363,13 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
         const int r = quarter * 32 + lane;
         const bool leaky = a.act == ACT_LEAKY;
         const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
-        // output tile rows are NOUT*2 bytes = the swizzle span: 16-byte chunk j of row r sits at chunk j ^ f(r)
+        // unpacked: output tile rows are NOUT*2 bytes = the swizzle span: 16-byte chunk j of row r sits at chunk j ^ f(r).
+        // packed (dense output, the usual case): `pack` neighbouring pixels share one 128-byte row (TMA moves rows, not
+        // bytes: ~4 cycles a row, so 64 rows per tile instead of 128 is what makes the stem's store side cheap)
         const uint32_t swz = NOUT == 32 ? ((uint32_t)(r >> 1) & 3u) : ((uint32_t)(r >> 2) & 1u);
+        const int px = r % kTW, py = r / kTW;
+        const uint32_t prow = (uint32_t)(py * (kTW / a.pack) + px / a.pack);
+        const uint32_t pchunk0 = (uint32_t)(px % a.pack) * (NOUT / 8);
         int i = g;
         for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2) {
             const int acc = i % kAcc, cs = i % kOutSlots;
@@ -376,7 +383,7 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             STEM_WAIT(&cempty[cs], ((i / kOutSlots) & 1) ^ 1);
-            const uint32_t row_addr = smem_u32(sC[cs]) + (uint32_t)r * ROWB;
+            const uint32_t row_addr = smem_u32(sC[cs]) + (a.pack > 1 ? prow * 128u : (uint32_t)r * ROWB);
 #pragma unroll
             for (int c = 0; c < NOUT; c += 8) {
                 float o[8];
@@ -394,7 +401,7 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
                 }
                 uint4 pk;
                 pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-                sts128(row_addr + (((uint32_t)(c >> 3) ^ swz) << 4), pk);
+                sts128(row_addr + (a.pack > 1 ? (((pchunk0 + (uint32_t)(c >> 3)) ^ (prow & 7u)) << 4) : (((uint32_t)(c >> 3) ^ swz) << 4)), pk);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -411,20 +418,20 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
 }
 
 // tensor maps depend on the buffers only: cache the last few (the chunked H2D path launches the stem per chunk)
-struct MapCacheEntry { const void *in; void *out; int n, h, w, c, ld; StemTcMaps maps; };
+struct MapCacheEntry { const void *in; void *out; int n, h, w, c, ld, pack; StemTcMaps maps; };
 static MapCacheEntry g_maps[16];
 static int g_maps_used = 0, g_maps_next = 0;
 
-static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView out)
+static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView out, int pack)
 {
     for (int i = 0; i < g_maps_used; ++i) {
         const MapCacheEntry &e = g_maps[i];
-        if (e.in == in && e.out == out.p && e.n == n && e.h == h && e.w == w && e.c == out.c && e.ld == out.ld) return &e.maps;
+        if (e.in == in && e.out == out.p && e.n == n && e.h == h && e.w == w && e.c == out.c && e.ld == out.ld && e.pack == pack) return &e.maps;
     }
     MapCacheEntry &e = g_maps[g_maps_next];
     g_maps_next = (g_maps_next + 1) % 16;
     if (g_maps_used < 16) ++g_maps_used;
-    e.in = in; e.out = out.p; e.n = n; e.h = h; e.w = w; e.c = out.c; e.ld = out.ld;
+    e.in = in; e.out = out.p; e.n = n; e.h = h; e.w = w; e.c = out.c; e.ld = out.ld; e.pack = pack;
     {
         unsigned long long dims[4] = {(unsigned long long)w, (unsigned long long)h, 3ull, (unsigned long long)n};
         unsigned long long strides[3] = {(unsigned long long)w * 4, (unsigned long long)h * w * 4, (unsigned long long)3 * h * w * 4};
@@ -432,10 +439,11 @@ static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView o
         tc_encode_tiled(&e.maps.in, 1, 4, (void *)in, dims, strides, box, 0);
     }
     {
-        unsigned long long dims[4] = {(unsigned long long)out.c, (unsigned long long)w, (unsigned long long)h, (unsigned long long)n};
-        unsigned long long strides[3] = {(unsigned long long)out.ld * 2, (unsigned long long)w * out.ld * 2, (unsigned long long)h * w * out.ld * 2};
-        unsigned box[4] = {(unsigned)out.c, kTW, kTH, 1};
-        tc_encode_tiled(&e.maps.out, 0, 4, out.p, dims, strides, box, out.c * 2);
+        // packed: the dense output seen as rows of `pack` pixels (128 bytes)
+        unsigned long long dims[4] = {(unsigned long long)out.c * pack, (unsigned long long)w / pack, (unsigned long long)h, (unsigned long long)n};
+        unsigned long long strides[3] = {(unsigned long long)out.ld * 2 * pack, (unsigned long long)w * out.ld * 2, (unsigned long long)h * w * out.ld * 2};
+        unsigned box[4] = {(unsigned)out.c * pack, (unsigned)(kTW / pack), kTH, 1};
+        tc_encode_tiled(&e.maps.out, 0, 4, out.p, dims, strides, box, out.c * 2 * pack);
     }
     return &e.maps;
 }
@@ -457,9 +465,11 @@ bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView
     const long long tiles = (long long)a.tiles_x * a.tiles_y * n;
     if (tiles > 0x7fffffff) return false;
     a.num_tiles = (int)tiles;
+    a.pack = 1;
     const int grid = a.num_tiles < 148 ? a.num_tiles : 148;
     if (w % 4 == 0 && ((uintptr_t)in_nchw & 15) == 0 && !getenv("B200_STEM_LDG")) {
-        const StemTcMaps *maps = stem_maps(in_nchw, n, h, w, out);
+        a.pack = (out.ld == out.c && w % (64 / out.c) == 0 && !getenv("B200_STEM_NOPACK")) ? 64 / out.c : 1;
+        const StemTcMaps *maps = stem_maps(in_nchw, n, h, w, out, a.pack);
         const size_t smem = 1024 + kSlots * 8192 + kOutSlots * 8192 + kPatches * kPatchPitch + 2048;
         static bool configured = false;
         if (!configured) {

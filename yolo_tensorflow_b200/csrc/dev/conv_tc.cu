@@ -1406,6 +1406,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     a.res_alpha = res_alpha; a.res_beta = res_beta;
     a.npix = (long long)in.n * out.h * out.w;
     a.block_n = cp.cout_pad < 256 ? cp.cout_pad : 256;
+    if (getenv("B200_BLOCK_N") && cp.cout_pad % atoi(getenv("B200_BLOCK_N")) == 0 && atoi(getenv("B200_BLOCK_N")) >= 64) a.block_n = atoi(getenv("B200_BLOCK_N"));
     a.n_tiles = (cp.cout_pad + a.block_n - 1) / a.block_n;
     const size_t esz = 2;
 
