@@ -103,6 +103,14 @@ typedef struct {
  * decode with warp-ballot compaction, class-wise bitmask NMS, and only the kept records cross PCIe.
  * `input` host fp32 NCHW (NULL = use the resident device input).  Returns the number of records written
  * to `out` (at most max_out); counts[b] (may be NULL) receives the per-image candidate count before NMS. */
+/* Device-side preprocessing (the step before the path: letterbox_image + resize_image, image.c:960-979,1347-1390, and for
+ * uint8 sources load_image_stb's HWC/255 conversion, image.c:1442-1464), bit-identical to the host functions.  n <= batch
+ * images of individual sizes become the letterboxed network input in device memory; then call
+ * b200_detect_batch(net, NULL, 0, 0, ...): w = h = 0 corrects each image's boxes with its own original size. */
+int b200_letterbox_batch_u8(network *net, const unsigned char *const *images, const int *widths, const int *heights, int n);  /* RGB, HWC */
+int b200_letterbox_batch(network *net, const image *images, int n);                                                            /* darknet images (fp32 CHW) */
+void b200_fetch_input(network *net, float *dst, int images);      /* the device input buffer as host fp32 NCHW (inspection) */
+
 int b200_detect_batch(network *net, const float *input, int w, int h, float thresh, float nms_thresh,
                       int relative, b200_det *out, int max_out, int *counts);
 

@@ -439,6 +439,59 @@ def test_resize_network_matches_fresh_parse(dn, model, prec, workdir):
     net.close(); fresh.close()
 
 
+def host_letterbox(dn, chw, w, h):
+    """this library's host letterbox_image (plain C restatement of image.c:960-979) on one float32 CHW image"""
+    a = np.ascontiguousarray(chw, dtype=np.float32)
+    im = dn.IMAGE(a.shape[2], a.shape[1], 3, a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    out = dn.letterbox_image(im, w, h)
+    res = np.ctypeslib.as_array(out.data, shape=(3, h, w)).copy()
+    dn.free_image(out)
+    return res
+
+
+def test_device_letterbox_is_bit_identical_to_the_host_path(dn, workdir):
+    """b200_letterbox_batch_u8 / b200_letterbox_batch == load_image_stb's /255 + letterbox_image (image.c:960-979, 1347-1390,
+    1442-1464) for wide, tall, square, tiny and upscaled sources; against the reference library's own letterbox_image too"""
+    net, _, _ = open_net(dn, "yolov3-tiny", 6, 160, workdir, dn.PREC_BF16)
+    rng = np.random.default_rng(7)
+    sizes = [(375, 500), (480, 300), (160, 160), (7, 3), (1, 9), (97, 641)]             # (h, w)
+    u8 = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    as_float = [np.ascontiguousarray((im.astype(np.float64) / 255.).astype(np.float32).transpose(2, 0, 1)) for im in u8]
+    want = np.stack([host_letterbox(dn, f, 160, 160) for f in as_float])
+    assert net.letterbox_batch_u8(u8) == 0
+    assert np.array_equal(net.fetch_input(6), want)
+    assert net.letterbox_batch(as_float) == 0
+    assert np.array_equal(net.fetch_input(6), want)
+    if R.available():
+        ref = R.RefNet(model_files("yolov3-tiny", 1, 160, workdir)[0])
+        class RIMG(ctypes.Structure):
+            _fields_ = [("w", ctypes.c_int), ("h", ctypes.c_int), ("c", ctypes.c_int), ("data", ctypes.POINTER(ctypes.c_float))]
+        ref.lib.letterbox_image.argtypes = [RIMG, ctypes.c_int, ctypes.c_int]; ref.lib.letterbox_image.restype = RIMG
+        for f, got in zip(as_float, want):
+            out = ref.lib.letterbox_image(RIMG(f.shape[2], f.shape[1], 3, f.ctypes.data_as(ctypes.POINTER(ctypes.c_float))), 160, 160)
+            theirs = np.ctypeslib.as_array(out.data, shape=(3, 160, 160))
+            assert np.abs(theirs - got).max() <= 1e-6          # the reference is built -Ofast: allow one rounding of slack
+    net.close()
+
+
+def test_letterboxed_batch_boxes_are_corrected_per_image(dn, workdir):
+    """detect_batch(None, 0, 0): image i's boxes are mapped back with ITS original size, as test_detector does per image
+    (get_network_boxes(net, im.w, im.h, ...), detector.c:599)"""
+    net, _, _ = open_net(dn, "yolov3-tiny", 3, 160, workdir, dn.PREC_BF16)
+    rng = np.random.default_rng(11)
+    sizes = [(375, 500), (480, 300), (200, 200)]
+    u8 = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    assert net.letterbox_batch_u8(u8) == 0
+    rec, counts = net.detect_batch(None, 0, 0, .3, .45)
+    assert len(rec) > 0
+    order = lambda r: r[np.lexsort((r["cls"], r["box_id"], r["image"]))]
+    for i, (h, w) in enumerate(sizes):
+        one, _ = net.detect_batch(None, w, h, .3, .45)                 # whole batch corrected with image i's size
+        a, b = order(rec[rec["image"] == i]), order(one[one["image"] == i])
+        assert len(a) == len(b) and a.tobytes() == b.tobytes()
+    net.close()
+
+
 def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
     net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
     x = synth.make_images(2, 3, 160, 160, 41)

@@ -147,12 +147,13 @@ decode_scan_kernel(const unsigned *__restrict__ flags, int words, int cap, int *
 
 __global__ void __launch_bounds__(256)
 decode_emit_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, int boxes, int words, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, int use_raw, const unsigned *__restrict__ flags,
-                   const int *__restrict__ offsets, CandBuffers cb)
+                   int imw, int imh, const int *__restrict__ im_dims, float thresh, int relative, int mode, int use_raw,
+                   const unsigned *__restrict__ flags, const int *__restrict__ offsets, CandBuffers cb)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= boxes) return;
     const int slot = blockIdx.y, img = first_image + blockIdx.y, lane = threadIdx.x & 31;
+    if (im_dims) { imw = im_dims[2 * img]; imh = im_dims[2 * img + 1]; }      // per-image original sizes (b200_letterbox_batch)
     const unsigned bits = flags[(size_t)slot * words + (t >> 5)];
     if (!((bits >> lane) & 1u)) return;
     const int dst = offsets[(size_t)slot * words + (t >> 5)] + __popc(bits & ((1u << lane) - 1));
@@ -218,7 +219,7 @@ decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_im
 }
 
 void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s)
+                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s, const int *im_dims)
 {
     const int boxes = cb.cap;                                       // cap == anchor boxes per image
     const int words = (boxes + 31) / 32;
@@ -227,7 +228,7 @@ void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int n
     B200_LAUNCHED();
     decode_scan_kernel<<<nimages, 1024, 0, s>>>(cb.flags, words, cb.cap, cb.offsets, cb.count);
     B200_LAUNCHED();
-    decode_emit_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, netw, neth, imw, imh, thresh, relative, mode,
+    decode_emit_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, netw, neth, imw, imh, im_dims, thresh, relative, mode,
                                             use_raw, cb.flags, cb.offsets, cb);
     B200_LAUNCHED();
     decode_probs_kernel<<<dim3(8, nimages), 256, 0, s>>>(heads_dev, nheads, first_image, thresh, mode, use_raw, cb);

@@ -62,6 +62,8 @@ struct b200_engine {
     int cand_slots;
     NmsScratch nms_scratch;
     DetRecord *d_records; int records_cap; int *d_record_count;
+    unsigned char *d_raw; size_t raw_cap;            // b200_letterbox_batch*: source images on the device
+    LetterboxItem *d_lb_items; int *d_im_dims;       // per-image resize geometry / original sizes (box correction)
     // host staging for one image's candidates
     float *h_box, *h_obj, *h_prob; int *h_id; int h_cap;
 };
@@ -416,6 +418,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     memset(&e->cand, 0, sizeof e->cand); e->cand_slots = 0;
     memset(&e->nms_scratch, 0, sizeof e->nms_scratch);
     e->d_records = nullptr; e->records_cap = 0; e->d_record_count = nullptr;
+    e->d_raw = nullptr; e->raw_cap = 0; e->d_lb_items = nullptr; e->d_im_dims = nullptr;
     e->h_box = e->h_obj = e->h_prob = nullptr; e->h_id = nullptr; e->h_cap = 0;
     e->boxes_per_image = 0; e->classes = 0;
     // Parsing a cfg (layer table, shapes) works on a machine without a GPU; anything that computes does not.
@@ -450,6 +453,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
         cudaFree(e->cand.flags); cudaFree(e->cand.offsets); cudaFree(e->cand.cls_count);
         cudaFree(e->nms_scratch.mask); cudaFree(e->d_records); cudaFree(e->d_record_count);
+        cudaFree(e->d_raw); cudaFree(e->d_lb_items); cudaFree(e->d_im_dims);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
         for (auto &ev : e->copy_done) cudaEventDestroy(ev);
         cudaStreamDestroy(e->copy_stream);
@@ -934,7 +938,10 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
         e->records_cap = max_out;
     }
     if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
-    launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, use_raw, e->cand, e->stream);
+    // w == h == 0: every image is corrected with its own original size, recorded by b200_letterbox_batch*
+    const int *im_dims = (w == 0 && h == 0) ? e->d_im_dims : nullptr;
+    if (w == 0 && h == 0 && !im_dims) { fprintf(stderr, "b200-darknet: w = h = 0 needs a preceding b200_letterbox_batch call\n"); abort(); }
+    launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, use_raw, e->cand, e->stream, im_dims);
     launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
                     e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, e->stream);
     B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));
@@ -960,6 +967,76 @@ extern "C" int b200_detect_batch(network *net, const float *input, int w, int h,
     need_device(e, "b200_detect_batch");
     const int first = input ? stage_input(e, net, input) : 0;
     return detect_core(e, net, first, w, h, thresh, nms_thresh, relative, out, max_out, counts);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// device-side preprocessing: n decoded images of individual sizes -> the letterboxed fp32 NCHW network
+// input, written straight into the engine's input buffer.  Follow with b200_detect_batch(net, NULL, 0, 0, ...): w = h = 0
+// corrects every image's boxes with its own size (what test_detector does per image: get_network_boxes(net, im.w, im.h, ..)).
+// ----------------------------------------------------------------------------------------------------
+static int letterbox_batch(network *net, const void *const *images, const int *widths, const int *heights, int n, int u8)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_letterbox_batch");
+    if (n < 1 || n > e->cap || net->c != 3) { fprintf(stderr, "b200-darknet: b200_letterbox_batch: 1..batch 3-channel images\n"); return -1; }
+    const size_t esz = u8 ? 1 : sizeof(float);
+    std::vector<LetterboxItem> items(n);
+    std::vector<int> dims(2 * (size_t)e->cap);
+    for (int i = 0; i < e->cap; ++i) { dims[2 * i] = net->w; dims[2 * i + 1] = net->h; }      // slots without an image: identity
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        const int sw = widths[i], sh = heights[i];
+        if (sw < 1 || sh < 1 || !images[i]) return -1;
+        LetterboxItem &it = items[i];
+        it.src_off = total; it.sw = sw; it.sh = sh;
+        if (((float)net->w / sw) < ((float)net->h / sh)) { it.nw = net->w; it.nh = (sh * net->w) / sw; }      // image.c:964-970
+        else { it.nh = net->h; it.nw = (sw * net->h) / sh; }
+        if (it.nw < 1) it.nw = 1;
+        if (it.nh < 1) it.nh = 1;
+        it.ox = (net->w - it.nw) / 2; it.oy = (net->h - it.nh) / 2;
+        it.w_scale = (float)(sw - 1) / (it.nw - 1);                                                            // image.c:1352-1353
+        it.h_scale = (float)(sh - 1) / (it.nh - 1);
+        total += (((size_t)sw * sh * 3 * esz) + 255) / 256 * 256;
+        dims[2 * i] = sw; dims[2 * i + 1] = sh;
+    }
+    if (total > e->raw_cap) {
+        cudaFree(e->d_raw);
+        e->d_raw = (unsigned char *)dev_alloc(total);
+        e->raw_cap = total;
+    }
+    if (!e->d_lb_items) e->d_lb_items = (LetterboxItem *)dev_alloc((size_t)e->cap * sizeof(LetterboxItem));
+    if (!e->d_im_dims) e->d_im_dims = (int *)dev_alloc(2 * (size_t)e->cap * sizeof(int));
+    for (int i = 0; i < n; ++i)
+        B200_CHECK(cudaMemcpyAsync(e->d_raw + items[i].src_off, images[i], (size_t)widths[i] * heights[i] * 3 * esz, cudaMemcpyHostToDevice, e->stream));
+    B200_CHECK(cudaMemcpyAsync(e->d_lb_items, items.data(), (size_t)n * sizeof(LetterboxItem), cudaMemcpyHostToDevice, e->stream));
+    B200_CHECK(cudaMemcpyAsync(e->d_im_dims, dims.data(), dims.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    launch_letterbox(e->d_raw, u8, e->d_lb_items, n, e->d_input, net->w, net->h, e->stream);
+    B200_CHECK(cudaStreamSynchronize(e->stream));           // items / dims live on this stack frame
+    return 0;
+}
+
+extern "C" int b200_letterbox_batch_u8(network *net, const unsigned char *const *images, const int *widths, const int *heights, int n)
+{
+    return letterbox_batch(net, (const void *const *)images, widths, heights, n, 1);
+}
+
+extern "C" int b200_letterbox_batch(network *net, const image *images, int n)
+{
+    std::vector<const void *> ptr(n > 0 ? n : 0); std::vector<int> w(ptr.size()), h(ptr.size());
+    for (int i = 0; i < n; ++i) {
+        if (images[i].c != 3) { fprintf(stderr, "b200-darknet: b200_letterbox_batch: 3-channel images only\n"); return -1; }
+        ptr[i] = images[i].data; w[i] = images[i].w; h[i] = images[i].h;
+    }
+    return letterbox_batch(net, ptr.data(), w.data(), h.data(), n, 0);
+}
+
+// device copy of the current network input as host fp32 NCHW (inspection / tests)
+extern "C" void b200_fetch_input(network *net, float *dst, int images)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_fetch_input");
+    B200_CHECK(cudaMemcpyAsync(dst, e->d_input, (size_t)images * net->inputs * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
 }
 
 // double-buffered serving loop: submit(k+1) ; detect_submitted(k) ; submit(k+2) ; ...  The H2D of the next batch runs on

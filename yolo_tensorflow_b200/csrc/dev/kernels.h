@@ -38,6 +38,14 @@ struct ConvParams {
 };
 // first-layer kernel: reads the fp32 NCHW network input directly (fuses the layout/precision conversion)
 void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);
+// device-side letterbox_image + resize_image (+ uint8 HWC -> fp32 CHW): image.c:960-979, 1347-1390, 1442-1464
+struct LetterboxItem {
+    size_t src_off;              // byte offset of the image in the raw buffer
+    int sw, sh;                  // source size
+    int nw, nh, ox, oy;          // resized size and its position inside the network input
+    float w_scale, h_scale;      // (sw-1)/(nw-1), (sh-1)/(nh-1) as the reference computes them (float division)
+};
+void launch_letterbox(const unsigned char *raw, int src_is_u8_hwc, const LetterboxItem *items_dev, int n, float *dst_nchw, int w, int h, cudaStream_t s);
 bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);   // false: shape not covered
 void conv_stem_invalidate_bank();      // call after the stem's weights changed in place (load_weights)
 // CUDA-core implicit-GEMM (fp32 accumulate); the fp32-exact path and the fallback for odd shapes
@@ -87,7 +95,7 @@ struct CandBuffers {
 // mode 0 = reference get_network_boxes semantics (yolo: obj>thresh only; region/detection: every box)
 // mode 1 = compact: additionally drops boxes whose objectness is 0 (what do_nms_sort's partition discards)
 void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s);
+                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s, const int *im_dims = nullptr);
 void launch_count_yolo(const HeadDesc *heads_dev, int nheads, int image, float thresh, int *count_dev, cudaStream_t s);
 
 struct NmsScratch { unsigned *mask; size_t words_per_cta; int ctas; };

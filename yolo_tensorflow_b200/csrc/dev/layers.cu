@@ -373,3 +373,60 @@ void launch_stem_im2col(const float *in_nchw, int n, int h, int w, int c, bf16 *
     stem_im2col_kernel<<<grid_for(total), kThreads, 0, s>>>(in_nchw, n, h, w, c, cols, oh, ow, kpad, size, stride, pad);
     B200_LAUNCHED();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Device-side preprocessing: letterbox_image (image.c:960-979) = aspect-preserving resize_image
+// (image.c:1347-1390: horizontal pass into `part`, then vertical pass, scale (src-1)/(dst-1), last row/column copied),
+// 0.5 fill, centred embed; for uint8 sources also load_image_stb's HWC uint8 -> CHW float / 255 (image.c:1442-1464).
+// Every product and sum is rounded separately, in the reference's order, so the result is bit-identical to the C code.
+// HBM-bound: one thread per output pixel, 4 source taps per channel.
+// ---------------------------------------------------------------------------------------------------
+template <bool U8>
+__device__ __forceinline__ float lb_src(const unsigned char *base, int sw, int sh, int x, int y, int k)
+{
+    if (U8) return (float)((double)base[((size_t)y * sw + x) * 3 + k] / 255.);
+    return reinterpret_cast<const float *>(base)[((size_t)k * sh + y) * sw + x];
+}
+template <bool U8>
+__device__ __forceinline__ float lb_part(const unsigned char *base, const LetterboxItem &it, int c, int r, int k)   // horizontal pass
+{
+    if (c == it.nw - 1 || it.sw == 1) return lb_src<U8>(base, it.sw, it.sh, it.sw - 1, r, k);
+    const float sx = __fmul_rn((float)c, it.w_scale);
+    const int ix = (int)sx;
+    const float dx = __fsub_rn(sx, (float)ix);
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.f, dx), lb_src<U8>(base, it.sw, it.sh, ix, r, k)),
+                     __fmul_rn(dx, lb_src<U8>(base, it.sw, it.sh, ix + 1, r, k)));
+}
+template <bool U8>
+__global__ void __launch_bounds__(256)
+letterbox_kernel(const unsigned char *__restrict__ raw, const LetterboxItem *__restrict__ items, float *__restrict__ dst, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= w) return;
+    const LetterboxItem it = items[img];
+    const unsigned char *base = raw + it.src_off;
+    float *out = dst + (size_t)img * 3 * h * w + (size_t)y * w + x;
+    const int c = x - it.ox, r = y - it.oy;
+    if (c < 0 || c >= it.nw || r < 0 || r >= it.nh) {
+        out[0] = .5f; out[(size_t)h * w] = .5f; out[(size_t)2 * h * w] = .5f;
+        return;
+    }
+    const float sy = __fmul_rn((float)r, it.h_scale);
+    const int iy = (int)sy;
+    const float dy = __fsub_rn(sy, (float)iy);
+    const bool last = r == it.nh - 1 || it.sh == 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = __fmul_rn(__fsub_rn(1.f, dy), lb_part<U8>(base, it, c, iy, k));
+        if (!last) v = __fadd_rn(v, __fmul_rn(dy, lb_part<U8>(base, it, c, iy + 1, k)));
+        out[(size_t)k * h * w] = v;
+    }
+}
+
+void launch_letterbox(const unsigned char *raw, int src_is_u8_hwc, const LetterboxItem *items_dev, int n, float *dst_nchw, int w, int h, cudaStream_t s)
+{
+    dim3 grid(div_up(w, 256), h, n);
+    if (src_is_u8_hwc) letterbox_kernel<true><<<grid, 256, 0, s>>>(raw, items_dev, dst_nchw, w, h);
+    else letterbox_kernel<false><<<grid, 256, 0, s>>>(raw, items_dev, dst_nchw, w, h);
+    B200_LAUNCHED();
+}

@@ -88,6 +88,9 @@ lib.b200_layer_kernel.argtypes = [c_void_p, c_int]; lib.b200_layer_kernel.restyp
 lib.b200_launch_count.restype = c_ulonglong
 lib.b200_layer_plan.argtypes = [c_void_p, c_int]; lib.b200_layer_plan.restype = c_char_p
 lib.b200_network_layers.argtypes = [c_void_p]; lib.b200_network_layers.restype = c_int
+lib.b200_letterbox_batch_u8.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int]; lib.b200_letterbox_batch_u8.restype = c_int
+lib.b200_letterbox_batch.argtypes = [c_void_p, POINTER(IMAGE), c_int]; lib.b200_letterbox_batch.restype = c_int
+lib.b200_fetch_input.argtypes = [c_void_p, c_void_p, c_int]; lib.b200_fetch_input.restype = None
 lib.resize_network.argtypes = [c_void_p, c_int, c_int]; lib.resize_network.restype = c_int
 lib.b200_layer_info.argtypes = [c_void_p, c_int, POINTER(c_int)]; lib.b200_layer_info.restype = c_int
 lib.b200_layer_output_host.argtypes = [c_void_p, c_int]; lib.b200_layer_output_host.restype = POINTER(c_float)
@@ -212,6 +215,26 @@ class Network:
         num = c_int(0)
         dets = lib.get_network_boxes_batch(self.ptr, b, w, h, thresh, .5, None, relative, byref(num))
         return dets, num.value
+
+    def letterbox_batch_u8(self, images):
+        """device-side letterbox of decoded RGB images (list of HxWx3 uint8 arrays) into the network input; follow with
+        detect_batch(None, 0, 0, ...) so every image's boxes are corrected with its own size"""
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        n = len(imgs)
+        ptrs = (c_void_p * n)(*[im.ctypes.data for im in imgs])
+        ws = (c_int * n)(*[im.shape[1] for im in imgs]); hs = (c_int * n)(*[im.shape[0] for im in imgs])
+        return lib.b200_letterbox_batch_u8(self.ptr, ptrs, ws, hs, n)
+
+    def letterbox_batch(self, images):
+        """the same for darknet images (list of 3xHxW float32 arrays)"""
+        arrs = [np.ascontiguousarray(im, dtype=np.float32) for im in images]
+        ims = (IMAGE * len(arrs))(*[IMAGE(a.shape[2], a.shape[1], 3, a.ctypes.data_as(POINTER(c_float))) for a in arrs])
+        return lib.b200_letterbox_batch(self.ptr, ims, len(arrs))
+
+    def fetch_input(self, n):
+        out = np.empty((n, 3, self.h, self.w), np.float32)
+        lib.b200_fetch_input(self.ptr, out.ctypes.data_as(c_void_p), n)
+        return out
 
     def detect_batch(self, x, w, h, thresh, nms, relative=1, max_out=1 << 20):
         """fused device path; x host float32 array or None (resident input). Returns (structured array, counts)."""
