@@ -732,11 +732,13 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
             }
         }
     } else if (warp == 1) {
-        // ===================================== MMA issuer (leader CTA only) =====================
-        if (leader && lane == 0) {
+        // ===================================== MMA issuer (leader CTA only; whole warp, elected lane) =====
+        if (leader) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.block_n >> 3) << 17) | ((256u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            const uint64_t adesc0 = make_desc<BLOCK_K>(smem_u32(sA)), bdesc0 = make_desc<BLOCK_K>(smem_u32(sB));
+            const uint32_t a_step = (uint32_t)A_BYTES >> 4, b_step = (uint32_t)args.b_stage_bytes >> 4;
             for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -744,15 +746,15 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                 for (int kb = 0; kb < args.num_kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_desc<BLOCK_K>(smem_u32(sA + (size_t)stage * A_BYTES));
-                    const uint64_t bdesc = make_desc<BLOCK_K>(smem_u32(sB + (size_t)stage * args.b_stage_bytes));
+                    const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)stage * a_step);
+                    const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)stage * b_step);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k)
-                        tc2_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc2_commit_both(&empty[stage]);
+                        tc2_mma_bf16_elect(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc2_commit_both_elect(&empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                tc2_commit_both(&tfull[acc]);
+                tc2_commit_both_elect(&tfull[acc]);
                 if (++acc == args.acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }

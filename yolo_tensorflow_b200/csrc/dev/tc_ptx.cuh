@@ -147,6 +147,27 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)   // arrive on
 }
 
 
+// cta_group::2 flavours of the elected whole-warp issue (see tc_mma_bf16_elect)
+__device__ __forceinline__ void tc2_mma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc2_commit_both_elect(uint64_t *bar)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+        "}" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // ---- programmatic dependent launch -------------------------------------------------------------------------
 // Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while the previous kernel
 // of the stream is still draining: everything before pdl_wait() (barrier init, TMEM allocation, loads of WEIGHTS, which no
