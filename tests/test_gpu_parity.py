@@ -549,6 +549,50 @@ def test_full_size_yolov3_batch64_properties(dn, workdir):
     assert np.array_equal(dn.nms_sort_arrays(bx, pr, .45), pr)
 
 
+@pytest.mark.parametrize("model,size,batch,thresh,nms", [("yolov3", 608, 32, .5, .45), ("yolov2", 416, 64, .5, .45), ("yolov1", 448, 64, .2, .4)])
+def test_full_size_configs_replica_property(dn, model, size, batch, thresh, nms, workdir):
+    """BASELINE configs C3-C5 at full size (608x608 x 32 per GPU, YOLOv2 and YOLOv1 at batch 64): too big for the oracle, so
+    the size-independent property is checked: replicas of an image give identical detections wherever they sit in the batch
+    (different tiles, CTAs and pair halves), and the serving loop reproduces the synchronous call"""
+    net, _, _ = open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
+    base = synth.make_images(4, 3, size, size, 1003)
+    x = np.ascontiguousarray(np.concatenate([base] * (batch // 4)))
+    rec, counts = net.detect_batch(x, size, size, thresh, nms)
+    assert len(rec) > 0
+    assert (counts.reshape(batch // 4, 4) == counts[:4]).all()
+    per = {}
+    for b in range(batch):
+        r = rec[rec["image"] == b]
+        per.setdefault(b % 4, []).append(sorted(zip(r["box_id"].tolist(), r["cls"].tolist(), r["prob"].tolist())))
+    for k, lst in per.items():
+        assert all(v == lst[0] for v in lst), k
+    net.set_head_sync(0)
+    rec2, counts2 = net.detect_batch(x, size, size, thresh, nms)
+    order = lambda r: r[np.lexsort((r["cls"], r["box_id"], r["image"]))]
+    assert np.array_equal(counts, counts2) and order(rec).tobytes() == order(rec2).tobytes()
+    net.close()
+
+
+def test_zero_copy_concat_equals_copying_route(dn, workdir):
+    """route inputs produced in place in the concat buffer (default) == route_layer.c's copies (B200_NO_ZERO_COPY_ROUTE)"""
+    x = synth.make_images(2, 3, 160, 160, 5)
+    outs = []
+    for env in (None, "1"):
+        if env:
+            os.environ["B200_NO_ZERO_COPY_ROUTE"] = env
+        try:
+            net, _, _ = open_net(dn, "yolov3", 2, 160, workdir, dn.PREC_BF16)
+        finally:
+            os.environ.pop("B200_NO_ZERO_COPY_ROUTE", None)
+        names = [net.kernel(i) for i in range(net.n)]
+        assert ("concat_in_place" in names) == (env is None) and ("route_copy" in names) == (env is not None)
+        net.predict(x)
+        outs.append([net.layer_output(i) for i in (86, 98, 106)])
+        net.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_python_wrapper_detect_on_ppm(dn, workdir, tmp_path):
     """python/darknet.py detect(): load_image_color -> network_predict_image (letterbox) -> boxes -> do_nms_obj"""
     net, cfg, wpath = open_net(dn, "yolov3-tiny", 1, 416, workdir, dn.PREC_FP32)
