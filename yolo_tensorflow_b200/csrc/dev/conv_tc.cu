@@ -62,6 +62,7 @@ struct ConvTcArgs {
     int nb, b_koff[12];      // resident weight tiles: K offset of each [block_n x b_k] box
     int nseg, seg_a[12], seg_b[12], seg_k[12];   // K segments: patch byte offset (row shift), weight byte offset, K/16 steps
     int sub_cols, out_f32;   // ring epilogue sub-tile: filters per slot (64 or 32), fp32 output rows
+    const float *scale1, *shift1; int act1, block;   // fused residual block (conv_tc_block_kernel): the 1x1's folded BN, block = 1
     int ring;                // 1: ring epilogue (ring_roles) with 384 threads; c_bufs = ring depth (<= 4)
     int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
     int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
@@ -1165,6 +1166,314 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Fused residual block for the widest feature maps:  out = x + leaky(BN2(conv3x3(leaky(BN1(conv1x1(x))))))   (64 -> 32 -> 64)
+// YOLOv3 layers 2-4 at 208 x 208 are pure HBM traffic: the 1x1 reads x and writes y (32 channels), the 3x3 reads y, reads x
+// again as the residual and writes out.  Here y never leaves the SM: per tile the x halo patch arrives by TMA, a first pair
+// of MMAs (M = 2 x 128 patch pixels, N = 32, K = 64) computes y for the WHOLE patch into TMEM, the "middle" epilogue applies
+// BN1 + leaky, zeroes the pixels outside the image (the 3x3's padding is zero in y, not leaky(BN1(0))) and writes y as the
+// 64-byte-row swizzled patch the patch kernel would have loaded; the 3x3 then runs exactly as in conv_tc_patch_kernel
+// (18 MMAs on row-shifted descriptors), and the last epilogue adds the residual and feeds the output ring.
+// Roles (480 threads): warp 0 TMA producer (x patches, residual tiles, weights), warp 1 MMA issuer (software-pipelined:
+// MMA1 of tile i+1 is issued before MMA2 of tile i), warp 2 store warp, warps 3-10 two middle-epilogue groups, warps 11-14
+// final epilogue.  Traffic per block: x once (+ halo, mostly L2) and out once, instead of 2 x + 2 y + out.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(480, 1)
+conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
+{
+    constexpr int XS_BYTES = 256 * 128, YS_BYTES = 256 * 64, W2_TILE = 64 * 64, W1_BYTES = 32 * 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int XS = args.stages;                                      // x patch stages
+    uint8_t *sX = smem;
+    uint8_t *sY = sX + (size_t)XS * XS_BYTES;                        // 2 y patches
+    uint8_t *sW2 = sY + 2 * YS_BYTES;                                // 9 tap tiles [64 filters x 32 ch], 64B-swizzled
+    uint8_t *sW1 = sW2 + 9 * W2_TILE;                                // [32 filters x 64 ch], 128B-swizzled
+    uint8_t *sC = sW1 + W1_BYTES;                                    // output ring
+    uint8_t *aux = sC + (size_t)args.c_bufs * 16384;
+    uint64_t *xfull = (uint64_t *)aux;        // [4]
+    uint64_t *xempty = xfull + 4;             // [4]
+    uint64_t *a1full = xempty + 4;            // [2]
+    uint64_t *a1empty = a1full + 2;           // [2]
+    uint64_t *yfull = a1empty + 2;            // [2]
+    uint64_t *yempty = yfull + 2;             // [2]
+    uint64_t *a2full = yempty + 2;            // [4]
+    uint64_t *a2empty = a2full + 4;           // [4]
+    uint64_t *cfull = a2empty + 4;            // [4]
+    uint64_t *cempty = cfull + 4;             // [4]
+    uint64_t *cwritten = cempty + 4;          // [4]
+    uint64_t *wfull = cwritten + 4;
+    uint32_t *tmem_slot = (uint32_t *)(wfull + 1);
+    float *s_sc2 = (float *)(aux + 512), *s_sh2 = s_sc2 + 64, *s_sc1 = s_sh2 + 64, *s_sh1 = s_sc1 + 32;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = args.m_tiles, NBUF = args.c_bufs;
+    const int P = args.halo_P, TWv = args.halo_TWv, THv = args.halo_THv;
+    const int PR = (THv + 2) * P;                                    // patch pixels (<= 256)
+    const int nhalf = PR > 128 ? 2 : 1;
+    const int my_first = blockIdx.x, step = gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); mbar_init(&a2full[i], 1); mbar_init(&a2empty[i], 4);
+            mbar_init(&cfull[i], 1); mbar_init(&cempty[i], 1); mbar_init(&cwritten[i], 4);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a1full[i], 1); mbar_init(&a1empty[i], 4); mbar_init(&yfull[i], 4); mbar_init(&yempty[i], 1); }
+        mbar_init(wfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x < 64) { s_sc2[threadIdx.x] = args.scale[threadIdx.x]; s_sh2[threadIdx.x] = args.shift[threadIdx.x]; }
+    if (threadIdx.x < 32) { s_sc1[threadIdx.x] = args.scale1[threadIdx.x]; s_sh1[threadIdx.x] = args.shift1[threadIdx.x]; }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    // TMEM columns: y accumulators [t][half] at t*64 + half*32 (t = 0,1); output accumulators at 128 + v*64 (v = 0..3)
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0 && my_first < num_tiles) {
+            mbar_expect_tx(wfull, (uint32_t)(9 * W2_TILE + W1_BYTES));
+            for (int i = 0; i < 9; ++i) tma_load_2d(&maps.b, sW2 + (size_t)i * W2_TILE, wfull, i * 32, 0);
+            tma_load_2d(&maps.a[1], sW1, wfull, 0, 0);
+            pdl_wait();
+            // x patches run ahead of the residual tiles: the residual of tile j is only needed by its final epilogue, and its
+            // ring slot frees when tile j - NBUF has been STORED, so issuing it together with x(j) would tie the x prefetch
+            // distance to the depth of the whole pipeline (measured: the MMA warp then starves on xfull)
+            constexpr int LAG = 2;
+            int n_my = 0;
+            for (int tile = my_first; tile < num_tiles; tile += step) ++n_my;
+            TileWalk t; t.init(my_first, step, args.tiles_x, args.tiles_y);
+            TileWalk tr; tr.init(my_first, step, args.tiles_x, args.tiles_y);
+            for (int i = 0; i < n_my + LAG; ++i) {
+                if (i < n_my) {
+                    const int xs = i % XS;
+                    MBAR_WAIT_HERE(&xempty[xs], ((i / XS) & 1) ^ 1);
+                    mbar_expect_tx(&xfull[xs], (uint32_t)(PR * 128));
+                    tma_load_4d(&maps.a[0], sX + (size_t)xs * XS_BYTES, &xfull[xs], 0, t.tx * TWv - 1, t.ty * THv - 1, t.tn);
+                    t.next(args.tiles_x, args.tiles_y);
+                }
+                if (i >= LAG) {
+                    // the residual (= the patch interior) is fetched again, into the tile's output-ring slot: an L2 hit.  Copying
+                    // it out of the x stage instead was measured slower (0.37 vs 0.25 ms): the stage then lives until the
+                    // middle epilogue is through and the producer stalls
+                    const int j = i - LAG, cb = j % NBUF;
+                    const int ox0 = tr.tx * TWv, oy0 = tr.ty * THv;
+                    int rows_here = args.OH - oy0; if (rows_here > THv) rows_here = THv;
+                    MBAR_WAIT_HERE(&cempty[cb], ((j / NBUF) & 1) ^ 1);
+                    mbar_expect_tx(&cfull[cb], (uint32_t)(rows_here * TWv * 128));
+                    for (int yy = 0; yy < rows_here; ++yy)
+                        tma_load_4d(&maps.r, sC + (size_t)cb * 16384 + yy * P * 128, &cfull[cb], 0, ox0, oy0 + yy, tr.tn);
+                    tr.next(args.tiles_x, args.tiles_y);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (whole warp, elected lane) ============
+        if (my_first < num_tiles) {
+            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t a_off[9]; uint64_t b2desc[9];
+#pragma unroll
+            for (int sgm = 0; sgm < 9; ++sgm) {
+                a_off[sgm] = (uint32_t)(((sgm / 3) * P + (sgm % 3)) * 64) >> 4;
+                b2desc[sgm] = make_desc<32>(smem_u32(sW2) + (uint32_t)sgm * W2_TILE);
+            }
+            const uint64_t x0desc = make_desc<64>(smem_u32(sX)), y0desc = make_desc<32>(smem_u32(sY)), w1desc = make_desc<64>(smem_u32(sW1));
+            int n_my = 0;
+            for (int tile = my_first; tile < num_tiles; tile += step) ++n_my;
+            MBAR_WAIT_HERE(wfull, 0);
+            for (int it = 0; it <= n_my; ++it) {
+                if (it < n_my) {                           // first GEMM of tile `it`: y = x_patch * W1^T
+                    const int xs = it % XS, t = it & 1;
+                    MBAR_WAIT_HERE(&a1empty[t], ((it >> 1) & 1) ^ 1);
+                    MBAR_WAIT_HERE(&xfull[xs], (it / XS) & 1);
+                    tc_fence_after();
+                    const uint64_t xdesc = x0desc + (uint64_t)((uint32_t)xs * (XS_BYTES >> 4));
+                    for (int half = 0; half < nhalf; ++half) {
+                        const uint32_t d1 = tmem_base + (uint32_t)(t * 64 + half * 32);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16_elect(d1, xdesc + (uint64_t)(half * (128 * 128 >> 4) + 2 * k), w1desc + (uint64_t)(2 * k), idesc1, k != 0 ? 1u : 0u);
+                    }
+                    tc_commit_elect(&xempty[xs]);
+                    tc_commit_elect(&a1full[t]);
+                }
+                if (it >= 1) {                             // second GEMM of tile `it - 1`: the 3x3 over the y patch
+                    const int j = it - 1, u = j & 1, v = j & 3;
+                    MBAR_WAIT_HERE(&a2empty[v], ((j >> 2) & 1) ^ 1);
+                    MBAR_WAIT_HERE(&yfull[u], (j >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t d2 = tmem_base + (uint32_t)(128 + v * 64);
+                    const uint64_t ydesc = y0desc + (uint64_t)((uint32_t)u * (YS_BYTES >> 4));
+#pragma unroll
+                    for (int sgm = 0; sgm < 9; ++sgm) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            tc_mma_bf16_elect(d2, ydesc + (uint64_t)(a_off[sgm] + 2 * k), b2desc[sgm] + (uint64_t)(2 * k), idesc2, (sgm | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit_elect(&yempty[u]);
+                    tc_commit_elect(&a2full[v]);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================== store warp =======================================
+        if (lane == 0) {
+            pdl_wait();
+            TileWalk t; t.init(my_first, step, args.tiles_x, args.tiles_y);
+            int i = 0;
+            for (int tile = my_first; tile < num_tiles; tile += step, ++i, t.next(args.tiles_x, args.tiles_y)) {
+                const int ox0 = t.tx * TWv, oy0 = t.ty * THv, cb = i % NBUF;
+                int rows_here = args.OH - oy0; if (rows_here > THv) rows_here = THv;
+                const uint8_t *src = sC + (size_t)cb * 16384;
+                MBAR_WAIT_HERE(&cwritten[cb], (i / NBUF) & 1);
+                for (int yy = 0; yy < rows_here; ++yy)
+                    tma_store_4d(&maps.c, src + yy * P * 128, 0, ox0, oy0 + yy, t.tn);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                bulk_wait_read<0>();
+                mbar_arrive(&cempty[cb]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp <= 10) {
+        // ===================================== middle epilogue: y accumulators -> y patch =======
+        // two groups of four warps take alternate tiles (group g owns y accumulator / y patch buffer g): this stage sits
+        // between the two GEMMs of a tile, so its latency is the block's critical path
+        const int g1 = (warp - 3) >> 2;
+        const int quarter = warp & 3;
+        const bool leaky1 = args.act1 == ACT_LEAKY;
+        const uint32_t sc1 = smem_u32(s_sc1), sh1 = smem_u32(s_sh1);
+        TileWalk t; t.init(my_first + g1 * step, 2 * step, args.tiles_x, args.tiles_y);
+        int i = g1;
+        for (int tile = my_first + g1 * step; tile < num_tiles; tile += 2 * step, i += 2, t.next(args.tiles_x, args.tiles_y)) {
+            const int tb = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            MBAR_WAIT_HERE(&a1full[tb], ph);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tb * 64);
+            tmem_ld32(taddr, r0);
+            if (nhalf == 2) tmem_ld32(taddr + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a1empty[tb]);
+            MBAR_WAIT_HERE(&yempty[tb], ph ^ 1u);          // the 3x3 that last read this y patch has finished
+            const uint32_t ybase = smem_u32(sY) + (uint32_t)tb * YS_BYTES;
+            const int y0 = t.ty * THv - 1, x0 = t.tx * TWv - 1;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (half < nhalf) {
+                    const uint32_t *r = half ? r1 : r0;
+                    const int pp = half * 128 + quarter * 32 + lane;
+                    if (pp < PR) {
+                        const int pr = pp / P, pc = pp - pr * P;
+                        const bool inside = (unsigned)(y0 + pr) < (unsigned)args.OH && (unsigned)(x0 + pc) < (unsigned)args.OW;
+                        const uint32_t row_addr = ybase + (uint32_t)pp * 64u;
+                        const uint32_t sw = (uint32_t)(pp >> 1) & 3u;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q += 4) {
+                                const uint4 s4 = lds128(sc1 + (uint32_t)(c + q) * 4u), h4 = lds128(sh1 + (uint32_t)(c + q) * 4u);
+                                v[q + 0] = fmaf(__uint_as_float(r[c + q + 0]), __uint_as_float(s4.x), __uint_as_float(h4.x));
+                                v[q + 1] = fmaf(__uint_as_float(r[c + q + 1]), __uint_as_float(s4.y), __uint_as_float(h4.y));
+                                v[q + 2] = fmaf(__uint_as_float(r[c + q + 2]), __uint_as_float(s4.z), __uint_as_float(h4.z));
+                                v[q + 3] = fmaf(__uint_as_float(r[c + q + 3]), __uint_as_float(s4.w), __uint_as_float(h4.w));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (leaky1) v[q] = v[q] > 0.f ? v[q] : 0.1f * v[q];
+                                if (!inside) v[q] = 0.f;
+                            }
+                            uint4 o;
+                            __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                            sts128(row_addr + ((((uint32_t)c >> 3) ^ sw) << 4), o);
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&yfull[tb]);
+        }
+    } else {
+        // ===================================== final epilogue (warps 11..14) =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const bool leaky = args.act == ACT_LEAKY;
+        const float alpha = args.res_alpha, beta = args.res_beta;
+        const uint32_t sc2 = smem_u32(s_sc2), sh2 = smem_u32(s_sh2);
+        const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
+        int i = 0;
+        for (int tile = my_first; tile < num_tiles; tile += step, ++i) {
+            const int v = i & 3, cb = i % NBUF;
+            const uint32_t slot = smem_u32(sC + (size_t)cb * 16384);
+            MBAR_WAIT_HERE(&cfull[cb], (i / NBUF) & 1);
+            MBAR_WAIT_HERE(&a2full[v], (i >> 2) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 + v * 64);
+            uint32_t r[64];
+            tmem_ld32(taddr, r);
+            tmem_ld32(taddr + 32, r + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a2empty[v]);
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+                const uint32_t addr = slot + row_off + ((((uint32_t)j >> 3) ^ row_x) << 4);
+                float vv[8];
+#pragma unroll
+                for (int q = 0; q < 8; q += 4) {
+                    const uint4 s4 = lds128(sc2 + (uint32_t)(j + q) * 4u), h4 = lds128(sh2 + (uint32_t)(j + q) * 4u);
+                    vv[q + 0] = fmaf(__uint_as_float(r[j + q + 0]), __uint_as_float(s4.x), __uint_as_float(h4.x));
+                    vv[q + 1] = fmaf(__uint_as_float(r[j + q + 1]), __uint_as_float(s4.y), __uint_as_float(h4.y));
+                    vv[q + 2] = fmaf(__uint_as_float(r[j + q + 2]), __uint_as_float(s4.z), __uint_as_float(h4.z));
+                    vv[q + 3] = fmaf(__uint_as_float(r[j + q + 3]), __uint_as_float(s4.w), __uint_as_float(h4.w));
+                }
+                if (leaky) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) vv[q] = vv[q] > 0.f ? vv[q] : 0.1f * vv[q];
+                }
+                const uint4 rr = lds128(addr);
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __bfloat1622float2(h[q]);
+                    vv[2 * q] = fmaf(alpha, vv[2 * q], beta * f.x);
+                    vv[2 * q + 1] = fmaf(alpha, vv[2 * q + 1], beta * f.y);
+                }
+                uint4 o;
+                __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(vv[2 * q], vv[2 * q + 1]);
+                sts128(addr, o);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cwritten[cb]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -1330,6 +1639,16 @@ template <int NSUB> static void launch_patch(ConvTcPlan *p, cudaStream_t s)
 
 void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
 {
+    if (p->args.block) {
+        static bool configured = false;
+        if (!configured) {
+            B200_CHECK(cudaFuncSetAttribute(conv_tc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured = true;
+        }
+        launch_pdl(conv_tc_block_kernel, p->grid, 480, p->smem_bytes, s, 1, p->maps, p->args);
+        B200_LAUNCHED();
+        return;
+    }
     if (p->args.mode == 2 && !p->args.pair) {
         if (p->args.block_n == 64) launch_patch<1>(p, s);
         else launch_patch<2>(p, s);
@@ -1376,6 +1695,75 @@ bool conv_tc_shape_supported(int cin, int stride, int act)
     return cin % 16 == 0 && (stride == 1 || stride == 2) && (act == ACT_LEAKY || act == ACT_LINEAR);
 }
 const char *conv_tc_plan_desc(ConvTcPlan *p) { return p->desc.c_str(); }
+
+// Fused residual block x -> 1x1 (64 -> 32) -> 3x3 (32 -> 64) -> + x (conv_tc_block_kernel); nullptr when the shapes do not fit
+ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvParams p2, float res_alpha, float res_beta)
+{
+    if (getenv("B200_NO_BLOCK_FUSION") || getenv("B200_DISABLE_TC")) return nullptr;
+    if (x.dtype != DT_BF16 || out.dtype != DT_BF16 || x.c != 64 || out.c != 64 || x.n != out.n || x.h != out.h || x.w != out.w) return nullptr;
+    if (p1.size != 1 || p1.cout_pad != 32 || p2.size != 3 || p2.stride != 1 || p2.pad != 1 || p2.cout_pad != 64) return nullptr;
+    if ((p1.act != ACT_LEAKY && p1.act != ACT_LINEAR) || (p2.act != ACT_LEAKY && p2.act != ACT_LINEAR)) return nullptr;
+    if (x.ld % 8 != 0 || out.ld % 8 != 0 || ((uintptr_t)x.p & 15) || ((uintptr_t)out.p & 15)) return nullptr;
+    ConvTcPlan *p = new ConvTcPlan();
+    memset(&p->maps, 0, sizeof p->maps);
+    ConvTcArgs &a = p->args;
+    memset(&a, 0, sizeof a);
+    p->block_k = 64; p->out_dtype = DT_BF16;
+    // tile: P = TW + 2 patch columns, TH = 128 / P output rows, (TH + 2) * P <= 256 patch pixels; same measured TMA cost model
+    // as the patch kernel (patch rows + residual rows + store rows, ~38 cycles per TMA instruction)
+    double best = 1e30; int bTW = 0;
+    for (int tw = 4; tw <= out.w && tw + 2 <= 62; ++tw) {
+        int P = tw + 2, th = 128 / P; if (th > out.h) th = out.h;
+        if ((th + 2) * P > 256) continue;
+        double tiles = (double)div_up(out.w, tw) * div_up(out.h, th);
+        double cost = tiles * (4.0 * ((th + 2.0) * P + 2.0 * th * tw) + 38.0 * (1 + 2.0 * th));
+        if (cost < best) { best = cost; bTW = tw; }
+    }
+    if (getenv("B200_BLOCK_TW")) { int f = atoi(getenv("B200_BLOCK_TW")); if (f >= 4 && f <= out.w && f + 2 <= 62 && (128 / (f + 2) + 2) * (f + 2) <= 256) bTW = f; }
+    if (!bTW) { delete p; return nullptr; }
+    const int TWv = bTW, P = TWv + 2;
+    int TH = 128 / P; if (TH > out.h) TH = out.h;
+    a.mode = 2; a.block = 1; a.pair = 0; a.resident_b = 1; a.staged = 1;
+    a.batch = x.n; a.OH = out.h; a.OW = out.w; a.cout_pad = 64; a.ldo = out.ld;
+    a.size = 3; a.stride = 1; a.pad = 1; a.block_n = 64; a.n_tiles = 1;
+    a.halo_P = P; a.halo_TWv = TWv; a.halo_THv = TH; a.TW = TWv; a.TH = TH; a.TN = 1;
+    a.tiles_x = div_up(out.w, TWv); a.tiles_y = div_up(out.h, TH);
+    a.m_tiles = a.tiles_x * a.tiles_y * x.n;
+    a.a_rows = TH * P;
+    a.npix = (long long)x.n * out.h * out.w;
+    a.act = p2.act; a.scale = p2.scale; a.shift = p2.shift;
+    a.act1 = p1.act; a.scale1 = p1.scale; a.shift1 = p1.shift;
+    a.out = out.p; a.res = (const bf16 *)x.p; a.ldr = x.ld; a.res_alpha = res_alpha; a.res_beta = res_beta;
+    a.c_bufs = 3; a.stages = 3;
+    if (getenv("B200_BLOCK_XS")) { int f = atoi(getenv("B200_BLOCK_XS")); if (f >= 2 && f <= 3) a.stages = f; }
+    {
+        unsigned long long dims[4] = {64ull, (unsigned long long)x.w, (unsigned long long)x.h, (unsigned long long)x.n};
+        unsigned long long strides[3] = {(unsigned long long)x.ld * 2, (unsigned long long)x.w * x.ld * 2, (unsigned long long)x.h * x.w * x.ld * 2};
+        unsigned box[4] = {64, (unsigned)P, (unsigned)(TH + 2), 1};
+        tc_encode_tiled(&p->maps.a[0], 0, 4, x.p, dims, strides, box, 128);
+    }
+    {
+        unsigned long long dims[2] = {64ull, 32ull}, strides[1] = {64ull * 2};
+        unsigned box[2] = {64, 32};
+        tc_encode_tiled(&p->maps.a[1], 0, 2, (void *)p1.w, dims, strides, box, 128);
+    }
+    {
+        unsigned long long dims[2] = {288ull, 64ull}, strides[1] = {288ull * 2};
+        unsigned box[2] = {32, 64};
+        tc_encode_tiled(&p->maps.b, 0, 2, (void *)p2.w, dims, strides, box, 64);
+    }
+    encode_tile_view(&p->maps.c, out, 64, a);
+    encode_tile_view(&p->maps.r, x, 64, a);
+    a.tmem_cols = 512;
+    p->grid = a.m_tiles < 148 ? a.m_tiles : 148;
+    p->smem_bytes = (size_t)a.stages * 32768 + 2 * 16384 + 9 * 4096 + 4096 + (size_t)a.c_bufs * 16384 + (512 + 4096) + 1024;
+    p->flops = 2.0 * (double)a.npix * (32.0 * 64 + 64.0 * 288);
+    char buf[256];
+    snprintf(buf, sizeof buf, "conv_tc BLOCK 1x1(64->32)+3x3(32->64)+shortcut tile %dx%d (pitch %d) m_tiles %d x-stages %d ring %d smem %zu grid %d",
+             TWv, TH, P, a.m_tiles, a.stages, a.c_bufs, p->smem_bytes, p->grid);
+    p->desc = buf;
+    return p;
+}
 
 ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual, float res_alpha, float res_beta)
 {

@@ -32,6 +32,7 @@ struct DevLayer {
     bf16 *stem_cols;
     int fused_into;            // conv whose epilogue also performs shortcut layer `fused_into` (its own output is not materialised)
     bool fused_away;           // shortcut executed inside the previous conv's epilogue
+    bool block_head;           // 1x1 conv computed inside the following 3x3's kernel (fused residual block): launches nothing
     std::string kernel;
 };
 
@@ -172,6 +173,18 @@ static void build_engine_device_state(b200_engine *e, network *net)
         if (src == YOLO || src == REGION || src == DETECTION || src == CONNECTED) continue;
         e->L[i].fused_into = i + 1;
         e->L[i + 1].fused_away = true;
+    }
+
+    // ---- fused residual blocks: 1x1 (64 -> 32) -> 3x3 (32 -> 64) -> shortcut from the block input, in ONE kernel ----------
+    for (int i = 1; i + 2 < net->n; ++i) {
+        const layer &c1 = net->layers[i], &c2 = net->layers[i + 1], &sc = net->layers[i + 2];
+        if (c1.type != CONVOLUTIONAL || c2.type != CONVOLUTIONAL || sc.type != SHORTCUT) continue;
+        if (e->L[i + 1].fused_into != i + 2 || sc.index != i - 1 || e->L[i].fused_into >= 0) continue;
+        if (cons[i].size() != 1 || cons[i][0] != i + 1) continue;
+        if (c1.size != 1 || c1.c != 64 || c1.n != 32 || c2.size != 3 || c2.stride != 1 || c2.pad != 1 || c2.n != 64) continue;
+        if ((c1.activation != LEAKY && c1.activation != LINEAR) || (c2.activation != LEAKY && c2.activation != LINEAR)) continue;
+        if (net->layers[i - 1].out_c != 64) continue;
+        e->L[i].block_head = true;
     }
 
     // ---- zero-copy concatenation: a route's inputs are produced straight into channel slices of the route's buffer ----
@@ -335,6 +348,18 @@ static void build_engine_device_state(b200_engine *e, network *net)
             }
             if (!d.stem && e->precision == B200_PREC_BF16) {
                 ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
+                if (d.block_head) { d.kernel = "conv_tc(block)"; break; }          // computed by the next layer's kernel
+                if (d.fused_into >= 0 && i > 0 && e->L[i - 1].block_head) {
+                    const layer &c1 = net->layers[i - 1], &sc = net->layers[d.fused_into];
+                    DevLayer &d1 = e->L[i - 1];
+                    ConvParams p1{c1.size, c1.stride, c1.pad, act_id(c1.activation), d1.w, d1.scale, d1.shift, d1.cout_pad};
+                    d.tc = conv_tc_block_plan_create(e->L[sc.index].out, e->L[d.fused_into].out, p1, p, sc.alpha, sc.beta);
+                    if (d.tc) { d.kernel = "conv_tc+shortcut"; break; }
+                    // shapes the block kernel does not take: the 1x1 runs on its own after all
+                    d1.block_head = false;
+                    d1.tc = conv_tc_plan_create(e->L[i - 2].out, d1.out, p1, nullptr, 1.f, 1.f);
+                    d1.kernel = d1.tc ? "conv_tc" : "conv_simt";
+                }
                 if (d.fused_into >= 0) {
                     const layer &sc = net->layers[d.fused_into];
                     d.tc = conv_tc_plan_create(e->L[i - 1].out, e->L[d.fused_into].out, p, &e->L[sc.index].out, sc.alpha, sc.beta);
@@ -411,7 +436,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; }
     e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->d_input_next = nullptr; e->submitted = 0; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
@@ -570,6 +595,7 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
     switch (l.type) {
     case CONVOLUTIONAL: {
         ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
+        if (d.block_head) break;                                   // computed inside the next layer's fused block kernel
         if (d.stem && d.tc && e->conv_backend == 0) {
             launch_stem_im2col(e->d_input, batch, l.h, l.w, l.c, d.stem_cols, l.out_h, l.out_w, d.stem_kpad, l.size, l.stride, l.pad, s);
             launch_conv_tc(d.tc, s);
@@ -715,7 +741,7 @@ extern "C" void b200_set_conv_backend(network *net, int backend)
 {
     b200_engine *e = b200_engine_of(net);
     for (auto &d : e->L)
-        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0)) {
+        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0 || d.block_head)) {
             fprintf(stderr, "b200-darknet: the CUDA-core conv backend needs an unfused plan (parse with B200_FUSE=0 B200_STEM_SIMT=1)\n");
             abort();
         }
@@ -728,6 +754,11 @@ extern "C" void b200_set_head_sync(network *net, int on) { b200_engine_of(net)->
 // ----------------------------------------------------------------------------------------------------
 static void need_materialised(const b200_engine *e, int i)
 {
+    if (e->L[i].block_head) {
+        fprintf(stderr, "b200-darknet: layer %d's output is not materialised: it is computed inside the fused residual block kernel of layer %d. "
+                        "Parse with B200_FUSE=0 (or b200_set_default_fusion(0)) to inspect it.\n", i, i + 1);
+        abort();
+    }
     if (e->L[i].fused_into >= 0) {
         fprintf(stderr, "b200-darknet: layer %d's output is not materialised: its shortcut (layer %d) is fused into the conv epilogue. "
                         "Parse with B200_FUSE=0 (or b200_set_default_fusion(0)) to inspect it.\n", i, e->L[i].fused_into);

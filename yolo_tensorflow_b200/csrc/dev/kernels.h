@@ -54,6 +54,7 @@ void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
 struct ConvTcPlan;
 ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams p, const TView *residual, float res_alpha, float res_beta);   // nullptr if unsupported
 void conv_tc_plan_destroy(ConvTcPlan *plan);
+ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvParams p2, float res_alpha, float res_beta);   // fused residual block
 bool conv_tc_shape_supported(int cin, int stride, int act);
 void launch_conv_tc(ConvTcPlan *plan, cudaStream_t s);
 const char *conv_tc_plan_desc(ConvTcPlan *plan);
