@@ -1172,20 +1172,26 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
 // of MMAs (M = 2 x 128 patch pixels, N = 32, K = 64) computes y for the WHOLE patch into TMEM, the "middle" epilogue applies
 // BN1 + leaky, zeroes the pixels outside the image (the 3x3's padding is zero in y, not leaky(BN1(0))) and writes y as the
 // 64-byte-row swizzled patch the patch kernel would have loaded; the 3x3 then runs exactly as in conv_tc_patch_kernel
-// (18 MMAs on row-shifted descriptors), and the last epilogue adds the residual and feeds the output ring.
-// Roles (480 threads): warp 0 TMA producer (x patches, residual tiles, weights), warp 1 MMA issuer (software-pipelined:
+// (18 MMAs on row-shifted descriptors), and the last epilogue adds the residual — the interior of the x patch, still in
+// shared memory — and feeds the output ring.  MEASURED: 0.245 ms against 0.127 + 0.165 ms for the two separate kernels.  DRAM
+// traffic is x once + out once (ncu: 354 MB read, 312 MB written), but the SM-side work of both layers now shares one SM's
+// shared-memory bandwidth (~240 KB of operand/staging traffic per 120-pixel tile), which is what bounds it: neither more x
+// stages, L2 prefetch of the patches, a second middle-epilogue group nor dropping the residual's TMA fetch moved it.
+// Roles (480 threads): warp 0 TMA producer (x patches, weights), warp 1 MMA issuer (software-pipelined:
 // MMA1 of tile i+1 is issued before MMA2 of tile i), warp 2 store warp, warps 3-10 two middle-epilogue groups, warps 11-14
 // final epilogue.  Traffic per block: x once (+ halo, mostly L2) and out once, instead of 2 x + 2 y + out.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(480, 1)
 conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 {
-    constexpr int XS_BYTES = 256 * 128, YS_BYTES = 256 * 64, W2_TILE = 64 * 64, W1_BYTES = 32 * 128;
+    constexpr int YS_BYTES = 256 * 64, W2_TILE = 64 * 64, W1_BYTES = 32 * 128;
+    const int XS_BYTES = args.a_stage_bytes;                         // patch pixels * 128, 1024-aligned; the first GEMM reads 256 rows,
+                                                                     // so the ring is followed by padding up to a full 32 KB
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int XS = args.stages;                                      // x patch stages
     uint8_t *sX = smem;
-    uint8_t *sY = sX + (size_t)XS * XS_BYTES;                        // 2 y patches
+    uint8_t *sY = sX + (size_t)(XS - 1) * XS_BYTES + 256 * 128;      // 2 y patches
     uint8_t *sW2 = sY + 2 * YS_BYTES;                                // 9 tap tiles [64 filters x 32 ch], 64B-swizzled
     uint8_t *sW1 = sW2 + 9 * W2_TILE;                                // [32 filters x 64 ch], 128B-swizzled
     uint8_t *sC = sW1 + W1_BYTES;                                    // output ring
@@ -1214,7 +1220,7 @@ conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); mbar_init(&a2full[i], 1); mbar_init(&a2empty[i], 4);
+            mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 4); mbar_init(&a2full[i], 1); mbar_init(&a2empty[i], 4);
             mbar_init(&cfull[i], 1); mbar_init(&cempty[i], 1); mbar_init(&cwritten[i], 4);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&a1full[i], 1); mbar_init(&a1empty[i], 4); mbar_init(&yfull[i], 4); mbar_init(&yempty[i], 1); }
@@ -1242,35 +1248,24 @@ conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
             for (int i = 0; i < 9; ++i) tma_load_2d(&maps.b, sW2 + (size_t)i * W2_TILE, wfull, i * 32, 0);
             tma_load_2d(&maps.a[1], sW1, wfull, 0, 0);
             pdl_wait();
-            // x patches run ahead of the residual tiles: the residual of tile j is only needed by its final epilogue, and its
-            // ring slot frees when tile j - NBUF has been STORED, so issuing it together with x(j) would tie the x prefetch
-            // distance to the depth of the whole pipeline (measured: the MMA warp then starves on xfull)
-            constexpr int LAG = 2;
-            int n_my = 0;
-            for (int tile = my_first; tile < num_tiles; tile += step) ++n_my;
             TileWalk t; t.init(my_first, step, args.tiles_x, args.tiles_y);
-            TileWalk tr; tr.init(my_first, step, args.tiles_x, args.tiles_y);
-            for (int i = 0; i < n_my + LAG; ++i) {
-                if (i < n_my) {
-                    const int xs = i % XS;
-                    MBAR_WAIT_HERE(&xempty[xs], ((i / XS) & 1) ^ 1);
-                    mbar_expect_tx(&xfull[xs], (uint32_t)(PR * 128));
-                    tma_load_4d(&maps.a[0], sX + (size_t)xs * XS_BYTES, &xfull[xs], 0, t.tx * TWv - 1, t.ty * THv - 1, t.tn);
-                    t.next(args.tiles_x, args.tiles_y);
+            // the x stages are 25 KB and live until the final epilogue has read the residual, so only 4 fit: too few to
+            // cover the DRAM latency by themselves.  The patches of the tiles further ahead are pulled into L2 instead.
+            const int ahead = args.b_stages;                       // prefetch distance in tiles (0 = off)
+            TileWalk tp; tp.init(my_first, step, args.tiles_x, args.tiles_y);
+            int pf = 0;
+            for (; pf < ahead && my_first + pf * step < num_tiles; ++pf, tp.next(args.tiles_x, args.tiles_y))
+                tma_prefetch_4d(&maps.a[0], 0, tp.tx * TWv - 1, tp.ty * THv - 1, tp.tn);
+            int i = 0;
+            for (int tile = my_first; tile < num_tiles; tile += step, ++i, t.next(args.tiles_x, args.tiles_y)) {
+                const int xs = i % XS;
+                if (ahead > 0 && my_first + pf * step < num_tiles) {
+                    tma_prefetch_4d(&maps.a[0], 0, tp.tx * TWv - 1, tp.ty * THv - 1, tp.tn);
+                    ++pf; tp.next(args.tiles_x, args.tiles_y);
                 }
-                if (i >= LAG) {
-                    // the residual (= the patch interior) is fetched again, into the tile's output-ring slot: an L2 hit.  Copying
-                    // it out of the x stage instead was measured slower (0.37 vs 0.25 ms): the stage then lives until the
-                    // middle epilogue is through and the producer stalls
-                    const int j = i - LAG, cb = j % NBUF;
-                    const int ox0 = tr.tx * TWv, oy0 = tr.ty * THv;
-                    int rows_here = args.OH - oy0; if (rows_here > THv) rows_here = THv;
-                    MBAR_WAIT_HERE(&cempty[cb], ((j / NBUF) & 1) ^ 1);
-                    mbar_expect_tx(&cfull[cb], (uint32_t)(rows_here * TWv * 128));
-                    for (int yy = 0; yy < rows_here; ++yy)
-                        tma_load_4d(&maps.r, sC + (size_t)cb * 16384 + yy * P * 128, &cfull[cb], 0, ox0, oy0 + yy, tr.tn);
-                    tr.next(args.tiles_x, args.tiles_y);
-                }
+                MBAR_WAIT_HERE(&xempty[xs], ((i / XS) & 1) ^ 1);
+                mbar_expect_tx(&xfull[xs], (uint32_t)(PR * 128));
+                tma_load_4d(&maps.a[0], sX + (size_t)xs * XS_BYTES, &xfull[xs], 0, t.tx * TWv - 1, t.ty * THv - 1, t.tn);
             }
         }
     } else if (warp == 1) {
@@ -1294,15 +1289,14 @@ conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
                     MBAR_WAIT_HERE(&a1empty[t], ((it >> 1) & 1) ^ 1);
                     MBAR_WAIT_HERE(&xfull[xs], (it / XS) & 1);
                     tc_fence_after();
-                    const uint64_t xdesc = x0desc + (uint64_t)((uint32_t)xs * (XS_BYTES >> 4));
+                    const uint64_t xdesc = x0desc + (uint64_t)((uint32_t)xs * ((uint32_t)XS_BYTES >> 4));
                     for (int half = 0; half < nhalf; ++half) {
                         const uint32_t d1 = tmem_base + (uint32_t)(t * 64 + half * 32);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             tc_mma_bf16_elect(d1, xdesc + (uint64_t)(half * (128 * 128 >> 4) + 2 * k), w1desc + (uint64_t)(2 * k), idesc1, k != 0 ? 1u : 0u);
                     }
-                    tc_commit_elect(&xempty[xs]);
-                    tc_commit_elect(&a1full[t]);
+                    tc_commit_elect(&a1full[t]);       // the x stage also holds the residual: the final epilogue releases it
                 }
                 if (it >= 1) {                             // second GEMM of tile `it - 1`: the 3x3 over the y patch
                     const int j = it - 1, u = j & 1, v = j & 3;
@@ -1414,11 +1408,14 @@ conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
         const float alpha = args.res_alpha, beta = args.res_beta;
         const uint32_t sc2 = smem_u32(s_sc2), sh2 = smem_u32(s_sh2);
         const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
+        // the residual of output position (ry, rx) is the patch pixel (ry + 1, rx + 1) of the x stage: no second fetch of x
+        const uint32_t res_row = (uint32_t)((row / P + 1) * P + row % P + 1), res_x = res_row & 7u;
         int i = 0;
         for (int tile = my_first; tile < num_tiles; tile += step, ++i) {
-            const int v = i & 3, cb = i % NBUF;
+            const int v = i & 3, cb = i % NBUF, xs = i % XS;
             const uint32_t slot = smem_u32(sC + (size_t)cb * 16384);
-            MBAR_WAIT_HERE(&cfull[cb], (i / NBUF) & 1);
+            const uint32_t xres = smem_u32(sX) + (uint32_t)xs * (uint32_t)XS_BYTES + res_row * 128u;     // this row's residual pixel
+            MBAR_WAIT_HERE(&cempty[cb], ((i / NBUF) & 1) ^ 1);     // slot free
             MBAR_WAIT_HERE(&a2full[v], (i >> 2) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(128 + v * 64);
@@ -1445,7 +1442,7 @@ conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
 #pragma unroll
                     for (int q = 0; q < 8; ++q) vv[q] = vv[q] > 0.f ? vv[q] : 0.1f * vv[q];
                 }
-                const uint4 rr = lds128(addr);
+                const uint4 rr = lds128(xres + ((((uint32_t)j >> 3) ^ res_x) << 4));
                 const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rr);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1461,7 +1458,7 @@ conv_tc_block_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&cwritten[cb]);
+            if (lane == 0) { mbar_arrive(&cwritten[cb]); mbar_arrive(&xempty[xs]); }
         }
     }
 
@@ -1734,8 +1731,12 @@ ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvPar
     a.act = p2.act; a.scale = p2.scale; a.shift = p2.shift;
     a.act1 = p1.act; a.scale1 = p1.scale; a.shift1 = p1.shift;
     a.out = out.p; a.res = (const bf16 *)x.p; a.ldr = x.ld; a.res_alpha = res_alpha; a.res_beta = res_beta;
-    a.c_bufs = 3; a.stages = 3;
-    if (getenv("B200_BLOCK_XS")) { int f = atoi(getenv("B200_BLOCK_XS")); if (f >= 2 && f <= 3) a.stages = f; }
+    a.c_bufs = 2; a.stages = 4;
+    a.a_stage_bytes = ((TH + 2) * P * 128 + 1023) / 1024 * 1024;
+    if (getenv("B200_BLOCK_XS")) { int f = atoi(getenv("B200_BLOCK_XS")); if (f >= 2 && f <= 4) a.stages = f; }
+    if (getenv("B200_BLOCK_RING")) { int f = atoi(getenv("B200_BLOCK_RING")); if (f >= 2 && f <= 4) a.c_bufs = f; }
+    a.b_stages = 0;                                                   // L2 prefetch distance of the x patches, in tiles (measured: no effect)
+    if (getenv("B200_BLOCK_PREFETCH")) a.b_stages = atoi(getenv("B200_BLOCK_PREFETCH"));
     {
         unsigned long long dims[4] = {64ull, (unsigned long long)x.w, (unsigned long long)x.h, (unsigned long long)x.n};
         unsigned long long strides[3] = {(unsigned long long)x.ld * 2, (unsigned long long)x.w * x.ld * 2, (unsigned long long)x.h * x.w * x.ld * 2};
@@ -1756,7 +1757,8 @@ ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvPar
     encode_tile_view(&p->maps.r, x, 64, a);
     a.tmem_cols = 512;
     p->grid = a.m_tiles < 148 ? a.m_tiles : 148;
-    p->smem_bytes = (size_t)a.stages * 32768 + 2 * 16384 + 9 * 4096 + 4096 + (size_t)a.c_bufs * 16384 + (512 + 4096) + 1024;
+    p->smem_bytes = (size_t)(a.stages - 1) * a.a_stage_bytes + 32768 + 2 * 16384 + 9 * 4096 + 4096 + (size_t)a.c_bufs * 16384 + (512 + 4096) + 1024;
+    if (p->smem_bytes > 227 * 1024) { delete p; return nullptr; }
     p->flops = 2.0 * (double)a.npix * (32.0 * 64 + 64.0 * 288);
     char buf[256];
     snprintf(buf, sizeof buf, "conv_tc BLOCK 1x1(64->32)+3x3(32->64)+shortcut tile %dx%d (pitch %d) m_tiles %d x-stages %d ring %d smem %zu grid %d",

@@ -168,6 +168,13 @@ __device__ __forceinline__ void tc2_commit_both_elect(uint64_t *bar)
         "}" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// pull a tensor box into L2 ahead of the load that will consume it (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // ---- programmatic dependent launch -------------------------------------------------------------------------
 // Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while the previous kernel
 // of the stream is still draining: everything before pdl_wait() (barrier init, TMEM allocation, loads of WEIGHTS, which no
