@@ -264,6 +264,39 @@ def test_conv_tc_shape(dn, shape, tmp_path):
     net.close()
 
 
+@pytest.mark.parametrize("h,w,batch", [(21, 37, 2), (40, 56, 3), (13, 13, 5), (64, 4, 1)])
+def test_fused_residual_block_shapes(dn, h, w, batch, tmp_path):
+    """conv_tc_block_kernel (1x1 64->32 -> 3x3 32->64 -> shortcut in one kernel) on ragged sizes: against the same network
+    with fusion off (every layer its own kernel) and against the oracle"""
+    text = f"[net]\nbatch={batch}\nsubdivisions=1\nheight={h}\nwidth={w}\nchannels=3\nmomentum=0.9\ndecay=0.0005\nlearning_rate=0.001\nmax_batches=1\npolicy=constant\n"
+    text += "[convolutional]\nbatch_normalize=1\nfilters=64\nsize=3\nstride=1\npad=1\nactivation=leaky\n"
+    text += "[convolutional]\nbatch_normalize=1\nfilters=32\nsize=1\nstride=1\npad=1\nactivation=leaky\n"
+    text += "[convolutional]\nbatch_normalize=1\nfilters=64\nsize=3\nstride=1\npad=1\nactivation=leaky\n"
+    text += "[shortcut]\nfrom=-3\nactivation=linear\n"
+    text += "[convolutional]\nbatch_normalize=1\nfilters=32\nsize=1\nstride=1\npad=1\nactivation=leaky\n"
+    cfg = str(tmp_path / "block.cfg"); open(cfg, "w").write(text)
+    wpath = str(tmp_path / "block.weights")
+    synth.write_weights(cfg, wpath, seed=9, damp_heads=False)
+    fd = os.dup(2); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 2)
+    try:
+        fused = dn.Network(cfg, wpath, precision=dn.PREC_BF16, fuse=True)
+        plain = dn.Network(cfg, wpath, precision=dn.PREC_BF16, fuse=False)
+    finally:
+        os.dup2(fd, 2); os.close(fd); os.close(devnull)
+    assert fused.kernel(1) == "conv_tc(block)" and "BLOCK" in dn.lib.b200_layer_plan(fused.ptr, 2).decode()
+    assert plain.kernel(1) == "conv_tc"
+    x = synth.make_images(batch, 3, h, w, 21)
+    fused.predict(x); plain.predict(x)
+    port = P.Net(cfg, wpath)
+    outs = port.forward(x)
+    for i in (3, 4):
+        a, b, r = fused.layer_output(i), plain.layer_output(i), outs[i].reshape(batch, -1)
+        scale = np.abs(r).max()
+        assert np.abs(a - b).max() <= 2e-2 * scale          # two bf16 pipelines: they differ by rounding order only
+        assert np.abs(a - r).max() <= BF16_E2E_TOL * scale
+    fused.close(); plain.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # NMS kernel: bit-exact against the oracle on synthetic boxes, all sizes and edge cases
 # ---------------------------------------------------------------------------------------------------
