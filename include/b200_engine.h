@@ -10,6 +10,7 @@
 #ifndef B200_ENGINE_H
 #define B200_ENGINE_H
 #include "darknet.h"
+#include <stdio.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -103,6 +104,19 @@ typedef struct {
  * decode with warp-ballot compaction, class-wise bitmask NMS, and only the kept records cross PCIe.
  * `input` host fp32 NCHW (NULL = use the resident device input).  Returns the number of records written
  * to `out` (at most max_out); counts[b] (may be NULL) receives the per-image candidate count before NMS. */
+/* Result writers (the step after the path): the formats of examples/detector.c's print_cocos (:165-188),
+ * print_detector_detections (:190-209) and print_imagenet_detections (:211-232), fed from b200_detect_batch records taken
+ * with relative = 0 (pixel coordinates).  widths/heights/ids/paths are indexed by the record's image number. */
+int  b200_coco_image_id(const char *filename);                       /* get_coco_image_id, detector.c:157 */
+void b200_sort_records(b200_det *rec, int n);                         /* by (image, box, class): deterministic files */
+int  b200_write_coco(FILE *fp, const b200_det *rec, int n, const char *const *image_paths, const int *widths, const int *heights);
+int  b200_write_voc(FILE **fps, const b200_det *rec, int n, const char *const *ids, const int *widths, const int *heights);
+int  b200_write_imagenet(FILE *fp, const b200_det *rec, int n, const int *image_ids, const int *widths, const int *heights);
+int  b200_append_coco(const char *path, b200_det *rec, int n, const char *const *image_paths, const int *widths, const int *heights);
+int  b200_append_voc(const char *prefix, const char *const *names, int classes, b200_det *rec, int n, const char *const *ids,
+                     const int *widths, const int *heights);
+int  b200_append_imagenet(const char *path, b200_det *rec, int n, const int *image_ids, const int *widths, const int *heights);
+
 /* Device-side preprocessing (the step before the path: letterbox_image + resize_image, image.c:960-979,1347-1390, and for
  * uint8 sources load_image_stb's HWC/255 conversion, image.c:1442-1464), bit-identical to the host functions.  n <= batch
  * images of individual sizes become the letterboxed network input in device memory; then call

@@ -91,6 +91,10 @@ lib.b200_network_layers.argtypes = [c_void_p]; lib.b200_network_layers.restype =
 lib.b200_letterbox_batch_u8.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int]; lib.b200_letterbox_batch_u8.restype = c_int
 lib.b200_letterbox_batch.argtypes = [c_void_p, POINTER(IMAGE), c_int]; lib.b200_letterbox_batch.restype = c_int
 lib.b200_fetch_input.argtypes = [c_void_p, c_void_p, c_int]; lib.b200_fetch_input.restype = None
+lib.b200_coco_image_id.argtypes = [c_char_p]; lib.b200_coco_image_id.restype = c_int
+lib.b200_append_coco.argtypes = [c_char_p, POINTER(B200_DET), c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_int)]; lib.b200_append_coco.restype = c_int
+lib.b200_append_voc.argtypes = [c_char_p, POINTER(c_char_p), c_int, POINTER(B200_DET), c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_int)]; lib.b200_append_voc.restype = c_int
+lib.b200_append_imagenet.argtypes = [c_char_p, POINTER(B200_DET), c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]; lib.b200_append_imagenet.restype = c_int
 lib.resize_network.argtypes = [c_void_p, c_int, c_int]; lib.resize_network.restype = c_int
 lib.b200_layer_info.argtypes = [c_void_p, c_int, POINTER(c_int)]; lib.b200_layer_info.restype = c_int
 lib.b200_layer_output_host.argtypes = [c_void_p, c_int]; lib.b200_layer_output_host.restype = POINTER(c_float)
