@@ -626,6 +626,27 @@ def test_zero_copy_concat_equals_copying_route(dn, workdir):
         assert np.array_equal(a, b)
 
 
+def test_conv_upsample_fusion_is_exact(dn, workdir):
+    """[convolutional] -> [upsample] with the four copies written by the conv's store warp (default) == the separate upsample
+    kernel (B200_NO_UPSAMPLE_FUSION): identical bits in the upsample layers' buffers and in the heads"""
+    x = synth.make_images(2, 3, 160, 160, 6)
+    outs = []
+    for env in (None, "1"):
+        if env:
+            os.environ["B200_NO_UPSAMPLE_FUSION"] = env
+        try:
+            net, _, _ = open_net(dn, "yolov3", 2, 160, workdir, dn.PREC_BF16)
+        finally:
+            os.environ.pop("B200_NO_UPSAMPLE_FUSION", None)
+        assert (net.kernel(84) == "conv_tc+upsample" and net.kernel(85) == "fused") == (env is None)
+        assert (net.kernel(96) == "conv_tc+upsample" and net.kernel(97) == "fused") == (env is None)
+        net.predict(x)
+        outs.append([net.layer_output(i) for i in (85, 97, 94, 106)])
+        net.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_python_wrapper_detect_on_ppm(dn, workdir, tmp_path):
     """python/darknet.py detect(): load_image_color -> network_predict_image (letterbox) -> boxes -> do_nms_obj"""
     net, cfg, wpath = open_net(dn, "yolov3-tiny", 1, 416, workdir, dn.PREC_FP32)

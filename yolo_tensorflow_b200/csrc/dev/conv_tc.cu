@@ -36,6 +36,7 @@ struct alignas(64) ConvTcMaps {
     CUtensorMap b;           // weights [cout_pad][K]
     CUtensorMap c;           // output tile store (staged epilogue): same pixel-tile geometry as A, 64-channel boxes
     CUtensorMap r;           // residual tile load (fused shortcut), same geometry
+    CUtensorMap cu[3];       // fused 2x upsample: the other three phase views (dy,dx) = (0,1), (1,0), (1,1) of the upsampled tensor
 };
 
 struct ConvTcArgs {
@@ -63,6 +64,7 @@ struct ConvTcArgs {
     int nseg, seg_a[12], seg_b[12], seg_k[12];   // K segments: patch byte offset (row shift), weight byte offset, K/16 steps
     int sub_cols, out_f32;   // ring epilogue sub-tile: filters per slot (64 or 32), fp32 output rows
     const float *scale1, *shift1; int act1, block;   // fused residual block (conv_tc_block_kernel): the 1x1's folded BN, block = 1
+    int upsample;            // 1: the ring's store warp writes every tile to the four phase views of a 2x upsampled tensor
     int ring;                // 1: ring epilogue (ring_roles) with 384 threads; c_bufs = ring depth (<= 4)
     int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
     int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
@@ -413,7 +415,12 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
                     const uint8_t *src = sC + (size_t)slot * 16384;
                     MBAR_WAIT_HERE(&cwritten[slot], (j / NBUF) & 1);
                     if (args.mode == 0) tma_store_2d(&maps.c, src, t.col0 + SUBC * q, t.m_tile * 128);
-                    else if (args.mode == 1) tma_store_4d(&maps.c, src, t.col0 + SUBC * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
+                    else if (args.mode == 1) {
+                        tma_store_4d(&maps.c, src, t.col0 + SUBC * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
+                        if (args.upsample)                 // upsample_layer.c:72-96 (nearest, stride 2) fused: same tile, three more phases
+                            for (int ph = 0; ph < 3; ++ph)
+                                tma_store_4d(&maps.cu[ph], src, t.col0 + SUBC * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
+                    }
                     else
                         for (int yy = 0; yy < t.rows_here; ++yy)
                             tma_store_4d(&maps.c, src + yy * args.halo_P * row_bytes, t.col0 + SUBC * q, t.tx * args.halo_TWv, t.ty * args.halo_THv + yy, t.tn);
@@ -1767,8 +1774,10 @@ ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvPar
     return p;
 }
 
-ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual, float res_alpha, float res_beta)
+ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual, float res_alpha, float res_beta, const TView *up_out)
 {
+    if (up_out && (residual || up_out->dtype != DT_BF16 || up_out->h != 2 * out.h || up_out->w != 2 * out.w || up_out->c != out.c ||
+                   up_out->ld % 8 != 0 || ((uintptr_t)up_out->p & 15))) return nullptr;
     if (in.dtype != DT_BF16) return nullptr;
     if (residual && (residual->dtype != DT_BF16 || out.dtype != DT_BF16 || residual->ld % 8 != 0 || ((uintptr_t)residual->p & 15) ||
                      residual->c != out.c || residual->h != out.h || residual->w != out.w)) return nullptr;
@@ -1803,7 +1812,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     const size_t esz = 2;
 
     // ---- A views ----
-    if (cp.size == 1 && cp.stride == 1 && cp.pad == 0) {
+    if (cp.size == 1 && cp.stride == 1 && cp.pad == 0 && !up_out) {         // (a fused upsample needs spatial tiles)
         a.mode = 0;
         a.a_rows = 128;
         a.m_tiles = (int)((a.npix + 127) / 128);
@@ -2111,6 +2120,21 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         encode_tile_view(&p->maps.c, out, cp.cout_pad, a, a.sub_cols);
         if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a, a.sub_cols);
     }
+    if (up_out) {
+        // the conv's own output is not written: phase (dy, dx) of the upsampled tensor is a strided view with the conv
+        // output's geometry, so the same tile coordinates address all four copies
+        if (!a.ring || a.mode != 1 || a.sub_cols != 64) { delete p; return nullptr; }
+        a.upsample = 1;
+        for (int ph = 0; ph < 4; ++ph) {
+            const int dy = ph >> 1, dx = ph & 1;
+            const unsigned long long esz = 2, ld = (unsigned long long)up_out->ld, W2 = (unsigned long long)up_out->w, H2 = (unsigned long long)up_out->h;
+            unsigned long long dims[4] = {(unsigned long long)cp.cout_pad, (unsigned long long)out.w, (unsigned long long)out.h, (unsigned long long)out.n};
+            unsigned long long strides[3] = {2 * ld * esz, 2 * W2 * ld * esz, H2 * W2 * ld * esz};
+            unsigned box[4] = {64, (unsigned)a.TW, (unsigned)a.TH, (unsigned)a.TN};
+            void *base = (unsigned char *)up_out->p + ((size_t)dy * W2 + dx) * ld * esz;
+            tc_encode_tiled(ph == 0 ? (void *)&p->maps.c : (void *)&p->maps.cu[ph - 1], 0, 4, base, dims, strides, box, 128);
+        }
+    }
     a.acc_stages = 2;
     // deeper accumulator rings were measured (YOLOv3-416 b64) to give no gain on the small-filter layers: they are bound
     // by the TMA row rate, not by the MMA->epilogue hand-off.  Kept switchable for experiments.
@@ -2138,5 +2162,6 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     p->desc = buf;
     if (a.ring) p->desc += " ringEpilogue(" + std::to_string(a.c_bufs) + ")";
     else if (a.staged) p->desc += " stagedEpilogue";
+    if (a.upsample) p->desc += " +upsample2x";
     return p;
 }

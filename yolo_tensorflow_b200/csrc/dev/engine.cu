@@ -32,6 +32,8 @@ struct DevLayer {
     bf16 *stem_cols;
     int fused_into;            // conv whose epilogue also performs shortcut layer `fused_into` (its own output is not materialised)
     bool fused_away;           // shortcut executed inside the previous conv's epilogue
+    bool up_fused;             // conv that writes its result 2x upsampled straight into the following [upsample]'s buffer
+    bool up_away;              // [upsample] performed by the previous conv's store warp
     bool block_head;           // 1x1 conv computed inside the following 3x3's kernel (fused residual block): launches nothing
     std::string kernel;
 };
@@ -185,6 +187,17 @@ static void build_engine_device_state(b200_engine *e, network *net)
         if ((c1.activation != LEAKY && c1.activation != LINEAR) || (c2.activation != LEAKY && c2.activation != LINEAR)) continue;
         if (net->layers[i - 1].out_c != 64) continue;
         e->L[i].block_head = true;
+    }
+
+    // ---- conv -> [upsample] (stride 2, scale 1): the conv's store warp writes the four copies itself -----------------------
+    for (int i = 1; i + 1 < net->n && e->fusion && e->precision == B200_PREC_BF16 && !getenv("B200_NO_UPSAMPLE_FUSION"); ++i) {
+        const layer &c = net->layers[i], &u = net->layers[i + 1];
+        if (c.type != CONVOLUTIONAL || u.type != UPSAMPLE || u.stride != 2 || u.reverse || u.scale != 1.f) continue;
+        if (cons[i].size() != 1 || cons[i][0] != i + 1 || e->L[i].fused_into >= 0 || e->L[i].block_head) continue;
+        if (c.out_c % 64 != 0 || (c.activation != LEAKY && c.activation != LINEAR)) continue;
+        if (!conv_tc_shape_supported(c.c, c.stride, act_id(c.activation))) continue;
+        e->L[i].up_fused = true;
+        e->L[i + 1].up_away = true;
     }
 
     // ---- zero-copy concatenation: a route's inputs are produced straight into channel slices of the route's buffer ----
@@ -366,6 +379,11 @@ static void build_engine_device_state(b200_engine *e, network *net)
                     if (!d.tc) { fprintf(stderr, "b200-darknet: internal error: fused conv %d has no tcgen05 plan\n", i); abort(); }
                     d.kernel = "conv_tc+shortcut";
                 } else {
+                    if (d.up_fused) {
+                        d.tc = conv_tc_plan_create(e->L[i - 1].out, d.out, p, nullptr, 1.f, 1.f, &e->L[i + 1].out);
+                        if (d.tc) { d.kernel = "conv_tc+upsample"; break; }
+                        d.up_fused = false; e->L[i + 1].up_away = false;           // shape not covered: the two layers run separately
+                    }
                     d.tc = conv_tc_plan_create(e->L[i - 1].out, d.out, p, nullptr, 1.f, 1.f);
                     if (d.tc) d.kernel = "conv_tc";
                 }
@@ -373,7 +391,7 @@ static void build_engine_device_state(b200_engine *e, network *net)
             break;
         }
         case MAXPOOL: d.kernel = "maxpool"; break;
-        case UPSAMPLE: d.kernel = "upsample"; break;
+        case UPSAMPLE: d.kernel = d.up_away ? "fused" : "upsample"; break;
         case SHORTCUT: d.kernel = d.fused_away ? "fused" : "shortcut"; break;
         case REORG: d.kernel = "reorg"; break;
         case ROUTE: {
@@ -436,7 +454,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; }
     e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->d_input_next = nullptr; e->submitted = 0; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
@@ -605,7 +623,9 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
         break;
     }
     case MAXPOOL: launch_maxpool(in, out, l.size, l.stride, l.pad, s); break;
-    case UPSAMPLE: launch_upsample(in, out, l.stride, l.scale, s); break;
+    case UPSAMPLE:
+        if (!d.up_away || e->conv_backend != 0) launch_upsample(in, out, l.stride, l.scale, s);
+        break;
     case SHORTCUT:
         if (!d.fused_away || e->conv_backend != 0) launch_shortcut(in, view_of(e->L[l.index], batch), out, l.alpha, l.beta, act_id(l.activation), s);
         break;
@@ -741,7 +761,7 @@ extern "C" void b200_set_conv_backend(network *net, int backend)
 {
     b200_engine *e = b200_engine_of(net);
     for (auto &d : e->L)
-        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0 || d.block_head)) {
+        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0 || d.block_head || d.up_fused)) {
             fprintf(stderr, "b200-darknet: the CUDA-core conv backend needs an unfused plan (parse with B200_FUSE=0 B200_STEM_SIMT=1)\n");
             abort();
         }
@@ -756,6 +776,11 @@ static void need_materialised(const b200_engine *e, int i)
 {
     if (e->L[i].block_head) {
         fprintf(stderr, "b200-darknet: layer %d's output is not materialised: it is computed inside the fused residual block kernel of layer %d. "
+                        "Parse with B200_FUSE=0 (or b200_set_default_fusion(0)) to inspect it.\n", i, i + 1);
+        abort();
+    }
+    if (e->L[i].up_fused) {
+        fprintf(stderr, "b200-darknet: layer %d's output is not materialised: it is written upsampled into layer %d's buffer. "
                         "Parse with B200_FUSE=0 (or b200_set_default_fusion(0)) to inspect it.\n", i, i + 1);
         abort();
     }

@@ -52,7 +52,9 @@ void conv_stem_invalidate_bank();      // call after the stem's weights changed 
 void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
 // tcgen05/TMEM/TMA implicit-GEMM (bf16 in, fp32 accumulate).  Plans live in conv_tc.cu.
 struct ConvTcPlan;
-ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams p, const TView *residual, float res_alpha, float res_beta);   // nullptr if unsupported
+// nullptr if unsupported.  up_out: the convolution's result is written 2x nearest-upsampled into this view instead of `out`
+ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams p, const TView *residual, float res_alpha, float res_beta,
+                                const TView *up_out = nullptr);
 void conv_tc_plan_destroy(ConvTcPlan *plan);
 ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvParams p2, float res_alpha, float res_beta);   // fused residual block
 bool conv_tc_shape_supported(int cin, int stride, int act);
