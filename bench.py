@@ -51,19 +51,38 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.t0 = self.t1 = None                      # samples are kept between window_start() and window_end()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        # one streaming nvidia-smi (a line every 20 ms): the timed region is only ~0.1 s long, so polling a fresh process per
+        # sample would see it once
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        try:
+            for line in proc.stdout:
+                line = line.strip()
+                if line and self.t0 is not None and (self.t1 is None or time.time() <= self.t1 + 0.02):
+                    self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        finally:
+            proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                proc.wait(timeout=2)
             except Exception:
-                pass
-            time.sleep(0.1)
+                proc.kill()
+
+    def window_start(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
+        self.stop_flag = True
 
     def summary(self):
         if not self.rows:
@@ -236,16 +255,18 @@ def main_engine(args):
             ms = float(t.item())
         return ms, n
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.start()                               # nvidia-smi needs a moment to come up: start it before the warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    if sampler:
+        sampler.window_start()
     launches0 = dn.lib.b200_launch_count()
     ms, nrec = timed(step_resident, args.steps)
     launches = dn.lib.b200_launch_count() - launches0
     if sampler:
-        sampler.stop_flag = True
+        sampler.window_end()
     cand = float(np.mean(list(counts)))
     value = world * BATCH * args.steps / (ms / 1000.0)
 
