@@ -13,12 +13,20 @@
 //     the tensor.  1x1 layers use a dense 2-D [pixels][C] view, 3x3 layers a 4-D (C,W,H,N) view with a
 //     rectangular (TW x TH x TN) pixel tile chosen per layer to fill the 128 rows.
 //   * B operand: weights repacked [C_out][ky][kx][C_in] (K-major), 2-D TMA box [BLOCK_N x BLOCK_K].
-//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one elected thread, accumulators in TMEM,
-//     double-buffered (2 x BLOCK_N columns) so the epilogue of tile t overlaps the mainloop of tile t+1.
-//   * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
-//     (tcgen05.ld -> scale/shift/leaky -> bf16 or fp32 -> 16-byte global stores, NHWC with row pitch ldo so a
-//     layer can write into a channel slice of a concat buffer).
+//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one elected lane of a convergent warp, accumulators in TMEM,
+//     multi-buffered so the epilogue of tile t overlaps the mainloops of the following tiles.
 //   * Persistent: grid = min(tiles, #SM); tiles are walked filter-tile-fastest so co-running CTAs share A in L2.
+//   * Launched with programmatic stream serialization: prologue and weight loads overlap the previous layer's tail.
+//
+// Kernels in this file (one plan per layer, chosen by conv_tc_plan_create / conv_tc_block_plan_create):
+//   conv_tc_kernel        1 CTA per tile, weights streamed or resident (small layers, all 1x1 layers with <= 128 filters)
+//   conv_tc_pair_kernel   cta_group::2 CTA pair per 256-pixel tile, half of the weight tile per CTA (compute-heavy layers)
+//   conv_tc_halo_pair_kernel  opt-in experiment (B200_HALO): patch loads + row-shifted descriptors for the pair kernel
+//   conv_tc_patch_kernel  3x3 layers with 32/64 input channels: halo patch per tile, ALL weights resident, HBM-bound
+//   conv_tc_block_kernel  fused residual block 1x1 (64->32) + 3x3 (32->64) + shortcut: the intermediate never leaves the SM
+// Epilogues: ring_roles (store warp + residual loader + two epilogue groups over a ring of swizzled 64-filter sub-tile
+// slots, TMA stores; also writes a fused 2x upsample) for everything that can be staged, run_epilogue (serial, direct
+// 16-byte stores) for odd filter counts.
 //
 // Roofline: tensor pipe.  FLOPs per launch = 2 * pixels * C_out * K (darknet's own BFLOPs formula,
 // convolutional_layer.c:325).
