@@ -8,7 +8,7 @@
 // leaves the SM), ONE pair of tcgen05.mma (M = 128, N = C_out, K = 2 x 16) per tile does the arithmetic, and the epilogue
 // applies folded batch-norm + leaky and writes NHWC bf16.
 //
-// Warp roles (416 threads, persistent over 16 x 8 pixel tiles): warp 0 = MMA issuer + TMEM owner, warps 1-8 = two
+// Warp roles (416 threads, persistent over 32 x 4 pixel tiles): warp 0 = MMA issuer + TMEM owner, warps 1-8 = two
 // gather groups taking alternate tiles (hides the global-load latency of the window gather), warps 9-12 = epilogue.
 // Everything is handed over through mbarriers: gather -> afull -> MMA -> (aempty, tfull) -> epilogue -> tempty.
 //
@@ -18,7 +18,8 @@
 
 namespace {
 
-constexpr int kTW = 16, kTH = 8;            // pixel tile (128 GEMM rows)
+constexpr int kTW = 32, kTH = 4;            // pixel tile (128 GEMM rows); a warp = 32 consecutive pixels of one row: the window gather
+                                            // reads consecutive shared-memory words (16 x 8 tiles gave 2-way bank conflicts)
 constexpr int kSlots = 8;                   // A-tile ring (TMA-fed kernel)
 constexpr int kAcc = 8;                     // TMEM accumulator ring (TMA-fed kernel)
 constexpr int kSlots1 = 4, kAcc1 = 4;       // the same for the LDG-gather fallback (static shared memory)
@@ -213,14 +214,14 @@ conv_stem_tc_kernel(const StemTcArgs a)
 
 // ---------------------------------------------------------------------------------------------------
 // TMA-fed variant (image width a multiple of 4): the tile's fp32 window source arrives as ONE 4-D TMA box
-// [3 channels][10 rows][24 columns] (out-of-bounds = zero = the convolution's padding, so the gather needs no predicates
+// [3 channels][6 rows][40 columns] (out-of-bounds = zero = the convolution's padding, so the gather needs no predicates
 // and reads shared memory instead of global), and the output tile leaves as ONE TMA store from a swizzled staging tile.
 // Warp roles (608 threads): 0 = MMA, 1 = TMA loads, 2 = TMA stores, 3-10 = two gather groups, 11-18 = two epilogue groups
 // (gather and epilogue groups take alternate tiles: one warp per scheduler cannot issue a tile's epilogue fast enough).
 // ---------------------------------------------------------------------------------------------------
-// patch box: rows y0-1 .. y0+8, columns x0-4 .. x0+19.  An un-swizzled TMA box must START on a 16-byte boundary in
+// patch box: rows y0-1 .. y0+4, columns x0-4 .. x0+35.  An un-swizzled TMA box must START on a 16-byte boundary in
 // dimension 0 (scripts/tma_f32_probe.cu: x0-1 raises an illegal-instruction error), hence the 4-column left margin.
-constexpr int kPW = 24, kPH = 10, kPX = 4;
+constexpr int kPW = 40, kPH = 6, kPX = 4;
 constexpr int kPatchBytes = 3 * kPH * kPW * 4;    // 2880
 constexpr int kPatchPitch = 2944;                 // ring pitch (128-byte aligned TMA destinations)
 constexpr int kPatches = 16;
