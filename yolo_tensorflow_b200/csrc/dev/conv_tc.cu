@@ -44,6 +44,7 @@ struct alignas(64) ConvTcMaps {
     CUtensorMap b;           // weights [cout_pad][K]
     CUtensorMap c;           // output tile store (staged epilogue): same pixel-tile geometry as A, 64-channel boxes
     CUtensorMap r;           // residual tile load (fused shortcut), same geometry
+    CUtensorMap b2;          // tail-split tiles (CTA-pair kernel): weight boxes of block_n / split filters
     CUtensorMap cu[3];       // fused 2x upsample: the other three phase views (dy,dx) = (0,1), (1,0), (1,1) of the upsampled tensor
 };
 
@@ -73,6 +74,9 @@ struct ConvTcArgs {
     int sub_cols, out_f32;   // ring epilogue sub-tile: filters per slot (64 or 32), fp32 output rows
     const float *scale1, *shift1; int act1, block;   // fused residual block (conv_tc_block_kernel): the 1x1's folded BN, block = 1
     int upsample;            // 1: the ring's store warp writes every tile to the four phase views of a 2x upsampled tensor
+    // tail splitting (CTA-pair kernel, ring epilogue): the tiles of the last, partly filled wave are cut into `split` filter
+    // slices so that every pair works during it.  Virtual tile v < split_from is tile v at full width; the others are slices.
+    int split_from, split, vtiles;
     int ring;                // 1: ring epilogue (ring_roles) with 384 threads; c_bufs = ring depth (<= 4)
     int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
     int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
@@ -324,17 +328,32 @@ template <int PENDING> __device__ __forceinline__ void bulk_wait_read()
 // Nothing in a tile's epilogue waits on a DRAM round trip or on another role's bookkeeping; the roles only meet at
 // mbarriers.  With the serial epilogue (run_epilogue) a fused shortcut cost the 52x52 layers 18 % (990 vs 1200 TFLOP/s).
 // ---------------------------------------------------------------------------------------------------
+struct VTile { int tile, col_off, width; };
+__device__ __forceinline__ VTile vtile_of(const ConvTcArgs &a, int v)
+{
+    VTile t;
+    if (v < a.split_from) { t.tile = v; t.col_off = 0; t.width = a.block_n; return t; }
+    const int w = v - a.split_from;
+    t.width = a.block_n / a.split;
+    t.tile = a.split_from + w / a.split;
+    t.col_off = (w % a.split) * t.width;
+    return t;
+}
+
 struct RingTile {
-    int n_tile, m_tile, col0, tx, ty, tn, rows_here;
+    int n_tile, m_tile, col0, tx, ty, tn, rows_here, nsub;
     bool real;
 };
 template <bool PAIR>
-__device__ __forceinline__ RingTile ring_tile(const ConvTcArgs &args, int tile, int rank)
+__device__ __forceinline__ RingTile ring_tile(const ConvTcArgs &args, int vt, int rank)
 {
     RingTile t;
+    const VTile v = vtile_of(args, vt);
+    const int tile = v.tile;
     t.n_tile = tile % args.n_tiles;
     t.m_tile = PAIR ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
-    t.col0 = t.n_tile * args.block_n;
+    t.col0 = t.n_tile * args.block_n + v.col_off;
+    t.nsub = v.width / args.sub_cols;
     t.tx = t.ty = t.tn = 0; t.rows_here = 0;
     t.real = t.m_tile < args.m_tiles;                       // an odd tile count leaves the pair's second CTA a phantom tile
     if (args.mode >= 1) { t.tx = t.m_tile % args.tiles_x; t.ty = (t.m_tile / args.tiles_x) % args.tiles_y; t.tn = t.m_tile / (args.tiles_x * args.tiles_y); }
@@ -407,7 +426,7 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
     uint64_t *cfull = ring_bars, *cempty = ring_bars + 4, *cwritten = ring_bars + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int SUBC = args.sub_cols;                        // filters per sub-tile: 64 (bf16) or 32 (bf16 / fp32 outputs)
-    const int NSUB = args.block_n / SUBC, NBUF = args.c_bufs;
+    const int NBUF = args.c_bufs;
     const int row_bytes = SUBC * (args.out_f32 ? 4 : 2);   // 128 or 64: also the swizzle span of the slot
     const bool has_res = args.res != nullptr;
     if (warp == 2) {
@@ -418,7 +437,7 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 const RingTile t = ring_tile<PAIR>(args, tile, rank);
                 if (!t.real) continue;
-                for (int q = 0; q < NSUB; ++q, ++j) {
+                for (int q = 0; q < t.nsub; ++q, ++j) {
                     const int slot = j % NBUF;
                     const uint8_t *src = sC + (size_t)slot * 16384;
                     MBAR_WAIT_HERE(&cwritten[slot], (j / NBUF) & 1);
@@ -447,7 +466,7 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 const RingTile t = ring_tile<PAIR>(args, tile, rank);
                 if (!t.real) continue;
-                for (int q = 0; q < NSUB; ++q, ++j) {
+                for (int q = 0; q < t.nsub; ++q, ++j) {
                     const int slot = j % NBUF;
                     uint8_t *dst = sC + (size_t)slot * 16384;
                     MBAR_WAIT_HERE(&cempty[slot], ((j / NBUF) & 1) ^ 1);
@@ -478,6 +497,7 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
             MBAR_WAIT_HERE(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * args.block_n);
+            const int NSUB = t.nsub;
             if (!t.real || h >= NSUB) {                    // nothing to emit: just hand the accumulator back
                 tc_fence_before();
                 __syncwarp();
@@ -687,7 +707,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
     const bool leader = rank == 0;
     const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int m_pairs = (args.m_tiles + 1) / 2;
-    const int num_tiles = m_pairs * args.n_tiles;                   // pair tiles
+    const int num_tiles = RING ? args.vtiles : m_pairs * args.n_tiles;   // (virtual) pair tiles: the last wave may be filter-sliced
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -714,9 +734,13 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
         // ===================================== TMA producer (both CTAs) =========================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx_bytes = 2u * (uint32_t)(args.a_rows * BLOCK_K * 2 + half_n * BLOCK_K * 2);
             pdl_wait();
-            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            for (int vt = pair_id; vt < num_tiles; vt += num_pairs) {
+                VTile v; v.tile = vt; v.col_off = 0; v.width = args.block_n;
+                if (RING) v = vtile_of(args, vt);
+                const int tile = v.tile, half_w = v.width / 2;
+                const uint32_t tx_bytes = 2u * (uint32_t)(args.a_rows * BLOCK_K * 2 + half_w * BLOCK_K * 2);
+                const CUtensorMap *bmap = v.width == args.block_n ? &maps.b : &maps.b2;
                 const int n_tile = tile % args.n_tiles, m_tile = 2 * (tile / args.n_tiles) + (int)rank;
                 int ox0 = 0, oy0 = 0, n0 = 0;
                 if (args.mode == 1) {
@@ -741,8 +765,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                             tma2_load_4d(&maps.a[py * 2 + px], dstA, &full[stage], cb * BLOCK_K, ox0 + xoff, oy0 + yoff, n0);
                         }
                     }
-                    tma2_load_2d(&maps.b, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K,
-                                 n_tile * args.block_n + (int)rank * half_n);
+                    tma2_load_2d(bmap, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K,
+                                 n_tile * args.block_n + v.col_off + (int)rank * half_w);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -750,12 +774,14 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
     } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only; whole warp, elected lane) =====
         if (leader) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.block_n >> 3) << 17) | ((256u >> 4) << 24);
+            const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             const uint64_t adesc0 = make_desc<BLOCK_K>(smem_u32(sA)), bdesc0 = make_desc<BLOCK_K>(smem_u32(sB));
             const uint32_t a_step = (uint32_t)A_BYTES >> 4, b_step = (uint32_t)args.b_stage_bytes >> 4;
-            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            for (int vt = pair_id; vt < num_tiles; vt += num_pairs) {
+                const int width = RING ? vtile_of(args, vt).width : args.block_n;
+                const uint32_t idesc = idesc_base | ((uint32_t)(width >> 3) << 17);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * args.block_n);
@@ -2157,9 +2183,25 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     int tiles = a.m_tiles * a.n_tiles;
     p->grid = tiles < 148 ? tiles : 148;
+    a.split = 1; a.split_from = 0x7fffffff; a.vtiles = tiles;
     if (a.pair) {
         int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
         p->grid = 2 * (pair_tiles < 74 ? pair_tiles : 74);
+        a.vtiles = pair_tiles;
+        // tail splitting: when the last wave would keep at most half of the 74 pairs busy, its tiles are cut into 2 or 4
+        // filter slices (>= 64 filters each) so that all pairs share it: e.g. 184 tiles = 2 waves + 36 -> 2 waves + 72 halves
+        const int rem = pair_tiles > 74 ? pair_tiles % 74 : 0;
+        if (a.ring && rem > 0 && 2 * rem <= 74 && !getenv("B200_NO_TAIL_SPLIT")) {
+            int sp = (4 * rem <= 74 && a.block_n % 256 == 0) ? 4 : 2;
+            if (getenv("B200_TAIL_SPLIT")) { int f = atoi(getenv("B200_TAIL_SPLIT")); if (f == 2 || f == 4) sp = f; }
+            if ((a.block_n / sp) % 64 == 0 && a.block_n / sp >= 64 && a.sub_cols == 64) {
+                a.split = sp; a.split_from = pair_tiles - rem; a.vtiles = pair_tiles - rem + rem * sp;
+                cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cp.cout_pad};
+                cuuint64_t strides[1] = {(cuuint64_t)K * esz};
+                cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)(a.block_n / sp / 2)};
+                encode(&p->maps.b2, (void *)cp.w, 2, dims, strides, box, block_k);
+            }
+        }
     }
     p->flops = 2.0 * (double)a.npix * out.c * K;
     char buf[256];
@@ -2171,5 +2213,6 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     if (a.ring) p->desc += " ringEpilogue(" + std::to_string(a.c_bufs) + ")";
     else if (a.staged) p->desc += " stagedEpilogue";
     if (a.upsample) p->desc += " +upsample2x";
+    if (a.split > 1) p->desc += " tailSplit(" + std::to_string(a.split) + "x" + std::to_string(a.vtiles - a.split_from) + ")";
     return p;
 }
