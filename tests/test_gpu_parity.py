@@ -170,6 +170,31 @@ def test_bf16_end_to_end_heads(dn, model, size, batch, workdir):
             assert n == len(po)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_non_square_input(dn, prec, workdir):
+    """width != height (224 x 160): every tiling decision (pixel tiles, patches, fused block, upsample phases, concat slices)
+    with two different extents; heads against the oracle"""
+    from yolo_tensorflow_b200 import synth as S
+    cfg2 = S.make_cfg("yolov3", workdir, batch=2, width=224, height=160)
+    wpath = model_files("yolov3", 2, 160, workdir)[1]                     # same architecture, same seeded weights
+    fd = os.dup(2); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 2)
+    try:
+        net = dn.Network(cfg2, wpath, precision=dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16)
+    finally:
+        os.dup2(fd, 2); os.close(fd); os.close(devnull)
+    assert (net.w, net.h) == (224, 160)
+    port = P.Net(cfg2, wpath)
+    x = synth.make_images(2, 3, 160, 224, 31)
+    outs = port.forward(x)
+    net.predict(x)
+    tol = FP32_TOL if prec == "fp32" else BF16_E2E_TOL
+    for i, L in enumerate(port.layers):
+        if L.type == "yolo":
+            a, r = net.layer_output(i), outs[i].reshape(2, -1)
+            assert np.abs(a - r).max() <= tol * np.abs(r).max(), i
+    net.close()
+
+
 def test_shortcut_fusion_matches_unfused(dn, workdir):
     """conv+shortcut fused into one tcgen05 kernel vs the two-kernel plan: every shortcut output within bf16 rounding"""
     fused, cfg, wpath = open_net(dn, "yolov3", 2, 160, workdir, dn.PREC_BF16, fuse=True)
