@@ -672,6 +672,22 @@ def test_conv_upsample_fusion_is_exact(dn, workdir):
         assert np.array_equal(a, b)
 
 
+def test_fused_path_is_deterministic_at_full_size(dn, workdir):
+    """the asynchronous roles of the tcgen05 kernels (TMA producer, MMA issuer, epilogue groups, store warp, residual loader)
+    only meet at mbarriers: 25 runs of the full-size batch must give bit-identical records (a race would show up here)"""
+    import hashlib
+    net, _, _ = open_net(dn, "yolov3", 64, 416, workdir, dn.PREC_BF16)
+    net.set_head_sync(0)
+    x = synth.make_images(64, 3, 416, 416, 1002)
+    seen = set()
+    for _ in range(25):
+        rec, counts = net.detect_batch(x, 416, 416, .5, .45)
+        rec = rec[np.lexsort((rec["cls"], rec["box_id"], rec["image"]))]
+        seen.add(hashlib.sha256(rec.tobytes() + counts.tobytes()).hexdigest())
+    assert len(seen) == 1
+    net.close()
+
+
 def test_python_wrapper_detect_on_ppm(dn, workdir, tmp_path):
     """python/darknet.py detect(): load_image_color -> network_predict_image (letterbox) -> boxes -> do_nms_obj"""
     net, cfg, wpath = open_net(dn, "yolov3-tiny", 1, 416, workdir, dn.PREC_FP32)
