@@ -77,6 +77,7 @@ struct ConvTcArgs {
     // tail splitting (CTA-pair kernel, ring epilogue): the tiles of the last, partly filled wave are cut into `split` filter
     // slices so that every pair works during it.  Virtual tile v < split_from is tile v at full width; the others are slices.
     int split_from, split, vtiles;
+    int local, ss_stride;    // unshared convolution: weight box and shift row of tile's location (m_tile % locations); floats per shift row
     int ring;                // 1: ring epilogue (ring_roles) with 384 threads; c_bufs = ring depth (<= 4)
     int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
     int ep_groups, c_bufs;   // epilogue warp groups (1..2) taking alternate tiles; depth of the output/residual tile ring (<= 8)
@@ -508,7 +509,8 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
                     const uint32_t sphase = (uint32_t)(j / NBUF) & 1u;
                     const uint32_t slot_addr = sC_addr + (uint32_t)slot * 16384u;
                     const bool last = q + 2 >= NSUB;       // this group's last sub-tile: the accumulator can be reused after the load
-                    const float *gsc = args.scale + t.col0 + SUBC * q, *gsh = args.shift + t.col0 + SUBC * q;
+                    const float *gsc = args.scale + t.col0 + SUBC * q;
+                    const float *gsh = args.shift + t.col0 + SUBC * q + (args.local ? (size_t)(t.m_tile % (args.tiles_x * args.tiles_y)) * args.ss_stride : 0);
                     if (SUBC == 64) {
                         uint32_t r[64];
                         tmem_ld32(taddr + 64 * q, r);
@@ -623,7 +625,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
                             tma_load_4d(&maps.a[py * 2 + px], dstA, &full[stage], cb * BLOCK_K, ox0 + xoff, oy0 + yoff, n0);
                         }
                     }
-                    if (!args.resident_b)
+                    if (args.local)              // unshared convolution: this location's own weight slab
+                        tma_load_3d(&maps.b, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n,
+                                    m_tile % (args.tiles_x * args.tiles_y));
+                    else if (!args.resident_b)
                         tma_load_2d(&maps.b, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -1808,8 +1813,10 @@ ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvPar
     return p;
 }
 
-ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual, float res_alpha, float res_beta, const TView *up_out)
+ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView *residual, float res_alpha, float res_beta, const TView *up_out,
+                                int local)
 {
+    if (local && (residual || up_out || cp.cout_pad % 64 != 0 || out.c != cp.cout_pad || out.dtype != DT_BF16 || in.c % 64 != 0)) return nullptr;
     if (up_out && (residual || up_out->dtype != DT_BF16 || up_out->h != 2 * out.h || up_out->w != 2 * out.w || up_out->c != out.c ||
                    up_out->ld % 8 != 0 || ((uintptr_t)up_out->p & 15))) return nullptr;
     if (in.dtype != DT_BF16) return nullptr;
@@ -1841,6 +1848,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     a.res_alpha = res_alpha; a.res_beta = res_beta;
     a.npix = (long long)in.n * out.h * out.w;
     a.block_n = cp.cout_pad < 256 ? cp.cout_pad : 256;
+    if (local) a.block_n = 64;          // weight-bandwidth bound: many narrow tiles keep every SM streaming its own slab slice
     if (getenv("B200_BLOCK_N") && cp.cout_pad % atoi(getenv("B200_BLOCK_N")) == 0 && atoi(getenv("B200_BLOCK_N")) >= 64) a.block_n = atoi(getenv("B200_BLOCK_N"));
     a.n_tiles = (cp.cout_pad + a.block_n - 1) / a.block_n;
     const size_t esz = 2;
@@ -1870,6 +1878,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                     if (score > best) { best = score; bw = tw; bh = th; bn = tn; }
                 }
             }
+        if (local) { bw = 1; bh = 1; bn = in.n < 128 ? in.n : 128; }      // one location per tile: GEMM rows = images
         a.TW = bw; a.TH = bh; a.TN = bn;
         a.tiles_x = div_up(out.w, bw); a.tiles_y = div_up(out.h, bh);
         a.m_tiles = a.tiles_x * a.tiles_y * div_up(in.n, bn);
@@ -1893,7 +1902,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         }
     }
     // ---- single-CTA patch kernel (mode 2, pair 0): few input channels, all weights resident ----------------------------
-    if (a.mode == 1 && !getenv("B200_NO_PATCH") && cp.size == 3 && cp.pad == 1 && out.dtype == DT_BF16 && a.n_tiles == 1 &&
+    if (a.mode == 1 && !local && !getenv("B200_NO_PATCH") && cp.size == 3 && cp.pad == 1 && out.dtype == DT_BF16 && a.n_tiles == 1 &&
         (cp.cout_pad == 64 || cp.cout_pad == 128 || cp.cout_pad == 256) && out.c == cp.cout_pad &&
         ((cp.stride == 1 && (C == 32 || C == 64)) || (cp.stride == 2 && C == 32 && in.ld == 32 && in.w % 2 == 0))) {
         const bool s2 = cp.stride == 2;
@@ -2019,7 +2028,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     // kernel, but only ~81 % of its MMA rows are valid outputs, so it ends up 5-20 % slower on every layer; the L2/TMA row
     // rate is therefore NOT the binding limit of the pair kernel (shared-memory bandwidth / MMA issue is).  The mode stays
     // available for experiments (B200_HALO=1 picks it by the cost model, B200_FORCE_HALO=1 always) but is off by default.
-    if (a.mode == 1 && (getenv("B200_HALO") || getenv("B200_FORCE_HALO")) && cp.stride == 1 && (cp.size & 1) && cp.size >= 3 && cp.pad == cp.size / 2 &&
+    if (a.mode == 1 && !local && (getenv("B200_HALO") || getenv("B200_FORCE_HALO")) && cp.stride == 1 && (cp.size & 1) && cp.size >= 3 && cp.pad == cp.size / 2 &&
         block_k == 64 && a.block_n % 32 == 0 && a.block_n >= 64 && out.dtype == DT_BF16) {
         const int halo = cp.size - 1, taps = cp.size * cp.size;
         int tiles_x = div_up(out.w + halo, 128) > 1 ? div_up(out.w, 128 - halo) : 1;
@@ -2073,7 +2082,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     if (getenv("B200_RING_SLOTS")) { int f = atoi(getenv("B200_RING_SLOTS")); if (f >= 2 && f <= 4) ring_slots = f; }
     const int sc_bytes = use_ring ? ring_slots * 16384 : (a.block_n / 64) * 16384;
     const long long slab_ = (long long)a.num_kblocks * ((a.block_n * block_k * 2 + 1023) / 1024 * 1024);
-    const bool could_reside = a.n_tiles == 1 && !getenv("B200_NO_RESIDENT_B") &&
+    const bool could_reside = a.n_tiles == 1 && !local && !getenv("B200_NO_RESIDENT_B") &&
                               slab_ + (want_staged ? 3LL * a_bytes_ + sc_bytes : 4LL * a_bytes_) <= budget_all;
     if (a.mode == 2) {
         // the patch kernel always runs as a CTA pair with its own smem budget (patch ring + weight ring + staging tile)
@@ -2111,14 +2120,21 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         p->desc = buf2;
         return p;
     }
-    a.pair = (!getenv("B200_NO_PAIR") && !could_reside && a.block_n % 32 == 0 && a.block_n >= 64 && a.m_tiles >= 2 &&
+    a.pair = (!getenv("B200_NO_PAIR") && !local && !could_reside && a.block_n % 32 == 0 && a.block_n >= 64 && a.m_tiles >= 2 &&
               (long long)a.num_kblocks * a.block_n >= 4 * 256) ? 1 : 0;
     // ---- B view ----
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cp.cout_pad};
         cuuint64_t strides[1] = {(cuuint64_t)K * esz};
         cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)(a.pair ? a.block_n / 2 : a.block_n)};
-        encode(&p->maps.b, (void *)cp.w, 2, dims, strides, box, block_k);
+        if (!local) encode(&p->maps.b, (void *)cp.w, 2, dims, strides, box, block_k);
+        else {                               // [location][filters][K]: the tile's location picks the slab
+            cuuint64_t dims3[3] = {(cuuint64_t)K, (cuuint64_t)cp.cout_pad, (cuuint64_t)out.h * out.w};
+            cuuint64_t strides3[2] = {(cuuint64_t)K * esz, (cuuint64_t)K * cp.cout_pad * esz};
+            cuuint32_t box3[3] = {(cuuint32_t)block_k, (cuuint32_t)a.block_n, 1};
+            encode(&p->maps.b, (void *)cp.w, 3, dims3, strides3, box3, block_k);
+            a.local = 1; a.ss_stride = cp.cout_pad;
+        }
     }
     // ---- smem / tmem budget ----
     const int a_bytes = 128 * block_k * 2;
@@ -2134,6 +2150,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     a.c_bufs = ring_slots;
     a.sub_cols = stageable64 ? 64 : 32;
     a.out_f32 = out.dtype == DT_F32 ? 1 : 0;
+    if (local && !a.ring) { delete p; return nullptr; }      // only the ring epilogue knows the per-location bias rows
     // weight-stationary variant: when one filter tile covers all filters and its whole [block_n x K] slab fits next
     // to >= 4 activation stages, load it once per CTA and stream only activations (halves the TMA rows per k-block)
     const long long slab = (long long)a.num_kblocks * a.b_stage_bytes;
@@ -2213,6 +2230,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     if (a.ring) p->desc += " ringEpilogue(" + std::to_string(a.c_bufs) + ")";
     else if (a.staged) p->desc += " stagedEpilogue";
     if (a.upsample) p->desc += " +upsample2x";
+    if (a.local) p->desc += " unshared(local)";
     if (a.split > 1) p->desc += " tailSplit(" + std::to_string(a.split) + "x" + std::to_string(a.vtiles - a.split_from) + ")";
     return p;
 }

@@ -28,7 +28,7 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // ---- local ---------------------------------------------------------------------------------------------
-// weights repacked to [loc][o][(ky,kx,c)] (same dtype as activations); bias [o][loc] fp32 (reference layout)
+// weights repacked to [loc][o][(ky,kx,c)] (same dtype as activations); bias transposed to [loc][o] fp32 at upload
 template <typename T, bool EXACT>
 __global__ void __launch_bounds__(256)
 local_kernel(const T *__restrict__ in, int N, int H, int W, int C, int ldi, T *__restrict__ out, int OH, int OW, int ldo,
@@ -67,7 +67,7 @@ local_kernel(const T *__restrict__ in, int N, int H, int W, int C, int ldi, T *_
         for (int i = 0; i < DENSE_BT; ++i) {
             float v = warp_sum(acc[i]);
             if (lane == 0 && b0 + i < N)
-                Elem<T>::store(out + ((size_t)(b0 + i) * locations + loc) * ldo + o, apply_act<EXACT>(v + bias[(size_t)o * locations + loc], act));
+                Elem<T>::store(out + ((size_t)(b0 + i) * locations + loc) * ldo + o, apply_act<EXACT>(v + bias[(size_t)loc * F + o], act));
         }
     }
 }

@@ -321,6 +321,7 @@ static void build_engine_device_state(b200_engine *e, network *net)
             d.w_bytes = (size_t)l.nweights * esize;
             d.w_off = off; off = align_up(off + d.w_bytes, 256);
             d.lbias_off = off; off = align_up(off + (size_t)l.outputs * sizeof(float), 256);
+            d.scale_off = off; off = align_up(off + (size_t)l.n * sizeof(float), 256);      // ones: the tcgen05 epilogue multiplies by it
         } else if (l.type == CONNECTED) {
             d.w_bytes = (size_t)l.inputs * l.outputs * esize;
             d.w_off = off; off = align_up(off + d.w_bytes, 256);
@@ -336,7 +337,7 @@ static void build_engine_device_state(b200_engine *e, network *net)
         DevLayer &d = e->L[i];
         if (l.type == CONVOLUTIONAL || l.type == LOCAL || l.type == CONNECTED) d.w = e->arena + d.w_off;
         if (l.type == CONVOLUTIONAL || l.type == CONNECTED) { d.scale = (float *)(e->arena + d.scale_off); d.shift = (float *)(e->arena + d.shift_off); }
-        if (l.type == LOCAL) d.lbias = (float *)(e->arena + d.lbias_off);
+        if (l.type == LOCAL) { d.lbias = (float *)(e->arena + d.lbias_off); d.scale = (float *)(e->arena + d.scale_off); }
     }
 
     // ---- kernel selection ------------------------------------------------------------------------------------
@@ -401,7 +402,16 @@ static void build_engine_device_state(b200_engine *e, network *net)
             break;
         }
         case DROPOUT: d.kernel = "alias"; break;
-        case LOCAL: d.kernel = "local"; break;
+        case LOCAL:
+            d.kernel = "local";
+            if (e->precision == B200_PREC_BF16 && !getenv("B200_LOCAL_SIMT")) {
+                // 49 independent GEMMs [images x 9C] x [9C x filters]: the conv kernel with one pixel per tile and the weight
+                // box taken from that pixel's own slab
+                ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.lbias, l.n};
+                d.tc = conv_tc_plan_create(e->L[i - 1].out, d.out, p, nullptr, 1.f, 1.f, nullptr, 1);
+                if (d.tc) d.kernel = "local_tc";
+            }
+            break;
         case CONNECTED: d.kernel = "connected"; break;
         case YOLO: d.kernel = "yolo_forward"; break;
         case REGION: d.kernel = "region_forward"; break;
@@ -557,7 +567,11 @@ extern "C" void b200_engine_upload_weights(b200_engine *e, network *net)
                             float v = l.weights[((size_t)loc * l.n + o) * K + (size_t)c * l.size * l.size + t];
                             put_elem(w, ((size_t)loc * l.n + o) * K + (size_t)t * l.c + c, v, e->act_dtype);
                         }
-            memcpy(host.data() + d.lbias_off, l.biases, (size_t)l.outputs * sizeof(float));
+            float *lb = (float *)(host.data() + d.lbias_off), *ones = (float *)(host.data() + d.scale_off);
+            for (int o = 0; o < l.n; ++o) {                      // reference layout [o][loc] -> [loc][o]: one contiguous row per location
+                ones[o] = 1.f;
+                for (int loc = 0; loc < locations; ++loc) lb[(size_t)loc * l.n + o] = l.biases[(size_t)o * locations + loc];
+            }
         } else if (l.type == CONNECTED) {
             // the producer's CHW flattening becomes HWC on the device: permute the weight columns accordingly
             const layer &prev = net->layers[i - 1];
@@ -647,7 +661,10 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
         }
         break;
     case DROPOUT: break;
-    case LOCAL: launch_local(in, out, d.w, d.lbias, l.size, l.stride, l.pad, act_id(l.activation), s); break;
+    case LOCAL:
+        if (d.tc && e->conv_backend == 0) launch_conv_tc(d.tc, s);
+        else launch_local(in, out, d.w, d.lbias, l.size, l.stride, l.pad, act_id(l.activation), s);
+        break;
     case CONNECTED: {
         const DevLayer &pd = e->L[i - 1];
         if (pd.out.ld != pd.out.c) { fprintf(stderr, "b200-darknet: connected input must be dense\n"); abort(); }

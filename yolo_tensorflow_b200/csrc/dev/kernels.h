@@ -54,7 +54,8 @@ void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
 struct ConvTcPlan;
 // nullptr if unsupported.  up_out: the convolution's result is written 2x nearest-upsampled into this view instead of `out`
 ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams p, const TView *residual, float res_alpha, float res_beta,
-                                const TView *up_out = nullptr);
+                                const TView *up_out = nullptr, int local = 0);
+// local = 1: unshared ("local") convolution: p.w = [location][filters][K], p.shift = bias [location][filters], p.scale = ones[filters]
 void conv_tc_plan_destroy(ConvTcPlan *plan);
 ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvParams p2, float res_alpha, float res_beta);   // fused residual block
 bool conv_tc_shape_supported(int cin, int stride, int act);
