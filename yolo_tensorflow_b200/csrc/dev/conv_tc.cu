@@ -1848,6 +1848,9 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     a.res_alpha = res_alpha; a.res_beta = res_beta;
     a.npix = (long long)in.n * out.h * out.w;
     a.block_n = cp.cout_pad < 256 ? cp.cout_pad : 256;
+    // a GEMM with a handful of pixel tiles (connected layer: 64 images = half a tile) is weight-bandwidth bound as well
+    if (!local && cp.size == 1 && cp.cout_pad >= 512 && cp.cout_pad % 64 == 0 &&
+        ((long long)in.n * out.h * out.w + 127) / 128 * ((cp.cout_pad + 255) / 256) < 37) a.block_n = 64;
     if (local) a.block_n = 64;          // weight-bandwidth bound: many narrow tiles keep every SM streaming its own slab slice
     if (getenv("B200_BLOCK_N") && cp.cout_pad % atoi(getenv("B200_BLOCK_N")) == 0 && atoi(getenv("B200_BLOCK_N")) >= 64) a.block_n = atoi(getenv("B200_BLOCK_N"));
     a.n_tiles = (cp.cout_pad + a.block_n - 1) / a.block_n;

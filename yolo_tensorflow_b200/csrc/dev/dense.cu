@@ -136,3 +136,18 @@ void launch_connected(const void *in, int in_dtype, int batch, int inputs, int o
         connected_kernel<bf16, false><<<grid, 256, 0, s>>>((const bf16 *)in, batch, inputs, outputs, (const bf16 *)w, scale, shift, act, out);
     B200_LAUNCHED();
 }
+
+// [rows][ld] fp32 -> dense [rows][cols]: the tcgen05 connected layer computes into 64-filter-padded rows
+__global__ void unpad_rows_f32_kernel(const float *__restrict__ src, int ld, float *__restrict__ dst, int cols, long long total)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+        dst[t] = src[(t / cols) * ld + t % cols];
+}
+
+void launch_unpad_rows_f32(const float *src, int ld, float *dst, int cols, int rows, cudaStream_t s)
+{
+    long long total = (long long)rows * cols;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    unpad_rows_f32_kernel<<<grid, 256, 0, s>>>(src, ld, dst, cols, total);
+    B200_LAUNCHED();
+}

@@ -21,6 +21,7 @@ struct DevLayer {
     TView out;                 // NHWC output view (n = planned batch capacity)
     bool owns_out;
     float *head_out;           // YOLO / REGION / DETECTION / CONNECTED: fp32 [batch][outputs]
+    float *fc_tmp;             // CONNECTED on tcgen05: fp32 [batch][cout_pad] (row-padded GEMM output, compacted into head_out)
     // parameters (inside the arena)
     void *w;
     float *scale, *shift, *lbias;
@@ -323,10 +324,11 @@ static void build_engine_device_state(b200_engine *e, network *net)
             d.lbias_off = off; off = align_up(off + (size_t)l.outputs * sizeof(float), 256);
             d.scale_off = off; off = align_up(off + (size_t)l.n * sizeof(float), 256);      // ones: the tcgen05 epilogue multiplies by it
         } else if (l.type == CONNECTED) {
-            d.w_bytes = (size_t)l.inputs * l.outputs * esize;
+            d.cout_pad = (int)align_up(l.outputs, 64);                  // zero rows pad the GEMM's N to whole 64-filter tiles
+            d.w_bytes = (size_t)l.inputs * d.cout_pad * esize;
             d.w_off = off; off = align_up(off + d.w_bytes, 256);
-            d.scale_off = off; off = align_up(off + (size_t)l.outputs * sizeof(float), 256);
-            d.shift_off = off; off = align_up(off + (size_t)l.outputs * sizeof(float), 256);
+            d.scale_off = off; off = align_up(off + (size_t)d.cout_pad * sizeof(float), 256);
+            d.shift_off = off; off = align_up(off + (size_t)d.cout_pad * sizeof(float), 256);
         }
     }
     e->arena_bytes = off;
@@ -412,7 +414,22 @@ static void build_engine_device_state(b200_engine *e, network *net)
                 if (d.tc) d.kernel = "local_tc";
             }
             break;
-        case CONNECTED: d.kernel = "connected"; break;
+        case CONNECTED: {
+            d.kernel = "connected";
+            const DevLayer &pd = e->L[i - 1];
+            if (e->precision == B200_PREC_BF16 && !getenv("B200_CONNECTED_SIMT") && pd.out.dtype == DT_BF16 && pd.out.ld == pd.out.c &&
+                l.inputs % 64 == 0) {
+                // out[b][o] = sum_i in[b][i] W[o][i] is a 1x1 convolution over a 1 x 1 "image" with `inputs` channels
+                d.fc_tmp = (float *)dev_alloc((size_t)e->cap * d.cout_pad * sizeof(float));
+                TView fin{pd.out.p, e->cap, 1, 1, l.inputs, l.inputs, DT_BF16};
+                TView fout{d.fc_tmp, e->cap, 1, 1, l.outputs, d.cout_pad, DT_F32};
+                ConvParams p{1, 1, 0, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
+                d.tc = (l.activation == LEAKY || l.activation == LINEAR) ? conv_tc_plan_create(fin, fout, p, nullptr, 1.f, 1.f) : nullptr;
+                if (d.tc) d.kernel = "connected_tc";
+                else { cudaFree(d.fc_tmp); d.fc_tmp = nullptr; }
+            }
+            break;
+        }
         case YOLO: d.kernel = "yolo_forward"; break;
         case REGION: d.kernel = "region_forward"; break;
         case DETECTION: d.kernel = "detection_forward"; break;
@@ -464,7 +481,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; d.fc_tmp = nullptr; }
     e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->d_input_next = nullptr; e->submitted = 0; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
@@ -499,7 +516,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         for (auto &d : e->L) {
             if (d.tc) conv_tc_plan_destroy(d.tc);
             if (d.owns_out) cudaFree(d.out.p);
-            cudaFree(d.stem_cols);
+            cudaFree(d.stem_cols); cudaFree(d.fc_tmp);
             if (d.head_out && d.type != DROPOUT) cudaFree(d.head_out);
         }
         cudaFree(e->d_input); cudaFree(e->d_input_next); cudaEventDestroy(e->submit_done); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
@@ -668,6 +685,11 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
     case CONNECTED: {
         const DevLayer &pd = e->L[i - 1];
         if (pd.out.ld != pd.out.c) { fprintf(stderr, "b200-darknet: connected input must be dense\n"); abort(); }
+        if (d.tc && e->conv_backend == 0) {
+            launch_conv_tc(d.tc, s);
+            launch_unpad_rows_f32(d.fc_tmp, d.cout_pad, d.head_out, l.outputs, batch, s);
+            break;
+        }
         launch_connected(pd.out.p, pd.out.dtype, batch, l.inputs, l.outputs, d.w, e->act_dtype, d.scale, d.shift,
                          act_id(l.activation), d.head_out, s);
         break;

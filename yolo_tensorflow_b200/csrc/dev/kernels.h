@@ -67,6 +67,7 @@ void tc_encode_tiled(void *map, int dtype, int rank, void *base, const unsigned 
 
 // YOLOv1 dense layers (dense.cu)
 void launch_local(TView in, TView out, const void *w, const float *bias, int size, int stride, int pad, int act, cudaStream_t s);
+void launch_unpad_rows_f32(const float *src, int ld, float *dst, int cols, int rows, cudaStream_t s);
 void launch_connected(const void *in, int in_dtype, int batch, int inputs, int outputs, const void *w, int w_dtype,
                       const float *scale, const float *shift, int act, float *out, cudaStream_t s);
 
