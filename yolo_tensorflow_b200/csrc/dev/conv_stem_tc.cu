@@ -418,31 +418,240 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Generalised TMA-fed stem for large windows (YOLOv1: 7x7, stride 2, pad 3, 64 filters).  Same pipeline as above; the im2col
+// row of a pixel is KS*KS*3 taps padded to a multiple of 32 and laid out as NKB K-blocks of [128 pixels x 32] (64B-swizzled),
+// built block by block so that only 32 taps are live in registers at a time; NKB * 2 MMAs per tile.
+// Tile = 32 x 4 output pixels; patch = [3][STRIDE*3 + KS rows][STRIDE*31 + KS + margin columns] of the fp32 input.
+// ---------------------------------------------------------------------------------------------------
+template <int KS, int STRIDE> struct StemGeom {
+    static constexpr int PAD = (KS - 1) / 2;
+    static constexpr int TAPS = KS * KS * 3;
+    static constexpr int NKB = (TAPS + 31) / 32;                      // K-blocks of 32
+    static constexpr int MARGIN = 4;                                  // patch starts 4 columns left of STRIDE*ox0 (16-byte aligned start)
+    static constexpr int PW = (STRIDE * (kTW - 1) + KS + (MARGIN - PAD) + 3) / 4 * 4;
+    static constexpr int PH = STRIDE * (kTH - 1) + KS;
+    static constexpr int PATCH_BYTES = 3 * PH * PW * 4;
+    static constexpr int PATCH_PITCH = (PATCH_BYTES + 127) / 128 * 128;
+};
+constexpr int kGenSlots = 2, kGenPatches = 4, kGenOut = 2, kGenAcc = 4;
+
+template <int NOUT, int KS, int STRIDE>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_stem_tc_gen_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArgs a)
+{
+    using G = StemGeom<KS, STRIDE>;
+    static_assert(NOUT == 64, "one 128-byte output row per pixel");
+    constexpr int A_SLOT = G::NKB * 8192, B_BYTES = G::NKB * NOUT * 64, C_SLOT = 128 * NOUT * 2;
+    extern __shared__ uint8_t stem_smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)stem_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                                              // kGenSlots x NKB x 8 KB
+    uint8_t *sC = sA + kGenSlots * A_SLOT;                           // kGenOut x 16 KB
+    uint8_t *sB = sC + kGenOut * C_SLOT;                             // NKB x [NOUT x 32]
+    uint8_t *sP = sB + (B_BYTES + 1023) / 1024 * 1024;               // patch ring
+    __shared__ uint64_t pfull[kGenPatches], pempty[kGenPatches], afull[kGenSlots], aempty[kGenSlots], tfull[kGenAcc], tempty[kGenAcc],
+                        cwritten[kGenOut], cempty[kGenOut];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_scale[NOUT], s_shift[NOUT];
+    if (threadIdx.x < NOUT) { s_scale[threadIdx.x] = a.scale[threadIdx.x]; s_shift[threadIdx.x] = a.shift[threadIdx.x]; }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = a.num_tiles;
+
+    for (int idx = threadIdx.x; idx < NOUT * G::NKB * 32; idx += kThreads2) {
+        const int co = idx / (G::NKB * 32), k = idx % (G::NKB * 32), kb = k >> 5, kk = k & 31;
+        const bf16 v = k < G::TAPS ? a.w[co * G::TAPS + k] : __float2bfloat16(0.f);
+        *reinterpret_cast<bf16 *>(sB + kb * (NOUT * 64) + co * 64 + ((((kk >> 3) ^ ((co >> 1) & 3))) << 4) + (kk & 7) * 2) = v;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGenPatches; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 4); }
+        for (int i = 0; i < kGenSlots; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < kGenAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < kGenOut; ++i) { mbar_init(&cwritten[i], 4); mbar_init(&cempty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kGenAcc * NOUT) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===================================== MMA issuer ===========================================================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bdesc0 = make_desc<32>(smem_u32(sB)), adesc0 = make_desc<32>(smem_u32(sA));
+        int i = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+            const int slot = i % kGenSlots, acc = i % kGenAcc;
+            STEM_WAIT(&tempty[acc], ((i / kGenAcc) & 1) ^ 1);
+            STEM_WAIT(&afull[slot], (i / kGenSlots) & 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NOUT);
+#pragma unroll
+            for (int kb = 0; kb < G::NKB; ++kb) {
+                const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(slot * A_SLOT + kb * 8192) >> 4);
+                const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(kb * NOUT * 64) >> 4);
+                tc_mma_bf16_elect(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                tc_mma_bf16_elect(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            }
+            tc_commit_elect(&aempty[slot]);
+            tc_commit_elect(&tfull[acc]);
+        }
+    } else if (warp == 1) {
+        // ===================================== TMA loads ============================================================
+        if (lane == 0) {
+            pdl_wait();
+            Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
+            int i = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
+                const int ps = i % kGenPatches;
+                STEM_WAIT(&pempty[ps], ((i / kGenPatches) & 1) ^ 1);
+                mbar_expect_tx(&pfull[ps], G::PATCH_BYTES);
+                tma_load_4d(&maps.in, sP + ps * G::PATCH_PITCH, &pfull[ps], STRIDE * t.tx * kTW - G::MARGIN, STRIDE * t.ty * kTH - G::PAD, 0, t.tn);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================== TMA stores ===========================================================
+        if (lane == 0) {
+            pdl_wait();
+            Walk t; t.init(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
+            int i = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
+                const int cs = i % kGenOut;
+                STEM_WAIT(&cwritten[cs], (i / kGenOut) & 1);
+                tma_store_4d(&maps.out, sC + cs * C_SLOT, 0, t.tx * kTW, t.ty * kTH, t.tn);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(&cempty[cs]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp <= 10) {
+        // ===================================== window gather (two groups of 4 warps) ================================
+        const int g = (warp - 3) >> 2;
+        const int r = ((warp - 3) & 3) * 32 + lane;
+        const int px = r % kTW, py = r / kTW;
+        const uint32_t sw = (uint32_t)(r >> 1) & 3u;
+        int i = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2) {
+            const int slot = i % kGenSlots, ps = i % kGenPatches;
+            STEM_WAIT(&pfull[ps], (i / kGenPatches) & 1);
+            STEM_WAIT(&aempty[slot], ((i / kGenSlots) & 1) ^ 1);
+            const float *P = reinterpret_cast<const float *>(sP + ps * G::PATCH_PITCH) + (STRIDE * py) * G::PW + STRIDE * px + (G::MARGIN - G::PAD);
+            const uint32_t row_addr = smem_u32(sA) + (uint32_t)(slot * A_SLOT) + (uint32_t)r * 64u;
+#pragma unroll
+            for (int kb = 0; kb < G::NKB; ++kb) {
+                float v[32];
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int t = kb * 32 + kk;                       // tap index (ky, kx, c), compile-time after unrolling
+                    if (t < G::TAPS) {
+                        const int c = t % 3, kx = (t / 3) % KS, ky = t / (3 * KS);
+                        v[kk] = P[c * (G::PH * G::PW) + ky * G::PW + kx];
+                    } else v[kk] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 q;
+                    q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]); q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                    q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                    sts128(row_addr + (uint32_t)(kb * 8192) + (((uint32_t)j ^ sw) << 4), q);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pempty[ps]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[slot]);
+        }
+    } else {
+        // ===================================== epilogue (two groups of 4 warps) =====================================
+        const int g = (warp - 11) >> 2;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const bool leaky = a.act == ACT_LEAKY;
+        const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
+        const uint32_t swz = (uint32_t)(r & 7);                    // 128-byte rows
+        int i = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2) {
+            const int acc = i % kGenAcc, cs = i % kGenOut;
+            STEM_WAIT(&tfull[acc], (i / kGenAcc) & 1);
+            tc_fence_after();
+            uint32_t d[NOUT];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NOUT);
+            tmem_ld32(taddr, d);
+            tmem_ld32(taddr + 32, d + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            STEM_WAIT(&cempty[cs], ((i / kGenOut) & 1) ^ 1);
+            const uint32_t row_addr = smem_u32(sC) + (uint32_t)(cs * C_SLOT) + (uint32_t)r * 128u;
+#pragma unroll
+            for (int c = 0; c < NOUT; c += 8) {
+                float o[8];
+#pragma unroll
+                for (int q = 0; q < 8; q += 4) {
+                    const uint4 s4 = lds128(sc_addr + (uint32_t)(c + q) * 4u), h4 = lds128(sh_addr + (uint32_t)(c + q) * 4u);
+                    o[q + 0] = fmaf(__uint_as_float(d[c + q + 0]), __uint_as_float(s4.x), __uint_as_float(h4.x));
+                    o[q + 1] = fmaf(__uint_as_float(d[c + q + 1]), __uint_as_float(s4.y), __uint_as_float(h4.y));
+                    o[q + 2] = fmaf(__uint_as_float(d[c + q + 2]), __uint_as_float(s4.z), __uint_as_float(h4.z));
+                    o[q + 3] = fmaf(__uint_as_float(d[c + q + 3]), __uint_as_float(s4.w), __uint_as_float(h4.w));
+                }
+                if (leaky) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = fmaxf(o[q], 0.1f * o[q]);
+                }
+                uint4 pk;
+                pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+                sts128(row_addr + (((uint32_t)(c >> 3) ^ swz) << 4), pk);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cwritten[cs]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kGenAcc * NOUT) : "memory");
+    }
+}
+
 // tensor maps depend on the buffers only: cache the last few (the chunked H2D path launches the stem per chunk)
-struct MapCacheEntry { const void *in; void *out; int n, h, w, c, ld, pack; StemTcMaps maps; };
+struct MapCacheEntry { const void *in; void *out; int n, h, w, c, ld, pack, pw, ph; StemTcMaps maps; };
 static MapCacheEntry g_maps[16];
 static int g_maps_used = 0, g_maps_next = 0;
 
-static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView out, int pack)
+static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView out, int pack, int pw = kPW, int ph = kPH)
 {
     for (int i = 0; i < g_maps_used; ++i) {
         const MapCacheEntry &e = g_maps[i];
-        if (e.in == in && e.out == out.p && e.n == n && e.h == h && e.w == w && e.c == out.c && e.ld == out.ld && e.pack == pack) return &e.maps;
+        if (e.in == in && e.out == out.p && e.n == n && e.h == h && e.w == w && e.c == out.c && e.ld == out.ld && e.pack == pack && e.pw == pw && e.ph == ph) return &e.maps;
     }
     MapCacheEntry &e = g_maps[g_maps_next];
     g_maps_next = (g_maps_next + 1) % 16;
     if (g_maps_used < 16) ++g_maps_used;
-    e.in = in; e.out = out.p; e.n = n; e.h = h; e.w = w; e.c = out.c; e.ld = out.ld; e.pack = pack;
+    e.in = in; e.out = out.p; e.n = n; e.h = h; e.w = w; e.c = out.c; e.ld = out.ld; e.pack = pack; e.pw = pw; e.ph = ph;
     {
         unsigned long long dims[4] = {(unsigned long long)w, (unsigned long long)h, 3ull, (unsigned long long)n};
         unsigned long long strides[3] = {(unsigned long long)w * 4, (unsigned long long)h * w * 4, (unsigned long long)3 * h * w * 4};
-        unsigned box[4] = {kPW, kPH, 3, 1};
+        unsigned box[4] = {(unsigned)pw, (unsigned)ph, 3, 1};
         tc_encode_tiled(&e.maps.in, 1, 4, (void *)in, dims, strides, box, 0);
     }
     {
         // packed: the dense output seen as rows of `pack` pixels (128 bytes)
-        unsigned long long dims[4] = {(unsigned long long)out.c * pack, (unsigned long long)w / pack, (unsigned long long)h, (unsigned long long)n};
-        unsigned long long strides[3] = {(unsigned long long)out.ld * 2 * pack, (unsigned long long)w * out.ld * 2, (unsigned long long)h * w * out.ld * 2};
+        const unsigned long long ow = (unsigned long long)out.w, oh = (unsigned long long)out.h;      // = w, h for the stride-1 stems
+        unsigned long long dims[4] = {(unsigned long long)out.c * pack, ow / pack, oh, (unsigned long long)n};
+        unsigned long long strides[3] = {(unsigned long long)out.ld * 2 * pack, ow * out.ld * 2, oh * ow * out.ld * 2};
         unsigned box[4] = {(unsigned)out.c * pack, (unsigned)(kTW / pack), kTH, 1};
         tc_encode_tiled(&e.maps.out, 0, 4, out.p, dims, strides, box, out.c * 2 * pack);
     }
@@ -455,6 +664,31 @@ static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView o
 bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
 {
     if (getenv("B200_STEM_SIMT")) return false;
+    if (out.dtype == DT_BF16 && c == 3 && p.size == 7 && p.stride == 2 && p.pad == 3 && out.c == 64 && p.cout_pad == 64 &&
+        out.h == (h + 6 - 7) / 2 + 1 && out.w == (w + 6 - 7) / 2 + 1 && w % 4 == 0 && ((uintptr_t)in_nchw & 15) == 0 &&
+        out.ld % 8 == 0 && ((uintptr_t)out.p & 15) == 0 && (p.act == ACT_LEAKY || p.act == ACT_LINEAR) && !getenv("B200_STEM7_SIMT")) {
+        using G = StemGeom<7, 2>;                                   // YOLOv1's first layer
+        StemTcArgs a;
+        a.in = in_nchw; a.out = (bf16 *)out.p; a.w = (const bf16 *)p.w; a.scale = p.scale; a.shift = p.shift;
+        a.N = n; a.H = h; a.W = w; a.ldo = out.ld; a.act = p.act; a.pack = 1;
+        a.tiles_x = div_up(out.w, kTW); a.tiles_y = div_up(out.h, kTH);
+        a.num_tiles = a.tiles_x * a.tiles_y * n;
+        const StemTcMaps *maps = stem_maps(in_nchw, n, h, w, out, 1, G::PW, G::PH);
+        const size_t smem = 1024 + (size_t)kGenSlots * G::NKB * 8192 + kGenOut * 16384 + (G::NKB * 64 * 64 + 1023) / 1024 * 1024 + kGenPatches * G::PATCH_PITCH;
+        static bool configured7 = false;
+        if (!configured7) {
+            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_gen_kernel<64, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured7 = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(a.num_tiles < 148 ? a.num_tiles : 148); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = getenv("B200_NO_PDL") ? 0 : 1;
+        B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_gen_kernel<64, 7, 2>, *maps, a));
+        return true;
+    }
     if (out.dtype != DT_BF16 || c != 3 || p.size != 3 || p.stride != 1 || p.pad != 1) return false;
     if (out.c != p.cout_pad || (out.c != 16 && out.c != 32) || out.h != h || out.w != w) return false;
     if (out.ld % 8 != 0 || ((uintptr_t)out.p & 15)) return false;
