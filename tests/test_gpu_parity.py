@@ -240,6 +240,8 @@ SHAPES = [  # h, w, c, filters, size, stride, batch
     (33, 44, 32, 64, 3, 2, 2),       # patch kernel, stride 2 on pixel-pair rows, odd height
     (21, 37, 32, 128, 3, 1, 2),      # patch kernel, stride 1, 128 filters (two 64-channel sub-tiles), odd sizes
     (26, 30, 64, 128, 3, 1, 3),      # patch kernel, C=64: two CTAs per pixel tile, 64 filters each
+    (40, 56, 16, 32, 3, 1, 3),       # patch kernel, 16 -> 32 channels (32-byte patch rows, 64-byte output rows): yolov3-tiny layer 2
+    (17, 23, 16, 32, 3, 1, 2),
     (19, 23, 64, 256, 3, 1, 2),      # patch kernel, four filter slices
     (40, 56, 32, 64, 3, 1, 3, "tap"),    # the same shapes through the tap-per-box kernels (B200_NO_PATCH)
     (26, 26, 32, 64, 3, 2, 3, "tap"),
@@ -265,7 +267,8 @@ def test_conv_tc_shape(dn, shape, tmp_path):
         os.dup2(fd, 2); os.close(fd); os.close(devnull)
     assert net.kernel(1) == "conv_tc"
     plan = dn.lib.b200_layer_plan(net.ptr, 1).decode()
-    patchable = size == 3 and filters in (64, 128, 256) and ((stride == 1 and c in (32, 64)) or (stride == 2 and c == 32 and w % 2 == 0))
+    patchable = size == 3 and ((filters in (64, 128, 256) and ((stride == 1 and c in (32, 64)) or (stride == 2 and c == 32 and w % 2 == 0)))
+                               or (filters == 32 and c == 16 and stride == 1))
     assert ("PATCH" in plan) == (patchable and not tap_only), plan
     port = P.Net(cfg, wpath)
     x = synth.make_images(batch, 3, h, w, 5)

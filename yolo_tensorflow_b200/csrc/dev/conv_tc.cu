@@ -994,14 +994,20 @@ template <int NSUB, int NSEG, int KS0, int KS1>       // K segment s issues (s o
 __global__ void __launch_bounds__(352, 1)
 conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
 {
-    constexpr int N = NSUB * 64;
+    // NSUB = 64-filter sub-tiles per tile; NSUB = 0 stands for a single 32-filter sub-tile (64-byte output rows, 64B swizzle)
+    constexpr int N = NSUB ? NSUB * 64 : 32;
+    constexpr int SUBS = NSUB ? NSUB : 1;                            // sub-tiles per ring slot
+    constexpr int SUBC = NSUB ? 64 : 32;                             // filters per sub-tile
+    constexpr int RB = SUBC * 2;                                     // bytes per pixel row of a sub-tile = its swizzle span
+    constexpr int SUBT = 128 * RB;                                   // bytes per sub-tile
+    constexpr int SLOT = (SUBS * SUBT + 1023) / 1024 * 1024;         // ring slot pitch
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int stages = args.stages;
     uint8_t *sA = smem;                                              // patch ring
     uint8_t *sB = sA + (size_t)stages * args.a_stage_bytes;          // nb resident weight tiles
-    uint8_t *sC = sB + (size_t)args.nb * args.b_stage_bytes;         // output ring: c_bufs x NSUB x 16 KB
-    uint8_t *aux = sC + (size_t)args.c_bufs * NSUB * 16384;
+    uint8_t *sC = sB + (size_t)args.nb * args.b_stage_bytes;         // output ring: c_bufs slots of SUBS sub-tiles
+    uint8_t *aux = sC + (size_t)args.c_bufs * ((SUBS * SUBT + 1023) / 1024 * 1024);
     uint64_t *full = (uint64_t *)aux;                                // [8]
     uint64_t *empty = full + 8;                                      // [8]
     uint64_t *tfull = empty + 8;                                     // [8]
@@ -1061,11 +1067,11 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
                 if (has_res) {
                     int rows_here = args.OH - oy0; if (rows_here > args.halo_THv) rows_here = args.halo_THv;
                     MBAR_WAIT_HERE(&cempty[cb], cphase ^ 1);
-                    mbar_expect_tx(&cfull[cb], (uint32_t)(rows_here * args.halo_TWv * 128 * NSUB));
-                    uint8_t *cdst = sC + (size_t)cb * NSUB * 16384;
-                    for (int q = 0; q < NSUB; ++q)
+                    mbar_expect_tx(&cfull[cb], (uint32_t)(rows_here * args.halo_TWv * RB * SUBS));
+                    uint8_t *cdst = sC + (size_t)cb * SLOT;
+                    for (int q = 0; q < SUBS; ++q)
                         for (int yy = 0; yy < rows_here; ++yy)
-                            tma_load_4d(&maps.r, cdst + q * 16384 + yy * args.halo_P * 128, &cfull[cb], ch0 + 64 * q, ox0, oy0 + yy, t.tn);
+                            tma_load_4d(&maps.r, cdst + q * SUBT + yy * args.halo_P * RB, &cfull[cb], ch0 + SUBC * q, ox0, oy0 + yy, t.tn);
                     if (++cb == NBUF) { cb = 0; cphase ^= 1; }
                 }
             }
@@ -1116,11 +1122,11 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
             for (int tile = vb; tile < num_tiles; tile += vgrid, t.next(args.tiles_x, args.tiles_y)) {
                 const int ox0 = t.tx * args.halo_TWv, oy0 = t.ty * args.halo_THv;
                 int rows_here = args.OH - oy0; if (rows_here > args.halo_THv) rows_here = args.halo_THv;
-                const uint8_t *src = sC + (size_t)cb * NSUB * 16384;
+                const uint8_t *src = sC + (size_t)cb * SLOT;
                 MBAR_WAIT_HERE(&cwritten[cb], cphase);
-                for (int q = 0; q < NSUB; ++q)
+                for (int q = 0; q < SUBS; ++q)
                     for (int yy = 0; yy < rows_here; ++yy)
-                        tma_store_4d(&maps.c, src + q * 16384 + yy * args.halo_P * 128, ch0 + 64 * q, ox0, oy0 + yy, t.tn);
+                        tma_store_4d(&maps.c, src + q * SUBT + yy * args.halo_P * RB, ch0 + SUBC * q, ox0, oy0 + yy, t.tn);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 bulk_wait_read<0>();
                 mbar_arrive(&cempty[cb]);
@@ -1139,33 +1145,33 @@ conv_tc_patch_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a
         const bool leaky = args.act == ACT_LEAKY;
         const float alpha = args.res_alpha, beta = args.res_beta;
         const uint32_t scale_addr = smem_u32(s_scale), shift_addr = smem_u32(s_shift);
-        const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
+        const uint32_t row_off = (uint32_t)row * RB, row_x = RB == 128 ? (uint32_t)(row & 7) : ((uint32_t)(row >> 1) & 3u);
         int i = g;                                         // CTA-local tile counter
         for (int tile = vb + g * vgrid; tile < num_tiles; tile += G * vgrid, i += G) {
             const int acc = i % args.acc_stages;
             const uint32_t acc_phase = (uint32_t)(i / args.acc_stages) & 1u;
             const int cb = i % NBUF;
             const uint32_t cphase = (uint32_t)(i / NBUF) & 1u;
-            const uint32_t slot = smem_u32(sC + (size_t)cb * NSUB * 16384);
+            const uint32_t slot = smem_u32(sC + (size_t)cb * SLOT);
             if (has_res) MBAR_WAIT_HERE(&cfull[cb], cphase);          // residual landed (the producer waited for the slot)
             else MBAR_WAIT_HERE(&cempty[cb], cphase ^ 1);             // slot free
             MBAR_WAIT_HERE(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N);
 #pragma unroll
-            for (int c0 = 0; c0 < N; c0 += 64) {
-                uint32_t r[64];
+            for (int c0 = 0; c0 < N; c0 += SUBC) {
+                uint32_t r[SUBC];
                 tmem_ld32(taddr + c0, r);
-                tmem_ld32(taddr + c0 + 32, r + 32);
+                if constexpr (SUBC == 64) tmem_ld32(taddr + c0 + 32, r + 32);
                 tmem_ld_wait();
-                if (c0 + 64 == N) {                        // accumulator fully read: hand it back before the math
+                if (c0 + SUBC == N) {                      // accumulator fully read: hand it back before the math
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
 #pragma unroll
-                for (int j = 0; j < 64; j += 8) {
-                    const uint32_t addr = slot + (uint32_t)(c0 >> 6) * 16384u + row_off + ((((uint32_t)j >> 3) ^ row_x) << 4);
+                for (int j = 0; j < SUBC; j += 8) {
+                    const uint32_t addr = slot + (uint32_t)(c0 / SUBC) * SUBT + row_off + ((((uint32_t)j >> 3) ^ row_x) << 4);
                     float v[8];
 #pragma unroll
                     for (int q = 0; q < 8; q += 4) {
@@ -1676,6 +1682,7 @@ template <int NSUB> static void launch_patch(ConvTcPlan *p, cudaStream_t s)
 {
     const ConvTcArgs &a = p->args;
     if (a.nseg == 6) launch_patch_variant<NSUB, 6, 4, 2>(p, s);                 // stride 2 on pixel-pair rows
+    else if (a.seg_k[0] == 1) launch_patch_variant<NSUB, 9, 1, 1>(p, s);        // stride 1, 16 channels
     else if (a.seg_k[0] == 2) launch_patch_variant<NSUB, 9, 2, 2>(p, s);        // stride 1, 32 channels
     else launch_patch_variant<NSUB, 9, 4, 4>(p, s);                             // stride 1, 64 channels
 }
@@ -1693,7 +1700,8 @@ void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
         return;
     }
     if (p->args.mode == 2 && !p->args.pair) {
-        if (p->args.block_n == 64) launch_patch<1>(p, s);
+        if (p->args.block_n == 32) launch_patch<0>(p, s);
+        else if (p->args.block_n == 64) launch_patch<1>(p, s);
         else launch_patch<2>(p, s);
         B200_LAUNCHED();
         return;
@@ -1906,8 +1914,9 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     }
     // ---- single-CTA patch kernel (mode 2, pair 0): few input channels, all weights resident ----------------------------
     if (a.mode == 1 && !local && !getenv("B200_NO_PATCH") && cp.size == 3 && cp.pad == 1 && out.dtype == DT_BF16 && a.n_tiles == 1 &&
-        (cp.cout_pad == 64 || cp.cout_pad == 128 || cp.cout_pad == 256) && out.c == cp.cout_pad &&
-        ((cp.stride == 1 && (C == 32 || C == 64)) || (cp.stride == 2 && C == 32 && in.ld == 32 && in.w % 2 == 0))) {
+        (cp.cout_pad == 64 || cp.cout_pad == 128 || cp.cout_pad == 256 || (cp.cout_pad == 32 && C == 16 && cp.stride == 1)) &&
+        out.c == cp.cout_pad &&
+        ((cp.stride == 1 && (C == 16 || C == 32 || C == 64)) || (cp.stride == 2 && C == 32 && in.ld == 32 && in.w % 2 == 0))) {
         const bool s2 = cp.stride == 2;
         const int a_k = s2 ? 64 : C, b_k = a_k, row_bytes = a_k * 2;
         const int halo_x = s2 ? 1 : 2;
@@ -1922,7 +1931,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         const int b_tile = (N * b_k * 2 + 1023) / 1024 * 1024;
         int groups = 2;
         if (getenv("B200_PATCH_GROUPS")) groups = atoi(getenv("B200_PATCH_GROUPS")) == 1 ? 1 : 2;
-        const int aux_bytes = 512 + 2 * 512 * 4, slot_bytes = (N / 64) * 16384;
+        const int aux_bytes = 512 + 2 * 512 * 4, slot_bytes = N >= 64 ? (N / 64) * 16384 : 8192;      // 32 filters: 64-byte rows
         const int np = s2 ? 2 : 1;
         auto stage_bytes_for = [&](int P) {
             const int max_shift = s2 ? P + 1 : 2 * P + 2;
@@ -2006,8 +2015,8 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                     cuuint32_t box[2] = {(cuuint32_t)b_k, (cuuint32_t)N};
                     encode(&p->maps.b, (void *)cp.w, 2, dims, strides, box, b_k);
                 }
-                encode_tile_view(&p->maps.c, out, cp.cout_pad, a);
-                if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a);
+                encode_tile_view(&p->maps.c, out, cp.cout_pad, a, N >= 64 ? 64 : 32);
+                if (residual) encode_tile_view(&p->maps.r, *residual, cp.cout_pad, a, N >= 64 ? 64 : 32);
                 int fit = 512 / N;
                 a.acc_stages = fit >= 8 ? 8 : (fit >= 4 ? 4 : 2);
                 if (getenv("B200_PATCH_ACC")) { int f = atoi(getenv("B200_PATCH_ACC")); if (f >= 1 && f < a.acc_stages) a.acc_stages = f; }
