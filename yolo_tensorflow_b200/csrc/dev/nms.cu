@@ -16,7 +16,7 @@
 // change a comparison: keep-lists are bit-exact against the CPU path when fed the same boxes.
 #include "kernels.h"
 
-#define NMS_THREADS 256
+#define NMS_THREADS 1024                     // the general kernel serves the few very heavy classes (thousands of survivors): one unit per CTA, so CTA width is what parallelises it
 #define NMS_SMEM_M 512                       // survivors per class whose IoU bit-matrix lives in shared memory
 #define host_smem_work_bytes (512 * 28 + 512 * 16 * 4 + 64)   // == host_work_bytes(NMS_SMEM_M): size of the smem work area
 
