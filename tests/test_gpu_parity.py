@@ -654,6 +654,28 @@ def test_zero_copy_concat_equals_copying_route(dn, workdir):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("model,size,batch,probe", [("yolov3-tiny", 160, 3, (1, 2, 16, 23)), ("yolov2", 160, 2, (1, 2, 31)), ("yolov3-tiny", 416, 8, (1, 23))])
+def test_stem_maxpool_fusion_is_exact(dn, model, size, batch, probe, workdir):
+    """stem -> [maxpool] 2/2 pooled by the stem kernel's store warp (default) == the separate maxpool kernel
+    (B200_NO_POOL_FUSION): identical bits in the maxpool layer's buffer and everything downstream; also through the chunked
+    host-to-device path that launches the stem per chunk"""
+    x = synth.make_images(batch, 3, size, size, 8)
+    outs = []
+    for env in (None, "1"):
+        if env:
+            os.environ["B200_NO_POOL_FUSION"] = env
+        try:
+            net, _, _ = open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
+        finally:
+            os.environ.pop("B200_NO_POOL_FUSION", None)
+        assert (net.kernel(0) == "conv_stem+maxpool" and net.kernel(1) == "fused") == (env is None)
+        net.predict(x)
+        outs.append([net.layer_output(i) for i in probe])
+        net.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_conv_upsample_fusion_is_exact(dn, workdir):
     """[convolutional] -> [upsample] with the four copies written by the conv's store warp (default) == the separate upsample
     kernel (B200_NO_UPSAMPLE_FUSION): identical bits in the upsample layers' buffers and in the heads"""

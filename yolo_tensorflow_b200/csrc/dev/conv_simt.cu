@@ -268,12 +268,13 @@ static bool try_stem_fast(const float *in_nchw, int n, int h, int w, int c, TVie
     return true;
 }
 
-void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
+void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s, const TView *pool_out)
 {
-    if (launch_conv_stem_tc(in_nchw, n, h, w, c, out, p, s)) {     // bf16 3x3 stride-1 stems: tcgen05 (conv_stem_tc.cu)
+    if (launch_conv_stem_tc(in_nchw, n, h, w, c, out, p, s, pool_out)) {     // bf16 3x3 stride-1 stems: tcgen05 (conv_stem_tc.cu)
         B200_LAUNCHED();
         return;
     }
+    if (pool_out) { fprintf(stderr, "b200-darknet: internal error: fused stem + maxpool plan without a tcgen05 stem\n"); abort(); }
     if (out.dtype == DT_F32 ? try_stem_const<float, true>(in_nchw, n, h, w, c, out, p, s)
                             : try_stem_const<bf16, false>(in_nchw, n, h, w, c, out, p, s)) {
         B200_LAUNCHED();

@@ -33,6 +33,7 @@ struct StemTcArgs {
     int N, H, W, ldo, act;
     int tiles_x, tiles_y, num_tiles;
     int pack;                               // TMA kernel: pixels per 128-byte output row (dense outputs), 1 = one pixel per row
+    int pool;                               // TMA kernel: 1 = the store warp 2x2-max-pools every tile and stores only the pooled tensor
 };
 
 struct Walk {                               // tile = first, first + step, ... -> (tx, ty, n) without a division per tile
@@ -230,7 +231,7 @@ constexpr int kThreads2 = 19 * 32;
 
 struct alignas(64) StemTcMaps { CUtensorMap in, out; };
 
-template <int NOUT>
+template <int NOUT, bool POOL>                 // POOL: fused [maxpool] 2/2 (compile-time: the plain stem pays nothing for it)
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArgs a)
 {
@@ -312,7 +313,8 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i, t.next(a.tiles_x, a.tiles_y)) {
                 const int cs = i % kOutSlots;
                 STEM_WAIT(&cwritten[cs], (i / kOutSlots) & 1);
-                tma_store_4d(&maps.out, sC[cs], 0, t.tx * kTW / a.pack, t.ty * kTH, t.tn);
+                if constexpr (POOL) tma_store_4d(&maps.out, sC[cs], 0, t.tx * (kTW / 2), t.ty * (kTH / 2), t.tn);      // 16 x 2 pooled pixels
+                else tma_store_4d(&maps.out, sC[cs], 0, t.tx * kTW / a.pack, t.ty * kTH, t.tn);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 mbar_arrive(&cempty[cs]);
@@ -323,7 +325,10 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
         // ===================================== window gather (two groups of 4 warps) ================================
         const int g = (warp - 3) >> 2;
         const int r = ((warp - 3) & 3) * 32 + lane;
-        const int px = r % kTW, py = r / kTW;
+        // GEMM row -> pixel of the 32 x 4 tile.  Plain: row-major.  Fused max-pool: quad-major, so that the four pixels of every
+        // 2x2 window sit in four neighbouring TMEM lanes = four neighbouring lanes of ONE epilogue warp (shuffles do the max)
+        int px = r % kTW, py = r / kTW;
+        if constexpr (POOL) { const int w4 = r >> 5, l = r & 31; px = 2 * ((l >> 2) + 8 * (w4 & 1)) + (l & 1); py = 2 * (w4 >> 1) + ((l >> 1) & 1); }
         const uint32_t sw = (uint32_t)(r >> 1) & 3u;
         int i = g;
         for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2) {
@@ -371,6 +376,11 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
         const int px = r % kTW, py = r / kTW;
         const uint32_t prow = (uint32_t)(py * (kTW / a.pack) + px / a.pack);
         const uint32_t pchunk0 = (uint32_t)(px % a.pack) * (NOUT / 8);
+        // fused [maxpool] 2/2 (maxpool_layer.c:79-114): rows are quad-major (see the gather), lanes 4q..4q+3 hold one 2x2 window;
+        // the max of the four activations is taken with two shuffles and lane 4q stores pooled pixel (qx, qy) of the 16 x 2 tile.
+        // max and bf16 rounding commute (rounding is monotonic): bit-identical to pooling the stored bf16 tensor.
+        const uint32_t qrow = (uint32_t)((quarter >> 1) * (kTW / 2) + (lane >> 2) + 8 * (quarter & 1));
+        const uint32_t qswz = NOUT == 32 ? ((qrow >> 1) & 3u) : ((qrow >> 2) & 1u);
         int i = g;
         for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, i += 2) {
             const int acc = i % kAcc, cs = i % kOutSlots;
@@ -384,7 +394,7 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             STEM_WAIT(&cempty[cs], ((i / kOutSlots) & 1) ^ 1);
-            const uint32_t row_addr = smem_u32(sC[cs]) + (a.pack > 1 ? prow * 128u : (uint32_t)r * ROWB);
+            const uint32_t row_addr = smem_u32(sC[cs]) + (POOL ? qrow * ROWB : (a.pack > 1 ? prow * 128u : (uint32_t)r * ROWB));
 #pragma unroll
             for (int c = 0; c < NOUT; c += 8) {
                 float o[8];
@@ -402,7 +412,19 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
                 }
                 uint4 pk;
                 pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-                sts128(row_addr + (a.pack > 1 ? (((pchunk0 + (uint32_t)(c >> 3)) ^ (prow & 7u)) << 4) : (((uint32_t)(c >> 3) ^ swz) << 4)), pk);
+                if constexpr (POOL) {                      // max over the 2x2 window on the packed pairs: 2 shuffles per word
+                    uint32_t *pw = reinterpret_cast<uint32_t *>(&pk);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t o1 = __shfl_xor_sync(0xffffffffu, pw[q], 1);
+                        __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&pw[q]), *reinterpret_cast<__nv_bfloat162 *>(&o1));
+                        pw[q] = *reinterpret_cast<uint32_t *>(&m);
+                        uint32_t o2 = __shfl_xor_sync(0xffffffffu, pw[q], 2);
+                        m = __hmax2(*reinterpret_cast<__nv_bfloat162 *>(&pw[q]), *reinterpret_cast<__nv_bfloat162 *>(&o2));
+                        pw[q] = *reinterpret_cast<uint32_t *>(&m);
+                    }
+                    if ((lane & 3) == 0) sts128(row_addr + ((((uint32_t)(c >> 3)) ^ qswz) << 4), pk);
+                } else sts128(row_addr + (a.pack > 1 ? (((pchunk0 + (uint32_t)(c >> 3)) ^ (prow & 7u)) << 4) : (((uint32_t)(c >> 3) ^ swz) << 4)), pk);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -627,20 +649,20 @@ conv_stem_tc_gen_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
 }
 
 // tensor maps depend on the buffers only: cache the last few (the chunked H2D path launches the stem per chunk)
-struct MapCacheEntry { const void *in; void *out; int n, h, w, c, ld, pack, pw, ph; StemTcMaps maps; };
+struct MapCacheEntry { const void *in; void *out; int n, h, w, c, ld, pack, pw, ph, pooled; StemTcMaps maps; };
 static MapCacheEntry g_maps[16];
 static int g_maps_used = 0, g_maps_next = 0;
 
-static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView out, int pack, int pw = kPW, int ph = kPH)
+static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView out, int pack, int pw = kPW, int ph = kPH, int pooled = 0)
 {
     for (int i = 0; i < g_maps_used; ++i) {
         const MapCacheEntry &e = g_maps[i];
-        if (e.in == in && e.out == out.p && e.n == n && e.h == h && e.w == w && e.c == out.c && e.ld == out.ld && e.pack == pack && e.pw == pw && e.ph == ph) return &e.maps;
+        if (e.in == in && e.out == out.p && e.n == n && e.h == h && e.w == w && e.c == out.c && e.ld == out.ld && e.pack == pack && e.pw == pw && e.ph == ph && e.pooled == pooled) return &e.maps;
     }
     MapCacheEntry &e = g_maps[g_maps_next];
     g_maps_next = (g_maps_next + 1) % 16;
     if (g_maps_used < 16) ++g_maps_used;
-    e.in = in; e.out = out.p; e.n = n; e.h = h; e.w = w; e.c = out.c; e.ld = out.ld; e.pack = pack; e.pw = pw; e.ph = ph;
+    e.in = in; e.out = out.p; e.n = n; e.h = h; e.w = w; e.c = out.c; e.ld = out.ld; e.pack = pack; e.pw = pw; e.ph = ph; e.pooled = pooled;
     {
         unsigned long long dims[4] = {(unsigned long long)w, (unsigned long long)h, 3ull, (unsigned long long)n};
         unsigned long long strides[3] = {(unsigned long long)w * 4, (unsigned long long)h * w * 4, (unsigned long long)3 * h * w * 4};
@@ -653,6 +675,7 @@ static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView o
         unsigned long long dims[4] = {(unsigned long long)out.c * pack, ow / pack, oh, (unsigned long long)n};
         unsigned long long strides[3] = {(unsigned long long)out.ld * 2 * pack, ow * out.ld * 2, oh * ow * out.ld * 2};
         unsigned box[4] = {(unsigned)out.c * pack, (unsigned)(kTW / pack), kTH, 1};
+        if (pooled) { box[1] = kTW / 2; box[2] = kTH / 2; }      // `out` is the pooled tensor: a tile is 16 x 2 of its pixels
         tc_encode_tiled(&e.maps.out, 0, 4, out.p, dims, strides, box, out.c * 2 * pack);
     }
     return &e.maps;
@@ -661,7 +684,16 @@ static const StemTcMaps *stem_maps(const float *in, int n, int h, int w, TView o
 }  // namespace
 
 // true when the layer was launched here; false -> caller uses the CUDA-core stem
-bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s)
+// which stems the tcgen05 kernels take with the [maxpool] 2/2 that follows fused in (checked by the planner before it drops the
+// conv's own output buffer from the schedule)
+bool conv_stem_tc_pool_supported(int h, int w, int c, TView out, ConvParams p)
+{
+    return !getenv("B200_STEM_SIMT") && !getenv("B200_STEM_LDG") && !getenv("B200_NO_POOL_FUSION") && out.dtype == DT_BF16 && c == 3 &&
+           p.size == 3 && p.stride == 1 && p.pad == 1 && out.c == p.cout_pad && (out.c == 16 || out.c == 32) && out.h == h && out.w == w &&
+           w % 4 == 0 && h % 2 == 0 && (p.act == ACT_LEAKY || p.act == ACT_LINEAR);
+}
+
+bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s, const TView *pool_out)
 {
     if (getenv("B200_STEM_SIMT")) return false;
     if (out.dtype == DT_BF16 && c == 3 && p.size == 7 && p.stride == 2 && p.pad == 3 && out.c == 64 && p.cout_pad == 64 &&
@@ -670,7 +702,7 @@ bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView
         using G = StemGeom<7, 2>;                                   // YOLOv1's first layer
         StemTcArgs a;
         a.in = in_nchw; a.out = (bf16 *)out.p; a.w = (const bf16 *)p.w; a.scale = p.scale; a.shift = p.shift;
-        a.N = n; a.H = h; a.W = w; a.ldo = out.ld; a.act = p.act; a.pack = 1;
+        a.N = n; a.H = h; a.W = w; a.ldo = out.ld; a.act = p.act; a.pack = 1; a.pool = 0;
         a.tiles_x = div_up(out.w, kTW); a.tiles_y = div_up(out.h, kTH);
         a.num_tiles = a.tiles_x * a.tiles_y * n;
         const StemTcMaps *maps = stem_maps(in_nchw, n, h, w, out, 1, G::PW, G::PH);
@@ -700,16 +732,23 @@ bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView
     const long long tiles = (long long)a.tiles_x * a.tiles_y * n;
     if (tiles > 0x7fffffff) return false;
     a.num_tiles = (int)tiles;
-    a.pack = 1;
+    a.pack = 1; a.pool = 0;
     const int grid = a.num_tiles < 148 ? a.num_tiles : 148;
     if (w % 4 == 0 && ((uintptr_t)in_nchw & 15) == 0 && !getenv("B200_STEM_LDG")) {
         a.pack = (out.ld == out.c && w % (64 / out.c) == 0 && !getenv("B200_STEM_NOPACK")) ? 64 / out.c : 1;
-        const StemTcMaps *maps = stem_maps(in_nchw, n, h, w, out, a.pack);
-        const size_t smem = 1024 + kSlots * 8192 + kOutSlots * 8192 + kPatches * kPatchPitch + 2048;
+        const StemTcMaps *maps;
+        if (pool_out) {                                       // fused [maxpool]: only the pooled tensor is written
+            a.pool = 1; a.pack = 1;
+            TView pv = *pool_out;
+            maps = stem_maps(in_nchw, n, h, w, pv, 1, kPW, kPH, 1);
+        } else maps = stem_maps(in_nchw, n, h, w, out, a.pack);
+        const size_t smem = 1024 + kSlots * 8192 + kOutSlots * 8192 + 2048 + (kPatches * kPatchPitch + 1023) / 1024 * 1024;
         static bool configured = false;
         if (!configured) {
-            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CHECK(cudaFuncSetAttribute(conv_stem_tc_tma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
         cudaLaunchConfig_t cfg = {};
@@ -718,10 +757,14 @@ bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = getenv("B200_NO_PDL") ? 0 : 1;
-        if (out.c == 32) B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<32>, *maps, a));
-        else B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<16>, *maps, a));
+        if (a.pool) {
+            if (out.c == 32) B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<32, true>, *maps, a));
+            else B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<16, true>, *maps, a));
+        } else if (out.c == 32) B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<32, false>, *maps, a));
+        else B200_CHECK(cudaLaunchKernelEx(&cfg, conv_stem_tc_tma_kernel<16, false>, *maps, a));
         return true;
     }
+    if (pool_out) return false;                               // the LDG fallback has no pooled store: the caller runs the layers separately
     if (out.c == 32) conv_stem_tc_kernel<32><<<grid, kThreads, 0, s>>>(a);
     else conv_stem_tc_kernel<16><<<grid, kThreads, 0, s>>>(a);
     return true;

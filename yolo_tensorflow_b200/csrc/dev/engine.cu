@@ -35,6 +35,8 @@ struct DevLayer {
     bool fused_away;           // shortcut executed inside the previous conv's epilogue
     bool up_fused;             // conv that writes its result 2x upsampled straight into the following [upsample]'s buffer
     bool up_away;              // [upsample] performed by the previous conv's store warp
+    bool pool_fused;           // stem conv whose store warp also performs the following [maxpool] 2/2 (its own output is not written)
+    bool pool_away;            // [maxpool] performed inside the stem kernel
     bool block_head;           // 1x1 conv computed inside the following 3x3's kernel (fused residual block): launches nothing
     std::string kernel;
 };
@@ -393,7 +395,20 @@ static void build_engine_device_state(b200_engine *e, network *net)
             }
             break;
         }
-        case MAXPOOL: d.kernel = "maxpool"; break;
+        case MAXPOOL: {
+            d.kernel = "maxpool";
+            // stem -> [maxpool] size 2 stride 2 (YOLOv2, YOLOv3-tiny): pooled by the stem kernel's store warp
+            if (i == 1 && e->fusion && e->precision == B200_PREC_BF16 && e->L[0].stem && !e->L[0].stem_kpad && cons[0].size() == 1 &&
+                l.size == 2 && l.stride == 2 && l.out_w * 2 == l.w && l.out_h * 2 == l.h && d.out.ld == d.out.c) {
+                const layer &c0 = net->layers[0];
+                ConvParams p0{c0.size, c0.stride, c0.pad, act_id(c0.activation), e->L[0].w, e->L[0].scale, e->L[0].shift, e->L[0].cout_pad};
+                if (conv_stem_tc_pool_supported(c0.h, c0.w, c0.c, e->L[0].out, p0)) {
+                    e->L[0].pool_fused = true; d.pool_away = true;
+                    e->L[0].kernel = "conv_stem+maxpool"; d.kernel = "fused";
+                }
+            }
+            break;
+        }
         case UPSAMPLE: d.kernel = d.up_away ? "fused" : "upsample"; break;
         case SHORTCUT: d.kernel = d.fused_away ? "fused" : "shortcut"; break;
         case REORG: d.kernel = "reorg"; break;
@@ -481,7 +496,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; d.fc_tmp = nullptr; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; d.fc_tmp = nullptr; d.pool_fused = false; d.pool_away = false; }
     e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->d_input_next = nullptr; e->submitted = 0; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
@@ -648,12 +663,17 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
         if (d.stem && d.tc && e->conv_backend == 0) {
             launch_stem_im2col(e->d_input, batch, l.h, l.w, l.c, d.stem_cols, l.out_h, l.out_w, d.stem_kpad, l.size, l.stride, l.pad, s);
             launch_conv_tc(d.tc, s);
-        } else if (d.stem) launch_conv_stem(e->d_input, batch, l.h, l.w, l.c, out, p, s);
+        } else if (d.stem) {
+            TView pool = d.pool_fused ? view_of(e->L[1], batch) : TView{nullptr, 0, 0, 0, 0, 0, 0};
+            launch_conv_stem(e->d_input, batch, l.h, l.w, l.c, out, p, s, d.pool_fused && e->conv_backend == 0 ? &pool : nullptr);
+        }
         else if (d.tc && e->conv_backend == 0) launch_conv_tc(d.tc, s);
         else launch_conv_simt(in, out, p, s);
         break;
     }
-    case MAXPOOL: launch_maxpool(in, out, l.size, l.stride, l.pad, s); break;
+    case MAXPOOL:
+        if (!d.pool_away || e->conv_backend != 0) launch_maxpool(in, out, l.size, l.stride, l.pad, s);
+        break;
     case UPSAMPLE:
         if (!d.up_away || e->conv_backend != 0) launch_upsample(in, out, l.stride, l.scale, s);
         break;
@@ -754,7 +774,10 @@ static int stage_input(b200_engine *e, network *net, const float *input)
         TView out = d0.out;
         out.n = per;
         out.p = (unsigned char *)d0.out.p + k * out_stride;
-        launch_conv_stem(e->d_input + k * in_stride, per, l0.h, l0.w, l0.c, out, p, e->stream);
+        TView pool = e->L[d0.pool_fused ? 1 : 0].out;
+        pool.n = per;
+        pool.p = (unsigned char *)pool.p + (size_t)k * per * pool.h * pool.w * pool.ld * dt_size(pool.dtype);
+        launch_conv_stem(e->d_input + k * in_stride, per, l0.h, l0.w, l0.c, out, p, e->stream, d0.pool_fused ? &pool : nullptr);
     }
     return 1;
 }
@@ -800,7 +823,7 @@ extern "C" void b200_set_conv_backend(network *net, int backend)
 {
     b200_engine *e = b200_engine_of(net);
     for (auto &d : e->L)
-        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0 || d.block_head || d.up_fused)) {
+        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0 || d.block_head || d.up_fused || d.pool_fused)) {
             fprintf(stderr, "b200-darknet: the CUDA-core conv backend needs an unfused plan (parse with B200_FUSE=0 B200_STEM_SIMT=1)\n");
             abort();
         }
@@ -815,6 +838,11 @@ static void need_materialised(const b200_engine *e, int i)
 {
     if (e->L[i].block_head) {
         fprintf(stderr, "b200-darknet: layer %d's output is not materialised: it is computed inside the fused residual block kernel of layer %d. "
+                        "Parse with B200_FUSE=0 (or b200_set_default_fusion(0)) to inspect it.\n", i, i + 1);
+        abort();
+    }
+    if (e->L[i].pool_fused) {
+        fprintf(stderr, "b200-darknet: layer %d's output is not materialised: the stem kernel stores it max-pooled into layer %d's buffer. "
                         "Parse with B200_FUSE=0 (or b200_set_default_fusion(0)) to inspect it.\n", i, i + 1);
         abort();
     }

@@ -37,7 +37,7 @@ struct ConvParams {
     int cout_pad;           // rows in w (multiple of 16 for the tcgen05 path)
 };
 // first-layer kernel: reads the fp32 NCHW network input directly (fuses the layout/precision conversion)
-void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);
+void launch_conv_stem(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s, const TView *pool_out = nullptr);
 // device-side letterbox_image + resize_image (+ uint8 HWC -> fp32 CHW): image.c:960-979, 1347-1390, 1442-1464
 struct LetterboxItem {
     size_t src_off;              // byte offset of the image in the raw buffer
@@ -46,7 +46,9 @@ struct LetterboxItem {
     float w_scale, h_scale;      // (sw-1)/(nw-1), (sh-1)/(nh-1) as the reference computes them (float division)
 };
 void launch_letterbox(const unsigned char *raw, int src_is_u8_hwc, const LetterboxItem *items_dev, int n, float *dst_nchw, int w, int h, cudaStream_t s);
-bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s);   // false: shape not covered
+bool launch_conv_stem_tc(const float *in_nchw, int n, int h, int w, int c, TView out, ConvParams p, cudaStream_t s,
+                         const TView *pool_out = nullptr);   // false: shape not covered; pool_out: fused [maxpool] 2/2 output
+bool conv_stem_tc_pool_supported(int h, int w, int c, TView out, ConvParams p);
 void conv_stem_invalidate_bank();      // call after the stem's weights changed in place (load_weights)
 // CUDA-core implicit-GEMM (fp32 accumulate); the fp32-exact path and the fallback for odd shapes
 void launch_conv_simt(TView in, TView out, ConvParams p, cudaStream_t s);
