@@ -54,6 +54,9 @@ struct b200_engine {
     float *d_input_next;       // spare input buffer: b200_submit_batch copies batch k+1 here while batch k computes
     cudaEvent_t submit_done;
     int submitted;
+    cudaStream_t d2h_stream;   // serving loop: results of batch k are read back here while batch k+1 already computes
+    cudaEvent_t tail_done;     // decode + NMS + collect of the current batch finished (d2h_stream waits on it)
+    int fwd_enqueued;          // the submitted batch's forward pass is already in the compute stream (b200_detect_submitted)
     TView in_view;             // NHWC copy of the input (only when layer 0 is not a stem conv)
     unsigned char *arena;      // parameters
     size_t arena_bytes;
@@ -161,6 +164,9 @@ static void build_engine_device_state(b200_engine *e, network *net)
     e->d_input = (float *)dev_alloc((size_t)e->cap * net->inputs * sizeof(float));
     e->d_input_next = nullptr;                                    // allocated on the first b200_submit_batch
     B200_CHECK(cudaEventCreateWithFlags(&e->submit_done, cudaEventDisableTiming));
+    B200_CHECK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    B200_CHECK(cudaEventCreateWithFlags(&e->tail_done, cudaEventDisableTiming));
+    e->fwd_enqueued = 0;
     e->submitted = 0;
     size_t max_floats = (size_t)e->cap * net->inputs;
 
@@ -541,7 +547,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaFree(e->d_raw); cudaFree(e->d_lb_items); cudaFree(e->d_im_dims);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
         for (auto &ev : e->copy_done) cudaEventDestroy(ev);
-        cudaStreamDestroy(e->copy_stream);
+        cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaEventDestroy(e->tail_done);
         cudaStreamDestroy(e->stream);
     }
     delete e;
@@ -1045,15 +1051,19 @@ extern "C" int b200_engine_decode_image(b200_engine *e, network *net, int image,
 
 extern "C" int b200_engine_classes(b200_engine *e) { return e->classes; }
 
+// forward (from layer `first`; first = net->n: the forward pass is already in the stream) + decode + NMS + collect, all
+// enqueued on the compute stream; `after_tail` (optional) runs once they are enqueued and before the host waits, so that the
+// caller can put the NEXT batch's work behind them; the results then come back on their own stream while that work runs.
+template <typename F>
 static int detect_core(b200_engine *e, network *net, int first, int w, int h, float thresh, float nms_thresh, int relative,
-                       b200_det *out, int max_out, int *counts)
+                       b200_det *out, int max_out, int *counts, F after_tail)
 {
     int batch = logical_batch(e, net);
     // with head sync off nobody reads l.output of the heads: skip forward_yolo_layer and decode from the head convolutions'
     // fp32 logits (identical arithmetic: the logistic is evaluated on the fly for the objectness test and for survivors)
     const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
     forward_layers(e, net, first, net->n, use_raw != 0);
-    if (e->heads.empty()) { B200_CHECK(cudaStreamSynchronize(e->stream)); return 0; }
+    if (e->heads.empty()) { after_tail(); B200_CHECK(cudaStreamSynchronize(e->stream)); return 0; }
     ensure_candidates(e, e->cap);
     if (e->records_cap < max_out) {
         cudaFree(e->d_records);
@@ -1070,16 +1080,27 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
     B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));
     launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
                    e->d_records, max_out, e->d_record_count, e->stream);
+    B200_CHECK(cudaEventRecord(e->tail_done, e->stream));
+    after_tail();
+    B200_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->tail_done, 0));
     int n = 0;
-    B200_CHECK(cudaMemcpyAsync(&n, e->d_record_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    if (counts) B200_CHECK(cudaMemcpyAsync(counts, e->cand.count, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    B200_CHECK(cudaStreamSynchronize(e->stream));
+    B200_CHECK(cudaMemcpyAsync(&n, e->d_record_count, sizeof(int), cudaMemcpyDeviceToHost, e->d2h_stream));
+    if (counts) B200_CHECK(cudaMemcpyAsync(counts, e->cand.count, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, e->d2h_stream));
+    B200_CHECK(cudaStreamSynchronize(e->d2h_stream));
     if (n > max_out) n = max_out;
     static_assert(sizeof(DetRecord) == sizeof(b200_det), "record layouts must match");
     if (n > 0) {
-        B200_CHECK(cudaMemcpyAsync(out, e->d_records, (size_t)n * sizeof(DetRecord), cudaMemcpyDeviceToHost, e->stream));
-        B200_CHECK(cudaStreamSynchronize(e->stream));
+        B200_CHECK(cudaMemcpyAsync(out, e->d_records, (size_t)n * sizeof(DetRecord), cudaMemcpyDeviceToHost, e->d2h_stream));
+        B200_CHECK(cudaStreamSynchronize(e->d2h_stream));
     }
+    return n;
+}
+
+static int detect_core(b200_engine *e, network *net, int first, int w, int h, float thresh, float nms_thresh, int relative,
+                       b200_det *out, int max_out, int *counts)
+{
+    int n = detect_core(e, net, first, w, h, thresh, nms_thresh, relative, out, max_out, counts, [] {});
+    B200_CHECK(cudaStreamSynchronize(e->stream));       // synchronous callers expect the engine idle on return
     return n;
 }
 
@@ -1182,11 +1203,25 @@ extern "C" int b200_detect_submitted(network *net, const float *next_input, int 
     b200_engine *e = b200_engine_of(net);
     need_device(e, "b200_detect_submitted");
     if (!e->submitted) { fprintf(stderr, "b200-darknet: b200_detect_submitted without a submitted batch\n"); abort(); }
-    float *t = e->d_input; e->d_input = e->d_input_next; e->d_input_next = t;      // the submitted batch becomes current
-    e->submitted = 0;
-    B200_CHECK(cudaStreamWaitEvent(e->stream, e->submit_done, 0));
-    if (next_input) b200_submit_batch(net, next_input);                              // prefetch the following batch under this compute
-    return detect_core(e, net, 0, w, h, thresh, nms_thresh, relative, out, max_out, counts);
+    int first = net->n;                                                              // forward already enqueued by the previous call?
+    if (!e->fwd_enqueued) {
+        float *t = e->d_input; e->d_input = e->d_input_next; e->d_input_next = t;    // the submitted batch becomes current
+        B200_CHECK(cudaStreamWaitEvent(e->stream, e->submit_done, 0));
+        first = 0;
+    }
+    e->submitted = 0; e->fwd_enqueued = 0;
+    // Once this batch's decode / NMS / collect are in the stream, the NEXT batch's copy is submitted and its whole forward pass
+    // is enqueued behind them; the results of this batch are then read back on a separate stream while that forward runs.
+    // (Waiting for the results first left the GPU idle for the two D2H round trips: ~0.25 ms of every 5 ms step.)
+    return detect_core(e, net, first, w, h, thresh, nms_thresh, relative, out, max_out, counts, [&] {
+        if (!next_input) return;
+        b200_submit_batch(net, next_input);
+        float *t = e->d_input; e->d_input = e->d_input_next; e->d_input_next = t;
+        B200_CHECK(cudaStreamWaitEvent(e->stream, e->submit_done, 0));
+        const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
+        forward_layers(e, net, 0, net->n, use_raw != 0);
+        e->fwd_enqueued = 1;
+    });
 }
 
 // device NMS on caller-provided host arrays (the kernel behind do_nms_sort / do_nms_obj)
