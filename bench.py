@@ -19,6 +19,7 @@ PyTorch is used for torch.distributed (NCCL weight broadcast, barriers), pinned 
 on the engine's stream; every kernel in the timed region is this repo's own.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -219,8 +220,22 @@ def main_engine(args):
     out = (dn.B200_DET * max_out)()
     counts = (dn.c_int * BATCH)()
 
+    # value: the batch stays resident in HBM; every step is a full forward + decode + NMS + collect + read-back of its records.
+    # The steps run through the same one-deep pipelined call as the serving loop (the next step's forward is enqueued before
+    # this step's records are awaited), with B200_INPUT_RESIDENT instead of a host batch.
+    RESIDENT = ctypes.c_void_p(1)
+    resident_state = {"primed": False}
+
     def step_resident():
-        return dn.lib.b200_detect_batch(net.ptr, None, SIZE, SIZE, THRESH, NMS, 1, out, max_out, counts)
+        if not resident_state["primed"]:
+            dn.lib.b200_submit_batch(net.ptr, RESIDENT)
+            resident_state["primed"] = True
+        return dn.lib.b200_detect_submitted(net.ptr, RESIDENT, SIZE, SIZE, THRESH, NMS, 1, out, max_out, counts)
+
+    def drain_resident():
+        if resident_state["primed"]:
+            dn.lib.b200_detect_submitted(net.ptr, None, SIZE, SIZE, THRESH, NMS, 1, out, max_out, counts)
+            resident_state["primed"] = False
 
     # e2e: the serving loop a user of the C API runs — every step H2D-copies its own pinned host batch and D2H-reads its
     # detections; the copy of batch k+1 is submitted before batch k is computed (double-buffered device input)
@@ -269,6 +284,7 @@ def main_engine(args):
         sampler.window_end()
     cand = float(np.mean(list(counts)))
     value = world * BATCH * args.steps / (ms / 1000.0)
+    drain_resident()                                  # the forward pass pre-enqueued for a step that will not come
 
     dn.lib.b200_submit_batch(net.ptr, host_batches[0].data_ptr())      # prime the pipeline: every timed step still copies one batch
     for _ in range(2):
@@ -323,6 +339,7 @@ def main_engine(args):
                 "config": {"workload": f"YOLOv3 {SIZE}x{SIZE} batch {BATCH} per GPU, bf16 activations, fp32 accumulate; step = forward + decode + NMS",
                            "thresh": THRESH, "nms": NMS, "mean_candidates_per_image": cand, "kept_records_per_step": total_records,
                            "l2": "working set per step (133 MB input + >5 GB activations) exceeds the 126 MB L2; no explicit flush",
+                           "pipelining": "value and e2e both use b200_detect_submitted: step k+1's forward is enqueued before step k's records are awaited (value: B200_INPUT_RESIDENT, e2e: pinned host batches)",
                            "weights": "seed-0 synthetic, damped heads (yolo_tensorflow_b200/synth.py)",
                            "multi_gpu": "image-sharded, weights NCCL-broadcast once, no per-layer collective"},
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,

@@ -135,6 +135,14 @@ int b200_detect_batch(network *net, const float *input, int w, int h, float thre
  *     submit(b[0]); for k: n = detect_submitted(b[k+1], ...)      -> results of b[k]
  * so the PCIe copy of batch k+1 hides under the compute of batch k.  A host buffer must stay valid until the call that
  * returns ITS results has returned. */
+/* B200_INPUT_RESIDENT as `input` / `next_input`: nothing is copied from the host — the batch is what the engine's device
+ * input buffer holds when the call is made (b200_letterbox_batch* writes there), and its forward pass is enqueued by that
+ * call.  The loop
+ *   b200_letterbox_batch_u8(batch 0); b200_submit_batch(net, B200_INPUT_RESIDENT);
+ *   for k: b200_letterbox_batch_u8(batch k+1); b200_detect_submitted(net, B200_INPUT_RESIDENT, ...)   -> records of batch k
+ * keeps the GPU busy across the result read-back exactly like the host-input loop; with w = h = 0 every batch's boxes are
+ * corrected with the image sizes of ITS letterbox call. */
+#define B200_INPUT_RESIDENT ((const float *)1)
 void b200_submit_batch(network *net, const float *input);
 int  b200_detect_submitted(network *net, const float *next_input, int w, int h, float thresh, float nms_thresh, int relative,
                            b200_det *out, int max_out, int *counts);

@@ -553,6 +553,32 @@ def test_letterboxed_batch_boxes_are_corrected_per_image(dn, workdir):
     net.close()
 
 
+def test_resident_input_serving_loop(dn, workdir):
+    """B200_INPUT_RESIDENT: the device-side preprocessing loop (letterbox batch k+1, then b200_detect_submitted returns batch k)
+    gives exactly the records of the synchronous calls"""
+    net, _, _ = open_net(dn, "yolov3-tiny", 3, 160, workdir, dn.PREC_BF16)
+    rng = np.random.default_rng(21)
+    batches = [[rng.integers(0, 256, (150 + 10 * k + 7 * i, 220 - 9 * i, 3), dtype=np.uint8) for i in range(3)] for k in range(3)]
+    want = []
+    for b in batches:
+        assert net.letterbox_batch_u8(b) == 0
+        want.append(net.detect_batch(None, 0, 0, .3, .45, relative=0))
+    RES = ctypes.c_void_p(1)
+    out = (dn.B200_DET * 100000)(); counts = (ctypes.c_int * 3)()
+    assert net.letterbox_batch_u8(batches[0]) == 0
+    dn.lib.b200_submit_batch(net.ptr, RES)
+    order = lambda r: r[np.lexsort((r["cls"], r["box_id"], r["image"]))]
+    for k in range(3):
+        if k < 2:
+            assert net.letterbox_batch_u8(batches[k + 1]) == 0       # stream-ordered after batch k's forward, before its tail
+        n = dn.lib.b200_detect_submitted(net.ptr, RES if k < 2 else None, 0, 0, .3, .45, 0, out, 100000, counts)
+        rec = np.ctypeslib.as_array(out)[:n].copy()
+        ref, ref_counts = want[k]
+        assert n == len(ref) and n > 0 and list(counts) == ref_counts.tolist()
+        assert order(rec).tobytes() == order(ref).tobytes()
+    net.close()
+
+
 def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
     net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
     x = synth.make_images(2, 3, 160, 160, 41)

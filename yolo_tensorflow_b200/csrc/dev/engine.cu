@@ -72,7 +72,8 @@ struct b200_engine {
     NmsScratch nms_scratch;
     DetRecord *d_records; int records_cap; int *d_record_count;
     unsigned char *d_raw; size_t raw_cap;            // b200_letterbox_batch*: source images on the device
-    LetterboxItem *d_lb_items; int *d_im_dims;       // per-image resize geometry / original sizes (box correction)
+    LetterboxItem *d_lb_items; int *d_im_dims[2];    // per-image resize geometry / original sizes (box correction):
+    int dims_cur, dims_pending;                      // [dims_cur] belongs to the batch whose forward pass was enqueued last, the other slot to the next letterbox call
     // host staging for one image's candidates
     float *h_box, *h_obj, *h_prob; int *h_id; int h_cap;
 };
@@ -509,7 +510,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     memset(&e->cand, 0, sizeof e->cand); e->cand_slots = 0;
     memset(&e->nms_scratch, 0, sizeof e->nms_scratch);
     e->d_records = nullptr; e->records_cap = 0; e->d_record_count = nullptr;
-    e->d_raw = nullptr; e->raw_cap = 0; e->d_lb_items = nullptr; e->d_im_dims = nullptr;
+    e->d_raw = nullptr; e->raw_cap = 0; e->d_lb_items = nullptr; e->d_im_dims[0] = e->d_im_dims[1] = nullptr; e->dims_cur = 0; e->dims_pending = 0;
     e->h_box = e->h_obj = e->h_prob = nullptr; e->h_id = nullptr; e->h_cap = 0;
     e->boxes_per_image = 0; e->classes = 0;
     // Parsing a cfg (layer table, shapes) works on a machine without a GPU; anything that computes does not.
@@ -544,7 +545,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
         cudaFree(e->cand.flags); cudaFree(e->cand.offsets); cudaFree(e->cand.cls_count);
         cudaFree(e->nms_scratch.mask); cudaFree(e->d_records); cudaFree(e->d_record_count);
-        cudaFree(e->d_raw); cudaFree(e->d_lb_items); cudaFree(e->d_im_dims);
+        cudaFree(e->d_raw); cudaFree(e->d_lb_items); cudaFree(e->d_im_dims[0]); cudaFree(e->d_im_dims[1]);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
         for (auto &ev : e->copy_done) cudaEventDestroy(ev);
         cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaEventDestroy(e->tail_done);
@@ -1054,6 +1055,12 @@ extern "C" int b200_engine_classes(b200_engine *e) { return e->classes; }
 // forward (from layer `first`; first = net->n: the forward pass is already in the stream) + decode + NMS + collect, all
 // enqueued on the compute stream; `after_tail` (optional) runs once they are enqueued and before the host waits, so that the
 // caller can put the NEXT batch's work behind them; the results then come back on their own stream while that work runs.
+// the sizes recorded by the last b200_letterbox_batch* call belong to the batch whose forward pass is enqueued next
+static void adopt_letterbox_dims(b200_engine *e)
+{
+    if (e->dims_pending) { e->dims_cur ^= 1; e->dims_pending = 0; }
+}
+
 template <typename F>
 static int detect_core(b200_engine *e, network *net, int first, int w, int h, float thresh, float nms_thresh, int relative,
                        b200_det *out, int max_out, int *counts, F after_tail)
@@ -1062,6 +1069,7 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
     // with head sync off nobody reads l.output of the heads: skip forward_yolo_layer and decode from the head convolutions'
     // fp32 logits (identical arithmetic: the logistic is evaluated on the fly for the objectness test and for survivors)
     const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
+    if (first < net->n) adopt_letterbox_dims(e);
     forward_layers(e, net, first, net->n, use_raw != 0);
     if (e->heads.empty()) { after_tail(); B200_CHECK(cudaStreamSynchronize(e->stream)); return 0; }
     ensure_candidates(e, e->cap);
@@ -1072,7 +1080,7 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
     }
     if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
     // w == h == 0: every image is corrected with its own original size, recorded by b200_letterbox_batch*
-    const int *im_dims = (w == 0 && h == 0) ? e->d_im_dims : nullptr;
+    const int *im_dims = (w == 0 && h == 0) ? e->d_im_dims[e->dims_cur] : nullptr;
     if (w == 0 && h == 0 && !im_dims) { fprintf(stderr, "b200-darknet: w = h = 0 needs a preceding b200_letterbox_batch call\n"); abort(); }
     launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, use_raw, e->cand, e->stream, im_dims);
     launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
@@ -1149,13 +1157,15 @@ static int letterbox_batch(network *net, const void *const *images, const int *w
         e->raw_cap = total;
     }
     if (!e->d_lb_items) e->d_lb_items = (LetterboxItem *)dev_alloc((size_t)e->cap * sizeof(LetterboxItem));
-    if (!e->d_im_dims) e->d_im_dims = (int *)dev_alloc(2 * (size_t)e->cap * sizeof(int));
+    for (int k = 0; k < 2; ++k)
+        if (!e->d_im_dims[k]) e->d_im_dims[k] = (int *)dev_alloc(2 * (size_t)e->cap * sizeof(int));
     for (int i = 0; i < n; ++i)
         B200_CHECK(cudaMemcpyAsync(e->d_raw + items[i].src_off, images[i], (size_t)widths[i] * heights[i] * 3 * esz, cudaMemcpyHostToDevice, e->stream));
     B200_CHECK(cudaMemcpyAsync(e->d_lb_items, items.data(), (size_t)n * sizeof(LetterboxItem), cudaMemcpyHostToDevice, e->stream));
-    B200_CHECK(cudaMemcpyAsync(e->d_im_dims, dims.data(), dims.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    B200_CHECK(cudaMemcpyAsync(e->d_im_dims[e->dims_cur ^ 1], dims.data(), dims.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     launch_letterbox(e->d_raw, u8, e->d_lb_items, n, e->d_input, net->w, net->h, e->stream);
     B200_CHECK(cudaStreamSynchronize(e->stream));           // items / dims live on this stack frame
+    e->dims_pending = 1;
     return 0;
 }
 
@@ -1190,6 +1200,13 @@ extern "C" void b200_submit_batch(network *net, const float *input)
     b200_engine *e = b200_engine_of(net);
     need_device(e, "b200_submit_batch");
     if (e->submitted) { fprintf(stderr, "b200-darknet: b200_submit_batch called twice without b200_detect_submitted\n"); abort(); }
+    if (input == B200_INPUT_RESIDENT) {          // the batch is whatever the input buffer holds now: its forward pass starts here
+        const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
+        adopt_letterbox_dims(e);
+        forward_layers(e, net, 0, net->n, use_raw != 0);
+        e->submitted = 1; e->fwd_enqueued = 1;
+        return;
+    }
     int batch = logical_batch(e, net);
     if (!e->d_input_next) e->d_input_next = (float *)dev_alloc((size_t)e->cap * net->inputs * sizeof(float));
     B200_CHECK(cudaMemcpyAsync(e->d_input_next, input, (size_t)batch * net->inputs * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
@@ -1205,7 +1222,7 @@ extern "C" int b200_detect_submitted(network *net, const float *next_input, int 
     if (!e->submitted) { fprintf(stderr, "b200-darknet: b200_detect_submitted without a submitted batch\n"); abort(); }
     int first = net->n;                                                              // forward already enqueued by the previous call?
     if (!e->fwd_enqueued) {
-        float *t = e->d_input; e->d_input = e->d_input_next; e->d_input_next = t;    // the submitted batch becomes current
+        float *t = e->d_input; e->d_input = e->d_input_next; e->d_input_next = t;        // the submitted batch becomes current
         B200_CHECK(cudaStreamWaitEvent(e->stream, e->submit_done, 0));
         first = 0;
     }
@@ -1216,9 +1233,11 @@ extern "C" int b200_detect_submitted(network *net, const float *next_input, int 
     return detect_core(e, net, first, w, h, thresh, nms_thresh, relative, out, max_out, counts, [&] {
         if (!next_input) return;
         b200_submit_batch(net, next_input);
+        if (next_input == B200_INPUT_RESIDENT) return;                                   // forward enqueued by the submit
         float *t = e->d_input; e->d_input = e->d_input_next; e->d_input_next = t;
         B200_CHECK(cudaStreamWaitEvent(e->stream, e->submit_done, 0));
         const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
+        adopt_letterbox_dims(e);
         forward_layers(e, net, 0, net->n, use_raw != 0);
         e->fwd_enqueued = 1;
     });
