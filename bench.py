@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks_event_reasons.active,power.draw,power.limit")
         # one streaming nvidia-smi (a line every 20 ms): the timed region is only ~0.1 s long, so polling a fresh process per
         # sample would see it once
         try:
@@ -91,8 +91,28 @@ class ClockSampler(threading.Thread):
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for j, n in enumerate(names) if any(len(r) > 2 + j and r[2 + j].lower().startswith("active") for r in self.rows)]
+        # every other bit of the event-reason mask seen under load (nvml: 0x1 idle, 0x2 application clocks, 0x10 sync boost,
+        # 0x80 power brake, 0x100 display clocks), so that clocks below max never come without their reason
+        other = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x10: "sync_boost", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        mask = 0
+        for r in self.rows:
+            try:
+                mask |= int(r[6], 16) if len(r) > 6 else 0
+            except ValueError:
+                pass
+        reasons += [n for bit, n in other.items() if mask & bit]
+
+        def med(col):
+            v = []
+            for r in self.rows:
+                try:
+                    v.append(float(r[col]))
+                except (ValueError, IndexError):
+                    pass
+            return sorted(v)[len(v) // 2] if v else None
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "sm_min_mhz": sm[0] if sm else None, "reasons": reasons, "samples": len(self.rows),
+                "power_w": med(7), "power_limit_w": med(8)}
 
 
 def prepare_files(batch):
