@@ -117,6 +117,15 @@ int  b200_append_voc(const char *prefix, const char *const *names, int classes, 
                      const int *widths, const int *heights);
 int  b200_append_imagenet(const char *path, b200_det *rec, int n, const int *image_ids, const int *widths, const int *heights);
 
+/* validate_detector (examples/detector.c:364-487) as a batched driver over m decoded images (RGB, HWC, 8 bit; paths[i] names
+ * image i): device letterbox, forward, boxes corrected with each image's own size (pixels), NMS, result files — net->batch
+ * images at a time through the pipelined serving loop.  eval "coco" -> <prefix>/<outfile|coco_results>.json, "imagenet" ->
+ * <prefix>/<outfile|imagenet-detection>.txt, anything else (or NULL) -> <prefix>/<outfile|comp4_det_test_><names[class]>.txt;
+ * the reference runs it with thresh .005 and nms .45 (:418-419).  Returns the number of records written, -1 on error. */
+int  b200_validate_images(network *net, const unsigned char *const *rgb_hwc, const int *widths, const int *heights,
+                          const char *const *paths, int m, const char *eval, const char *prefix, const char *outfile,
+                          const char *const *names, float thresh, float nms);
+
 /* Device-side preprocessing (the step before the path: letterbox_image + resize_image, image.c:960-979,1347-1390, and for
  * uint8 sources load_image_stb's HWC/255 conversion, image.c:1442-1464), bit-identical to the host functions.  n <= batch
  * images of individual sizes become the letterboxed network input in device memory; then call

@@ -579,6 +579,45 @@ def test_resident_input_serving_loop(dn, workdir):
     net.close()
 
 
+def test_validate_images_batched_driver(dn, workdir, tmp_path):
+    """b200_validate_images (validate_detector, examples/detector.c:364-487, batched and pipelined): the three result files
+    equal the oracle's writers fed with the records of one-image-at-a-time calls, as the reference's loop produces them"""
+    net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_BF16)
+    rng = np.random.default_rng(33)
+    m = 5                                                                # batches of 2, 2 and a short one
+    images = [rng.integers(0, 256, (120 + 23 * i, 260 - 31 * i, 3), dtype=np.uint8) for i in range(m)]
+    paths = ["/data/val2014/COCO_val2014_%012d.jpg" % (100 + 7 * i) for i in range(m)]
+    widths = [im.shape[1] for im in images]; heights = [im.shape[0] for im in images]
+    names = ["n%02d" % j for j in range(80)]
+    records = []
+    for i, im in enumerate(images):
+        assert net.letterbox_batch_u8([im]) == 0
+        rec, _ = net.detect_batch(None, 0, 0, .005, .45, relative=0)
+        for r in rec[rec["image"] == 0]:
+            records.append((i, int(r["box_id"]), int(r["cls"]), np.float32(r["prob"]), (r["bbox"]["x"], r["bbox"]["y"], r["bbox"]["w"], r["bbox"]["h"])))
+    assert len(records) > 50
+    for kind in ("coco", "imagenet", "voc"):
+        out = tmp_path / kind
+        out.mkdir()
+        n = net.validate_images(images, paths, kind, str(out), names=names)
+        assert n == len(records)
+        if kind == "coco":
+            body = P.print_cocos(records, paths, widths, heights)
+            assert (out / "coco_results.json").read_text() == "[\n" + body[:-2] + "\n]\n"
+        elif kind == "imagenet":
+            assert (out / "imagenet-detection.txt").read_text() == P.print_imagenet_detections(records, list(range(1, m + 1)), widths, heights)
+        else:
+            ids = [os.path.basename(p).split(".")[0] for p in paths]
+            voc = P.print_detector_detections(records, ids, widths, heights, 80)
+            for j, name in enumerate(names):
+                assert (out / ("comp4_det_test_%s.txt" % name)).read_text() == voc[j]
+    # the engine is idle again: the synchronous call still works
+    assert net.letterbox_batch_u8(images[:2]) == 0
+    rec, _ = net.detect_batch(None, 0, 0, .005, .45, relative=0)
+    assert len(rec) > 0
+    net.close()
+
+
 def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
     net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
     x = synth.make_images(2, 3, 160, 160, 41)

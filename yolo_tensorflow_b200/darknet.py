@@ -94,6 +94,9 @@ lib.b200_fetch_input.argtypes = [c_void_p, c_void_p, c_int]; lib.b200_fetch_inpu
 lib.b200_coco_image_id.argtypes = [c_char_p]; lib.b200_coco_image_id.restype = c_int
 lib.b200_append_coco.argtypes = [c_char_p, POINTER(B200_DET), c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_int)]; lib.b200_append_coco.restype = c_int
 lib.b200_append_voc.argtypes = [c_char_p, POINTER(c_char_p), c_int, POINTER(B200_DET), c_int, POINTER(c_char_p), POINTER(c_int), POINTER(c_int)]; lib.b200_append_voc.restype = c_int
+lib.b200_validate_images.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_char_p), c_int, c_char_p, c_char_p, c_char_p,
+                                     POINTER(c_char_p), c_float, c_float]
+lib.b200_validate_images.restype = c_int
 lib.b200_append_imagenet.argtypes = [c_char_p, POINTER(B200_DET), c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]; lib.b200_append_imagenet.restype = c_int
 lib.resize_network.argtypes = [c_void_p, c_int, c_int]; lib.resize_network.restype = c_int
 lib.b200_layer_info.argtypes = [c_void_p, c_int, POINTER(c_int)]; lib.b200_layer_info.restype = c_int
@@ -234,6 +237,17 @@ class Network:
         arrs = [np.ascontiguousarray(im, dtype=np.float32) for im in images]
         ims = (IMAGE * len(arrs))(*[IMAGE(a.shape[2], a.shape[1], 3, a.ctypes.data_as(POINTER(c_float))) for a in arrs])
         return lib.b200_letterbox_batch(self.ptr, ims, len(arrs))
+
+    def validate_images(self, images, paths, eval_type, prefix, outfile=None, names=None, thresh=.005, nms=.45):
+        """validate_detector (examples/detector.c:364-487) over decoded HxWx3 uint8 images, batched; returns the record count"""
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        m = len(imgs)
+        ptrs = (c_void_p * m)(*[im.ctypes.data for im in imgs])
+        ws = (c_int * m)(*[im.shape[1] for im in imgs]); hs = (c_int * m)(*[im.shape[0] for im in imgs])
+        cpaths = (c_char_p * m)(*[p.encode() for p in paths])
+        cnames = (c_char_p * len(names))(*[n.encode() for n in names]) if names else None
+        return lib.b200_validate_images(self.ptr, ptrs, ws, hs, cpaths, m, eval_type.encode() if eval_type else None, prefix.encode(),
+                                        outfile.encode() if outfile else None, cnames, thresh, nms)
 
     def fetch_input(self, n):
         out = np.empty((n, 3, self.h, self.w), np.float32)
