@@ -56,6 +56,7 @@ struct b200_engine {
     int submitted;
     cudaStream_t d2h_stream;   // serving loop: results of batch k are read back here while batch k+1 already computes
     cudaEvent_t tail_done;     // decode + NMS + collect of the current batch finished (d2h_stream waits on it)
+    cudaEvent_t lb_uploaded, lb_done;   // b200_letterbox_batch*: raw images are on the device / the resize kernel has consumed them
     int fwd_enqueued;          // the submitted batch's forward pass is already in the compute stream (b200_detect_submitted)
     TView in_view;             // NHWC copy of the input (only when layer 0 is not a stem conv)
     unsigned char *arena;      // parameters
@@ -167,6 +168,8 @@ static void build_engine_device_state(b200_engine *e, network *net)
     B200_CHECK(cudaEventCreateWithFlags(&e->submit_done, cudaEventDisableTiming));
     B200_CHECK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
     B200_CHECK(cudaEventCreateWithFlags(&e->tail_done, cudaEventDisableTiming));
+    B200_CHECK(cudaEventCreateWithFlags(&e->lb_uploaded, cudaEventDisableTiming));
+    B200_CHECK(cudaEventCreateWithFlags(&e->lb_done, cudaEventDisableTiming));
     e->fwd_enqueued = 0;
     e->submitted = 0;
     size_t max_floats = (size_t)e->cap * net->inputs;
@@ -548,7 +551,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaFree(e->d_raw); cudaFree(e->d_lb_items); cudaFree(e->d_im_dims[0]); cudaFree(e->d_im_dims[1]);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
         for (auto &ev : e->copy_done) cudaEventDestroy(ev);
-        cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaEventDestroy(e->tail_done);
+        cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaEventDestroy(e->tail_done); cudaEventDestroy(e->lb_uploaded); cudaEventDestroy(e->lb_done);
         cudaStreamDestroy(e->stream);
     }
     delete e;
@@ -1159,12 +1162,27 @@ static int letterbox_batch(network *net, const void *const *images, const int *w
     if (!e->d_lb_items) e->d_lb_items = (LetterboxItem *)dev_alloc((size_t)e->cap * sizeof(LetterboxItem));
     for (int k = 0; k < 2; ++k)
         if (!e->d_im_dims[k]) e->d_im_dims[k] = (int *)dev_alloc(2 * (size_t)e->cap * sizeof(int));
+    // The uploads run on the copy stream, so that a serving loop can stage batch k+1 while batch k's forward pass still runs
+    // (d_raw / d_lb_items were last read by the previous letterbox kernel, which has finished: this function waited for the
+    // previous upload and the kernel was enqueued before the forward pass whose results the caller has meanwhile collected or
+    // is about to; the dims slot written is the one of the batch before the one in flight).  Only the letterbox kernel itself
+    // joins the compute stream, behind whatever is already there.
+    static const bool lb_sync = getenv("B200_LETTERBOX_SYNC") != nullptr;       // A/B knob: everything on the compute stream
+    cudaStream_t up = lb_sync ? e->stream : e->copy_stream;
+    if (!lb_sync) {                                                               // the previous letterbox kernel must be done with d_raw
+        B200_CHECK(cudaStreamWaitEvent(up, e->lb_done, 0));
+    }
     for (int i = 0; i < n; ++i)
-        B200_CHECK(cudaMemcpyAsync(e->d_raw + items[i].src_off, images[i], (size_t)widths[i] * heights[i] * 3 * esz, cudaMemcpyHostToDevice, e->stream));
-    B200_CHECK(cudaMemcpyAsync(e->d_lb_items, items.data(), (size_t)n * sizeof(LetterboxItem), cudaMemcpyHostToDevice, e->stream));
-    B200_CHECK(cudaMemcpyAsync(e->d_im_dims[e->dims_cur ^ 1], dims.data(), dims.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        B200_CHECK(cudaMemcpyAsync(e->d_raw + items[i].src_off, images[i], (size_t)widths[i] * heights[i] * 3 * esz, cudaMemcpyHostToDevice, up));
+    B200_CHECK(cudaMemcpyAsync(e->d_lb_items, items.data(), (size_t)n * sizeof(LetterboxItem), cudaMemcpyHostToDevice, up));
+    B200_CHECK(cudaMemcpyAsync(e->d_im_dims[e->dims_cur ^ 1], dims.data(), dims.size() * sizeof(int), cudaMemcpyHostToDevice, up));
+    if (!lb_sync) {
+        B200_CHECK(cudaEventRecord(e->lb_uploaded, up));
+        B200_CHECK(cudaStreamWaitEvent(e->stream, e->lb_uploaded, 0));
+    }
     launch_letterbox(e->d_raw, u8, e->d_lb_items, n, e->d_input, net->w, net->h, e->stream);
-    B200_CHECK(cudaStreamSynchronize(e->stream));           // items / dims live on this stack frame
+    B200_CHECK(cudaEventRecord(e->lb_done, e->stream));
+    B200_CHECK(cudaStreamSynchronize(up));                  // items / dims live on this stack frame
     e->dims_pending = 1;
     return 0;
 }
