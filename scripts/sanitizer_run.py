@@ -14,4 +14,8 @@ for model, size, batch in (("yolov3", 160, 2), ("yolov3-tiny", 96, 3), ("yolov2"
     net.letterbox_batch_u8(u8)
     rec, counts = net.detect_batch(None, 0, 0, .3, .45, relative=0)
     print(" letterboxed", len(rec))
+    import tempfile
+    imgs = [u8[i % batch] for i in range(2 * batch + 1)]
+    n = net.validate_images(imgs, ["im_%d.jpg" % i for i in range(len(imgs))], "coco", tempfile.mkdtemp(), thresh=.3)
+    print(" validate driver (pipelined, short last batch)", n)
     net.close()
