@@ -20,5 +20,15 @@ for it in range(iters):
     rec, counts = net.detect_batch(x, 416, 416, .5, .45)
     rec = rec[np.lexsort((rec["cls"], rec["box_id"], rec["image"]))]
     seen.add(hashlib.sha256(rec.tobytes() + counts.tobytes()).hexdigest())
-print("iterations", iters, "records", len(rec), "distinct results", len(seen))
+# the same batch through the pipelined serving loop (forward k+1 enqueued while the records of batch k are read back)
+import ctypes
+RES = ctypes.c_void_p(1)
+out = (dn.B200_DET * (1 << 20))(); cnt = (ctypes.c_int * 64)()
+dn.lib.b200_submit_batch(net.ptr, RES)
+for it in range(iters):
+    n = dn.lib.b200_detect_submitted(net.ptr, RES if it + 1 < iters else None, 416, 416, .5, .45, 1, out, 1 << 20, cnt)
+    rec = np.ctypeslib.as_array(out)[:n].copy()
+    rec = rec[np.lexsort((rec["cls"], rec["box_id"], rec["image"]))]
+    seen.add(hashlib.sha256(rec.tobytes() + np.array(list(cnt)).tobytes()).hexdigest())
+print("iterations", iters, "x 2 (synchronous + pipelined resident loop), records", len(rec), "distinct results", len(seen))
 sys.exit(0 if len(seen) == 1 else 1)
