@@ -579,6 +579,23 @@ def test_resident_input_serving_loop(dn, workdir):
     net.close()
 
 
+def test_host_input_right_after_letterbox(dn, workdir):
+    """the letterbox kernel is asynchronous: a host batch staged right behind it (chunked copies on the copy stream) must
+    land after it, not under it"""
+    net, _, _ = open_net(dn, "yolov3-tiny", 8, 160, workdir, dn.PREC_BF16)
+    x = synth.make_images(8, 3, 160, 160, 77)
+    want, want_counts = net.detect_batch(x, 160, 160, .3, .45)
+    order = lambda r: r[np.lexsort((r["cls"], r["box_id"], r["image"]))]
+    rng = np.random.default_rng(5)
+    big = [rng.integers(0, 256, (900, 1200, 3), dtype=np.uint8) for _ in range(8)]
+    for _ in range(5):
+        assert net.letterbox_batch_u8(big) == 0
+        got, got_counts = net.detect_batch(x, 160, 160, .3, .45)
+        assert got_counts.tolist() == want_counts.tolist()
+        assert order(got).tobytes() == order(want).tobytes()
+    net.close()
+
+
 def test_validate_images_batched_driver(dn, workdir, tmp_path):
     """b200_validate_images (validate_detector, examples/detector.c:364-487, batched and pipelined): the three result files
     equal the oracle's writers fed with the records of one-image-at-a-time calls, as the reference's loop produces them"""

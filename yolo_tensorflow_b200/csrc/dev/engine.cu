@@ -773,6 +773,7 @@ static int stage_input(b200_engine *e, network *net, const float *input)
     }
     const int per = batch / chunks;
     const size_t in_stride = (size_t)per * net->inputs;
+    B200_CHECK(cudaStreamWaitEvent(e->copy_stream, e->lb_done, 0));      // a letterbox kernel may still be writing the input buffer
     for (int k = 0; k < chunks; ++k) {
         B200_CHECK(cudaMemcpyAsync(e->d_input + k * in_stride, input + k * in_stride, in_stride * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
         B200_CHECK(cudaEventRecord(e->copy_done[k], e->copy_stream));
