@@ -162,6 +162,42 @@ metadata get_metadata(char *file);                                          /* o
 void   free_ptrs(void **ptrs, int n);
 void   reset_rnn(network *net);
 
+/* ---- what examples/detector.c, yolo.c and darknet.c call around the path (host C, csrc/host/drivers.c) ------------ */
+typedef struct node { void *val; struct node *next; struct node *prev; } node;     /* ref :591-595 */
+typedef struct list { int size; node *front; node *back; } list;                   /* ref :597-601 */
+list  *make_list(void);                                                     /* list.c:5    */
+void   list_insert(list *l, void *val);                                     /* list.c:42   */
+void   free_list(list *l);                                                  /* ref :778    */
+void **list_to_array(list *l);                                              /* ref :772    */
+list  *read_data_cfg(char *filename);                                       /* ref :604  option_list.c:7   */
+char  *option_find(list *l, char *key);                                     /* option_list.c:91            */
+char  *option_find_str(list *l, char *key, char *def);                      /* ref :676  option_list.c:105 */
+int    option_find_int(list *l, char *key, int def);                        /* ref :677  option_list.c:113 */
+int    option_find_int_quiet(list *l, char *key, int def);                  /* ref :678  option_list.c:121 */
+float  option_find_float(list *l, char *key, float def);                    /* option_list.c:135           */
+float  option_find_float_quiet(list *l, char *key, float def);              /* option_list.c:128           */
+void   option_unused(list *l);                                              /* option_list.c:79            */
+list  *get_paths(char *filename);                                           /* ref :762  data.c:12         */
+char **get_labels(char *filename);                                          /* ref :750  data.c:618        */
+int   *read_map(char *filename);                                            /* ref :774  utils.c:62        */
+int    find_arg(int argc, char *argv[], char *arg);                         /* ref :768  utils.c:120       */
+int    find_int_arg(int argc, char **argv, char *arg, int def);             /* ref :766  utils.c:133       */
+float  find_float_arg(int argc, char **argv, char *arg, float def);         /* ref :767  utils.c:148       */
+char  *find_char_arg(int argc, char **argv, char *arg, char *def);          /* ref :769  utils.c:163       */
+char  *basecfg(char *cfgfile);                                              /* ref :770  utils.c:179       */
+char  *fgetl(FILE *fp);                                                     /* ref :773  utils.c:335       */
+void   strip(char *s);                                                      /* ref :774  utils.c:302       */
+image  copy_image(image p);                                                 /* ref :712  */
+image **load_alphabet(void);                                                /* ref :737  image.c:223 (data/labels/<char>_<size>.png holding PNM data) */
+image  get_label(image **characters, char *string, int size);               /* ref :638  image.c:132 */
+void   draw_label(image a, int r, int c, image label, const float *rgb);    /* ref :639  image.c:149 */
+void   draw_box(image a, int x1, int y1, int x2, int y2, float r, float g, float b);             /* image.c:166 */
+void   draw_box_width(image a, int x1, int y1, int x2, int y2, int w, float r, float g, float b); /* ref :713  image.c:202 */
+float  get_color(int c, int x, int max);                                    /* image.c:17  */
+void   draw_detections(image im, detection *dets, int num, float thresh, char **names, image **alphabet, int classes); /* ref :734 image.c:239 */
+void   save_image(image im, const char *name);                              /* ref :707  image.c:713 (CPU build: <name>.png) */
+void   save_image_png(image im, const char *name);                          /* ref :640  image.c:696 */
+
 #ifdef __cplusplus
 }
 #endif

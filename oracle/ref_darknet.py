@@ -147,6 +147,22 @@ class RefNet:
             self.set_layer_output_ptr(i, p); self.set_layer_int(i, L_BATCH, bt)
         return dets, num.value
 
+    def boxes_as_is(self, w, h, thresh, relative=1):
+        """the reference's get_network_boxes exactly as a driver calls it (batch item 0; with cfg batch=2 the heads are
+        flip-averaged in place first, yolo_layer.c:320 / region_layer.c:368-390)"""
+        num = c_int(0)
+        dets = self.lib.get_network_boxes(self.ptr, w, h, thresh, .5, None, relative, ctypes.byref(num))
+        return dets, num.value
+
+    def resize(self, w, h):
+        """the reference's resize_network (network.c:358-438)"""
+        self.lib.resize_network.argtypes = [c_void_p, c_int, c_int]; self.lib.resize_network.restype = c_int
+        with _quiet():
+            rc = self.lib.resize_network(self.ptr, w, h)
+        self.w, self.h = self._net_int(N_W), self._net_int(N_H)
+        self.inputs = self._net_int(N_INPUTS)
+        return rc
+
     def classes(self):
         return self.layer_int(self.n - 1, L_CLASSES)
 

@@ -1,11 +1,19 @@
 """GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C-ABI library
 (yolo_tensorflow_b200/lib/libdarknet.so); the oracle is only the checker.
 
-Tolerances (BASELINE.json north star):
-  * fp32 mode (CUDA-core fp32 path): per-layer activations and decoded boxes within rtol 1e-4 of the reference,
-    measured as max|diff| <= 1e-4 * max|ref| per layer; detection identity and NMS keep-lists exact.
-  * bf16 mode (tcgen05 path): teacher-forced per-layer activations within 1e-2 * max|ref|;
-    free-running head outputs within 5e-2 * max|ref| (error of 75 stacked bf16 convolutions).
+Tolerances (BASELINE.json north star; derivations in DESIGN.md §2):
+  * fp32 mode (CUDA-core fp32 path): per-layer activations within 1e-4 * max|ref| per layer (norm-wise: the reference's own
+    -Ofast and -O2 builds agree bit for bit, but the port and the engine sum the GEMM in a different order); decoded boxes
+    free-running within 2e-3 (w,h = exp(t): a 1e-4 activation error on logits of magnitude ~10 is a 1e-3 relative error of
+    the box size); detection identity and NMS keep-lists exact.
+  * decode alone (the reference's head activations teacher-forced, either precision): boxes/objectness/probabilities to 1e-5.
+  * bf16 mode (tcgen05 path), teacher-forced per layer / per fused group, also at the headline sizes (416 b64, 608 b32):
+    1e-2 * max|ref| (norm-wise).
+  * bf16 mode free-running (75 convolutions deep): bounds of the bf16 STORAGE error model (scripts/bf16_error_model.py runs
+    it on the CPU with the oracle's port: per stored activation 2^-9/sqrt(3) relative rms, ~100 roundings deep => ~1e-2 of
+    the logits' rms, 4-5 sigma => 2-3e-2 of their max; measured on B200: the same); boxes compared by identity (box id, class) with the set difference
+    confined to scores next to the threshold.  rtol 1e-2 on w,h cannot hold free-running for ANY bf16 pipeline: w = exp(t)
+    turns the logit error (rms 0.015-0.02 absolute) into a relative size error of the same magnitude.
   * NMS: bit-exact keep-lists when fed the oracle's boxes.
 """
 import ctypes
@@ -25,7 +33,14 @@ from yolo_tensorflow_b200 import synth  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-FP32_TOL, BF16_LAYER_TOL, BF16_E2E_TOL = 1e-4, 1e-2, 5e-2
+FP32_TOL, BF16_LAYER_TOL = 1e-4, 1e-2
+# Free-running bf16 against the fp32 oracle.  Error model (scripts/bf16_error_model.py, the oracle's port with bf16 storage
+# emulated, CPU) and the engine measured on B200 agree (profiles/r2_bf16_error_model.txt): head activations max|err|/max|ref|
+# 1.4-2.2e-2 and rms(err)/rms(ref) 0.6-1.4e-2 on YOLOv3-416/608 and YOLOv2; boxes matched by identity x,y 1.1e-3 abs, w,h
+# median 1.7e-2 / max 7.8e-2 relative, score and objectness 1.5e-2 abs, every pair or candidate that changes side within
+# 1.2e-2 of the threshold.  The bounds below are those figures with 1.5-2x head-room.
+BF16_E2E_TOL, BF16_E2E_RMS_TOL = 3e-2, 2e-2
+BF16_BOX_XY_ATOL, BF16_BOX_WH_MEDIAN, BF16_BOX_WH_MAX, BF16_SCORE_ATOL, BF16_THRESH_BAND = 2.5e-3, 3e-2, 1.5e-1, 3e-2, 2.5e-2
 CASES = ["yolov3-tiny_96_b2", "yolov3-tiny_416_b1", "yolov3_96_b1", "yolov2_96_b2", "yolov1_448_b1"]
 
 
@@ -48,6 +63,52 @@ def open_net(dn, model, batch, size, workdir, prec, damp=True, fuse=None):
 def kept_set(probs):
     r, c = np.nonzero(probs)
     return set(zip(r.tolist(), c.tolist()))
+
+
+def oracle_pairs(boxes, obj, probs, ids):
+    """{(box id, class): (score, objectness, box)} of every (box, class) pair over the threshold"""
+    r, c = np.nonzero(probs)
+    return {(int(ids[i]), int(j)): (float(probs[i, j]), float(obj[i]), boxes[i]) for i, j in zip(r, c)}
+
+
+def record_pairs(rec):
+    return {(int(r["box_id"]), int(r["cls"])): (float(r["prob"]), float(r["objectness"]),
+                                                np.array([r["bbox"]["x"], r["bbox"]["y"], r["bbox"]["w"], r["bbox"]["h"]], np.float32)) for r in rec}
+
+
+def assert_pairs_match_by_identity(got, ref, thresh, tag=""):
+    """free-running bf16 engine vs fp32 oracle, (box, class) pairs over the threshold BEFORE suppression, matched by identity:
+    pairs present on one side only have a score next to the threshold; matched ones agree in position, size, objectness and
+    score within the bf16 storage error model (module docstring)"""
+    for k in set(got) - set(ref):
+        assert abs(got[k][0] - thresh) <= BF16_THRESH_BAND, (tag, "extra pair", k, got[k][0])
+    for k in set(ref) - set(got):
+        assert abs(ref[k][0] - thresh) <= BF16_THRESH_BAND, (tag, "missing pair", k, ref[k][0])
+    common = sorted(set(got) & set(ref))
+    assert len(common) >= 0.8 * len(ref) and len(common) > 0, (tag, len(common), len(ref))
+    A = np.array([ref[k][2] for k in common], np.float64); B = np.array([got[k][2] for k in common], np.float64)
+    assert np.abs(A - B)[:, :2].max() <= BF16_BOX_XY_ATOL, (tag, np.abs(A - B)[:, :2].max())
+    rel = np.abs(A - B)[:, 2:] / np.abs(A)[:, 2:]
+    assert np.median(rel) <= BF16_BOX_WH_MEDIAN and rel.max() <= BF16_BOX_WH_MAX, (tag, np.median(rel), rel.max())
+    score = np.array([[ref[k][0], got[k][0]] for k in common]); objn = np.array([[ref[k][1], got[k][1]] for k in common])
+    assert np.abs(score[:, 0] - score[:, 1]).max() <= BF16_SCORE_ATOL, (tag, np.abs(score[:, 0] - score[:, 1]).max())
+    assert np.abs(objn[:, 0] - objn[:, 1]).max() <= BF16_SCORE_ATOL, (tag, np.abs(objn[:, 0] - objn[:, 1]).max())
+    return len(common)
+
+
+def assert_engine_nms_is_the_reference_nms(dn, before, after, nms, classes, tag=""):
+    """`before` = the engine's records with suppression off (nms threshold 2: an IoU never exceeds it), `after` = with it on,
+    same image: the oracle's do_nms_sort applied to the engine's own candidates must keep exactly the pairs the engine kept"""
+    ids = sorted(set(int(v) for v in before["box_id"]))
+    row = {v: i for i, v in enumerate(ids)}
+    boxes = np.zeros((len(ids), 4), np.float32); probs = np.zeros((len(ids), classes), np.float32)
+    for r in before:
+        i = row[int(r["box_id"])]
+        boxes[i] = (r["bbox"]["x"], r["bbox"]["y"], r["bbox"]["w"], r["bbox"]["h"]); probs[i, int(r["cls"])] = r["prob"]
+    kept = P.do_nms_sort(boxes, np.ones(len(ids), np.float32), probs, nms)
+    want = {(ids[i], int(j)) for i, j in zip(*np.nonzero(kept))}
+    got = {(int(r["box_id"]), int(r["cls"])) for r in after}
+    assert got == want, (tag, len(got), len(want), sorted(got ^ want)[:10])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -107,6 +168,108 @@ def test_nms_kernel_bit_exact_on_reference_boxes(dn, name):
 
 
 # ---------------------------------------------------------------------------------------------------
+# decode alone: the REFERENCE's head activations in, the reference's boxes out (fp32 arithmetic on both sides)
+# ---------------------------------------------------------------------------------------------------
+DECODE_TOL = 2e-6          # the only difference left is libm exp/pow vs the device's: one or two ulp of fp32
+
+
+@pytest.mark.parametrize("name", ["yolov3-tiny_96_b2", "yolov3_96_b1", "yolov2_96_b2", "yolov1_448_b1"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_decode_teacher_forced_on_reference_heads(dn, name, prec, workdir):
+    """b200_set_layer_output puts the reference's own l.output of every head on the device; get_network_boxes_batch must then
+    return the reference's detections: same count, boxes / objectness / probabilities to 2e-6 (decode is fp32 in both
+    precisions, so the bf16 engine has to meet the same bound), thresholded probabilities exactly zero in the same places"""
+    g = load_golden(name)
+    model, size, batch = str(g["model"]), int(g["size"]), int(g["batch"])
+    net, _, _ = open_net(dn, model, batch, size, workdir, dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16)
+    net.predict(synth.make_images(batch, 3, size, size, int(g["seed"])))
+    for i in g["heads"]:
+        net.set_layer_output(int(i), g[f"head{int(i)}"])
+    classes = net.layers[-1]["classes"]
+    w_, h_ = (1, 1) if model == "yolov1" else (size, size)
+    for b in range(batch):
+        dets, n = net.boxes(b, w_, h_, float(g["thresh"]))
+        boxes, obj, probs = dn.dets_to_arrays(dets, n, classes)
+        dn.free_detections(dets, n)
+        assert n == len(g[f"img{b}_obj"])
+        np.testing.assert_allclose(boxes, g[f"img{b}_boxes"], rtol=DECODE_TOL, atol=1e-9)
+        assert np.array_equal(obj, g[f"img{b}_obj"])
+        gp = golden_probs(g, b, classes)
+        assert np.array_equal(probs == 0, gp == 0)
+        np.testing.assert_allclose(probs, gp, rtol=DECODE_TOL, atol=0)
+    net.close()
+
+
+FLIP_CASES = ["yolov3-tiny_96_flip", "yolov2_96_flip", "yolov3-tiny_105_flip"]
+
+
+@pytest.mark.parametrize("name", FLIP_CASES)
+def test_batch2_flip_average_matches_reference(dn, name, workdir):
+    """cfg batch=2 (`detector valid2`, detector.c:253-257): get_network_boxes averages item 0 with the mirrored item 1 in
+    place before decoding (yolo_layer.c:290-320, region_layer.c:368-390).  Heads teacher-forced with the reference's
+    activations; the returned array (counted before the average, filled after) and the rewritten l.output must equal the
+    reference's."""
+    g = load_golden(name)
+    model, size, thresh = str(g["model"]), int(g["size"]), float(g["thresh"])
+    net, _, _ = open_net(dn, model, 2, size, workdir, dn.PREC_FP32)
+    x0 = synth.make_images(1, 3, size, size, int(g["seed"]))
+    net.predict(np.ascontiguousarray(np.concatenate([x0, x0[..., ::-1]])))
+    heads = [int(i) for i in g["heads"]]
+    for i in heads:                                        # free-running fp32 activations are already within 1e-4 ...
+        a, r = net.layer_output(i), g[f"head{i}_before"]
+        assert np.abs(a - r).max() <= FP32_TOL * np.abs(r).max()
+        net.set_layer_output(i, r)                         # ... the flip/average/decode is checked on the reference's own
+    num = ctypes.c_int(0)
+    dets = dn.get_network_boxes(net.ptr, size, size, thresh, .5, None, 1, ctypes.byref(num))
+    classes = net.layers[-1]["classes"]
+    assert num.value == int(g["num"])
+    boxes, obj, probs = dn.dets_to_arrays(dets, num.value, classes)
+    dn.free_detections(dets, num.value)
+    gp = np.zeros((num.value, classes), np.float32)
+    gp[g["prob_rc"][0], g["prob_rc"][1]] = g["prob_v"]
+    np.testing.assert_allclose(boxes, g["boxes"], rtol=DECODE_TOL, atol=1e-9)
+    assert np.array_equal(obj, g["obj"])
+    assert np.array_equal(probs == 0, gp == 0)
+    np.testing.assert_allclose(probs, gp, rtol=DECODE_TOL, atol=0)
+    for i in heads:                                        # l.output rewritten in place, device and host copy alike
+        after = g[f"head{i}_after"]
+        assert np.array_equal(net.layer_output(i), after)
+        host = np.ctypeslib.as_array(dn.lib.b200_layer_output_host(net.ptr, i), shape=after.shape)
+        assert np.array_equal(host, after)
+    # the additive per-image entry point does not average
+    d0, n0 = net.boxes(0, size, size, thresh)
+    dn.free_detections(d0, n0)
+    net.close()
+
+
+def test_get_network_boxes_reads_the_host_head_buffers(dn, workdir):
+    """demo.c:54-83 averages the last frames INTO l.output on the host and then calls get_network_boxes: the host buffers of
+    the heads are the truth for the reference API (head sync on)"""
+    net, cfg, wpath = open_net(dn, "yolov3-tiny", 1, 160, workdir, dn.PREC_FP32)
+    xa, xb = synth.make_images(1, 3, 160, 160, 51), synth.make_images(1, 3, 160, 160, 52)
+    heads = [i for i, L in enumerate(net.layers) if L["type_name"] == "YOLO"]
+    net.predict(xa); fa = {i: net.layer_output(i) for i in heads}
+    net.predict(xb); fb = {i: net.layer_output(i) for i in heads}
+    port = P.Net(cfg, wpath)
+    outs = [None] * net.n
+    for i in heads:                                        # avg_predictions: mean of the remembered frames (demo.c:66-80)
+        mean = ((fa[i] + fb[i]) / np.float32(2)).astype(np.float32)
+        host = np.ctypeslib.as_array(dn.lib.b200_layer_output_host(net.ptr, i), shape=mean.shape)
+        host[...] = mean
+        outs[i] = mean
+    num = ctypes.c_int(0)
+    dets = dn.get_network_boxes(net.ptr, 160, 160, .3, .5, None, 1, ctypes.byref(num))
+    boxes, obj, probs = dn.dets_to_arrays(dets, num.value, 80)
+    dn.free_detections(dets, num.value)
+    pb, po, pp, _ = P.get_network_boxes(port, outs, 0, 160, 160, .3)
+    assert num.value == len(po) and num.value > 0
+    assert np.array_equal(obj, po)
+    np.testing.assert_allclose(boxes, pb, rtol=DECODE_TOL, atol=1e-9)
+    np.testing.assert_allclose(probs, pp, rtol=DECODE_TOL, atol=0)
+    net.close()
+
+
+# ---------------------------------------------------------------------------------------------------
 # teacher-forced per-layer parity against the (golden-pinned) numpy port
 # ---------------------------------------------------------------------------------------------------
 def layer_sources(L, i):
@@ -146,8 +309,70 @@ def test_teacher_forced_layers(dn, model, size, batch, prec, workdir):
         assert "conv_simt" in kernels
 
 
-@pytest.mark.parametrize("model,size,batch", [("yolov3", 416, 2), ("yolov2", 416, 2)])
-def test_bf16_end_to_end_heads(dn, model, size, batch, workdir):
+def assert_free_running_heads(a, r, tag=""):
+    """free-running bf16 head activations against the fp32 oracle: the bounds of the bf16 storage error model"""
+    assert np.abs(a - r).max() <= BF16_E2E_TOL * np.abs(r).max(), (tag, np.abs(a - r).max() / np.abs(r).max())
+    rms = np.sqrt(((a - r).astype(np.float64) ** 2).mean()) / np.sqrt((r.astype(np.float64) ** 2).mean())
+    assert rms <= BF16_E2E_RMS_TOL, (tag, rms)
+
+
+NOT_MATERIALISED = ("conv_tc+shortcut", "conv_tc(block)", "conv_tc+upsample", "conv_stem+maxpool")
+
+
+@pytest.mark.parametrize("model,size,batch", [("yolov3", 416, 64), ("yolov3", 608, 32), ("yolov2", 416, 64), ("yolov3-tiny", 416, 64)])
+def test_headline_plan_teacher_forced_groups(dn, model, size, batch, workdir):
+    """The plan the bench runs (fusion on, full batch: 16x8x1 / 4x4x8 / 2x2x32 / 2x1x64 pixel tiles, CTA pairs, patch and block
+    kernels, fused shortcut / upsample / maxpool, in-place concatenation) against the oracle, kernel by kernel: every
+    materialised layer is recomputed from the ORACLE's outputs of the layers its fused group reads (teacher-forced), so each
+    check isolates one launch.  The batch is two distinct oracle images repeated, compared on images spread over the batch.
+    Tolerance 1e-2 * max|ref| (norm-wise), bf16."""
+    net, cfg, wpath = open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
+    port = P.Net(synth.make_cfg(model, workdir, batch=2, width=size, height=size), wpath)
+    base = synth.make_images(2, 3, size, size, 1005)
+    outs = [o.reshape(2, -1) for o in port.forward(base)]
+    reps = batch // 2
+    x = np.ascontiguousarray(np.concatenate([base] * reps))
+    probe = sorted({0, 1, 2, 3, batch // 2, batch // 2 + 1, batch - 2, batch - 1})
+
+    def tiled(j):
+        return np.ascontiguousarray(np.tile(outs[j], (reps, 1)))
+
+    net.predict(x)
+    kernels = [net.kernel(i) for i in range(net.n)]
+    assert any(k.startswith("conv_tc") for k in kernels)
+    start, checked, worst = 0, 0, 0.
+    for j, L in enumerate(port.layers):
+        if kernels[j] in NOT_MATERIALISED:
+            continue                                        # its result appears in a later layer's buffer: same group
+        group = range(start, j + 1)
+        if start > 0:
+            sources = set()
+            for i in group:
+                for src in layer_sources(port.layers[i], i):
+                    if src < start:
+                        sources.add(src)
+            for src in sorted(sources):
+                assert kernels[src] not in NOT_MATERIALISED, (j, src)
+                net.set_layer_output(src, tiled(src))
+            net.run_layers(start, j + 1)
+        a = net.layer_output(j)[probe]
+        r = outs[j][[q % 2 for q in probe]]
+        scale = np.abs(r).max()
+        err = np.abs(a - r).max() / scale if scale > 0 else 0.
+        worst = max(worst, err)
+        assert np.isfinite(a).all() and err <= BF16_LAYER_TOL, (j, L.type, kernels[j], err)
+        checked += 1
+        start = j + 1
+    assert checked >= net.n // 2
+    net.close()
+
+
+@pytest.mark.parametrize("model,size,batch,thresh", [("yolov3", 416, 2, .5), ("yolov2", 416, 2, .5), ("yolov3", 608, 2, .5), ("yolov3-tiny", 416, 2, .5)])
+def test_bf16_end_to_end_heads_and_boxes(dn, model, size, batch, thresh, workdir):
+    """free-running bf16 engine against the fp32 oracle on the same images: head activations inside the bf16 storage error
+    model, l.output on the host populated, and the decoded (box, class) pairs matched by identity — position, size, objectness
+    and score numerically, differences of the SETS confined to scores next to the threshold; then the engine's suppression
+    equals the oracle's do_nms_sort on the engine's own candidates"""
     net, cfg, wpath = open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
     port = P.Net(cfg, wpath)
     x = synth.make_images(batch, 3, size, size, 1002)
@@ -156,18 +381,18 @@ def test_bf16_end_to_end_heads(dn, model, size, batch, workdir):
     for i, L in enumerate(port.layers):
         if L.type in ("yolo", "region"):
             a = net.layer_output(i); r = outs[i].reshape(batch, -1)
-            assert np.abs(a - r).max() <= BF16_E2E_TOL * np.abs(r).max()
+            assert_free_running_heads(a, r, (model, size, i))
             host = np.ctypeslib.as_array(dn.lib.b200_layer_output_host(net.ptr, i), shape=(batch * L.outputs,))
             assert np.array_equal(host.reshape(batch, -1), a)        # l.output on the host is populated (network.c:505)
-    # detections: same boxes up to the bf16 noise at the threshold
+    classes = port.layers[-1].classes
+    before, counts = net.detect_batch(x, size, size, thresh, 2.)     # nms threshold 2: nothing is suppressed
+    after, _ = net.detect_batch(x, size, size, thresh, .45)
     for b in range(batch):
-        dets, n = net.boxes(b, size, size, .5)
-        pb, po, pp, _ = P.get_network_boxes(port, outs, b, size, size, .5)
-        dn.free_detections(dets, n)
-        if model == "yolov3":
-            assert abs(n - len(po)) <= max(3, len(po) // 20)
-        else:
-            assert n == len(po)
+        ref = oracle_pairs(*P.get_network_boxes(port, outs, b, size, size, thresh))
+        got = record_pairs(before[before["image"] == b])
+        assert_pairs_match_by_identity(got, ref, thresh, (model, size, b))
+        assert_engine_nms_is_the_reference_nms(dn, before[before["image"] == b], after[after["image"] == b], .45, classes, (model, size, b))
+    net.close()
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -500,6 +725,79 @@ def test_resize_network_matches_fresh_parse(dn, model, prec, workdir):
     net.close(); fresh.close()
 
 
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("model", ["yolov3", "yolov2", "yolov3-tiny"])
+def test_resize_network_matches_the_reference_resize(dn, model, workdir):
+    """resize_network against the REFERENCE's resize_network (network.c:358-438 + resize_*_layer): both libraries parse at
+    160x160, load the same weights, resize to 224x192 (non-square) and run the same image; every layer's geometry and
+    activations (fp32 mode, 1e-4) and the decoded boxes must agree; then back to 160x160"""
+    net, cfg, wpath = open_net(dn, model, 1, 160, workdir, dn.PREC_FP32)
+    ref = R.RefNet(cfg, wpath)
+    for (w, h, seed) in ((224, 192, 61), (160, 160, 62)):
+        assert net.resize(w, h) == 0 and ref.resize(w, h) == 0
+        assert (net.w, net.h) == (ref.w, ref.h) == (w, h)
+        x = synth.make_images(1, 3, h, w, seed)
+        net.predict(x); ref.predict(x)
+        for i in range(net.n):
+            shp = ref.layer_shape(i)
+            L = net.layers[i]
+            assert (L["out_c"], L["outputs"]) == (shp["out_c"], shp["outputs"]), i
+            if L["type_name"] in ("YOLO", "REGION"):
+                # resize_yolo_layer / resize_region_layer (yolo_layer.c:62-73, region_layer.c:57-68) update w, h and outputs but
+                # leave out_w / out_h at the parse-time value; drivers read l.w / l.h of the heads (detector.c:592-603)
+                assert (L["w"], L["h"]) == (ref.layer_int(i, R.L_W), ref.layer_int(i, R.L_H)), i
+            else:
+                assert (L["out_w"], L["out_h"]) == (shp["out_w"], shp["out_h"]), i
+            a, r = net.layer_output(i), ref.layer_output(i)
+            assert np.abs(a - r).max() <= FP32_TOL * np.abs(r).max() + 1e-7, (i, L["type_name"])
+        dets, n = ref.boxes(0, w, h, .3)
+        rb, ro, rp = ref.dets_arrays(dets, n)
+        ref.free_dets(dets, n)
+        d, m = net.boxes(0, w, h, .3)
+        gb, go, gp = dn.dets_to_arrays(d, m, net.layers[-1]["classes"])
+        dn.free_detections(d, m)
+        assert m == n and n > 0
+        np.testing.assert_allclose(gb, rb, rtol=2e-3, atol=1e-5)
+        np.testing.assert_allclose(go, ro, rtol=1e-4, atol=1e-6)
+    ref.close(); net.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# NMS stress configuration (SURVEY §8d): undamped head weights (thousands of candidates per image) and thresh .005
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model,size,damp,thresh,e2e", [("yolov3", 416, False, .5, False), ("yolov3", 416, True, .005, True),
+                                                        ("yolov3-tiny", 416, False, .5, True)])
+def test_nms_stress_configuration(dn, model, size, damp, thresh, e2e, workdir):
+    """SURVEY §8d stress settings on one image: undamped seed-0 heads (YOLOv3: 9 898 candidates, 6 960 of them with
+    non-finite sizes because the logits reach 1e5 — the IoU is NaN there and must never suppress) and the `valid` threshold
+    .005 (all 10 647 boxes, 834 586 (box, class) pairs).  (1) The ORACLE's boxes through the device NMS: keep-list bit-exact
+    against the port and, where it travelled, the reference library's own do_nms_sort.  (2) Where the logits are sane, the
+    engine end to end in fp32 mode through b200_detect_batch: the pairs over the threshold are the oracle's except within the
+    fp32 activation tolerance of it, and the engine's suppression equals the oracle's on the engine's own candidates."""
+    net, cfg, wpath = open_net(dn, model, 1, size, workdir, dn.PREC_FP32, damp=damp)
+    port = P.Net(cfg, wpath)
+    x = synth.make_images(1, 3, size, size, 1002)
+    with np.errstate(all="ignore"):
+        outs = port.forward(x)
+        pb, po, pp, pid = P.get_network_boxes(port, outs, 0, size, size, thresh)
+        assert len(po) > 250, len(po)
+        want = P.do_nms_sort(pb, po, pp, .45)
+    got = dn.nms_sort_arrays(pb, pp, .45)
+    assert np.array_equal(got, want)
+    if R.available() and len(po) <= 3000:                    # the reference needs 4 s for 6.7k boxes and 80 classes
+        assert np.array_equal(got, R.ref_nms_sort_arrays(pb, pp, .45, po))
+    if e2e:
+        before, counts = net.detect_batch(x, size, size, thresh, 2.)
+        after, _ = net.detect_batch(x, size, size, thresh, .45)
+        ref_pairs, got_pairs = oracle_pairs(pb, po, pp, pid), record_pairs(before)
+        for k in set(ref_pairs) ^ set(got_pairs):
+            sc = (ref_pairs.get(k) or got_pairs.get(k))[0]
+            assert abs(sc - thresh) <= 5e-4, (k, sc)
+        assert len(set(ref_pairs) & set(got_pairs)) >= 0.99 * len(ref_pairs)
+        assert_engine_nms_is_the_reference_nms(dn, before, after, .45, 80, (model, damp, thresh))
+    net.close()
+
+
 def host_letterbox(dn, chw, w, h):
     """this library's host letterbox_image (plain C restatement of image.c:960-979) on one float32 CHW image"""
     a = np.ascontiguousarray(chw, dtype=np.float32)
@@ -672,16 +970,16 @@ def test_full_size_yolov3_batch64_properties(dn, workdir):
     for k, lst in per.items():
         assert all(v == lst[0] for v in lst), k
     assert (counts.reshape(16, 4) == counts[:4]).all()
-    # (b) image 0 against the oracle run on the same image: same candidates up to bf16 threshold noise
-    port = P.Net(synth.make_cfg("yolov3", workdir, batch=1, width=416, height=416), wpath)
-    outs = port.forward(base[:1])
-    pb, po, pp, pid = P.get_network_boxes(port, outs, 0, 416, 416, .5)
-    assert abs(int(counts[0]) - len(po)) <= max(3, len(po) // 20)
-    kept = P.do_nms_sort(pb, po, pp, .45)
-    want = set(zip(pid[np.nonzero(kept)[0]].tolist(), np.nonzero(kept)[1].tolist()))
+    # (b) the four distinct images against the oracle: (box, class) pairs matched by identity before suppression, and the
+    #     engine's suppression == the oracle's do_nms_sort on the engine's own candidates
+    port = P.Net(synth.make_cfg("yolov3", workdir, batch=4, width=416, height=416), wpath)
+    outs = port.forward(base)
+    before, _ = net.detect_batch(x, 416, 416, .5, 2.)
+    for b in range(4):
+        ref = oracle_pairs(*P.get_network_boxes(port, outs, b, 416, 416, .5))
+        assert_pairs_match_by_identity(record_pairs(before[before["image"] == b]), ref, .5, ("416 b64", b))
+        assert_engine_nms_is_the_reference_nms(dn, before[before["image"] == b], rec[rec["image"] == b], .45, 80, ("416 b64", b))
     r0 = rec[rec["image"] == 0]
-    got = set(zip(r0["box_id"].tolist(), r0["cls"].tolist()))
-    assert len(got & want) >= 0.85 * max(len(want), 1)
     # (c) NMS idempotence on the engine's own survivors
     boxes = np.stack([r0["bbox"]["x"], r0["bbox"]["y"], r0["bbox"]["w"], r0["bbox"]["h"]], axis=1).astype(np.float32)
     ids = sorted(set(r0["box_id"].tolist()))

@@ -55,6 +55,41 @@ def test_port_matches_reference_golden(name, workdir):
         assert np.array_equal(rc, g[f"img{b}_kept_rc"])
 
 
+FLIP_CASES = ["yolov3-tiny_96_flip", "yolov2_96_flip", "yolov3-tiny_105_flip"]
+
+
+def flip_golden_arrays(g, classes):
+    n = int(g["num"])
+    probs = np.zeros((n, classes), np.float32)
+    probs[g["prob_rc"][0], g["prob_rc"][1]] = g["prob_v"]
+    return g["boxes"], g["obj"], probs
+
+
+@pytest.mark.parametrize("name", FLIP_CASES)
+def test_port_flip_average_matches_reference_golden(name, workdir):
+    """cfg batch=2 (`detector valid2`): the reference's get_network_boxes rewrites l.output (item 1 mirrored, item 0 averaged)
+    and decodes item 0; the golden holds l.output before/after and the returned array (counted BEFORE the average)"""
+    g = load_golden(name)
+    model, size, thresh = str(g["model"]), int(g["size"]), float(g["thresh"])
+    cfg, wpath = model_files(model, 2, size, workdir)
+    net = P.Net(cfg, wpath)
+    heads = [int(i) for i in g["heads"]]
+    outs = [None] * len(net.layers)
+    for i in heads:
+        outs[i] = g[f"head{i}_before"]                      # the reference's own activations: only the flip/average is under test
+    av = P.avg_flipped(net, outs)
+    for i in heads:
+        assert np.array_equal(av[i], g[f"head{i}_after"]), i
+    boxes, obj, probs, _ = P.get_network_boxes(net, av, 0, size, size, thresh)
+    gb, go, gp = flip_golden_arrays(g, net.layers[-1].classes)
+    filled = len(obj)
+    assert filled <= int(g["num"])
+    np.testing.assert_allclose(boxes, gb[:filled], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(obj, go[:filled])
+    assert np.allclose(probs, gp[:filled], rtol=1e-5, atol=1e-7)
+    assert not go[filled:].any() and not gp[filled:].any()  # records the averaged output no longer fills stay calloc'd zeros
+
+
 def test_reorg_is_the_reference_permutation():
     """blas.c:9-30 with forward=0 (reorg_layer.c:107-109) on c=8,h=w=4,s=2: a permutation that is NOT space_to_depth"""
     x = np.arange(8 * 4 * 4, dtype=np.float32).reshape(1, 8, 4, 4)

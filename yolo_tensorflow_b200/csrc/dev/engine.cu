@@ -894,6 +894,8 @@ extern "C" void b200_set_layer_output(network *net, int i, const float *in)
     size_t bytes = (size_t)batch * net->layers[i].outputs * sizeof(float);
     if (e->L[i].head_out) {
         B200_CHECK(cudaMemcpyAsync(e->L[i].head_out, in, bytes, cudaMemcpyHostToDevice, e->stream));
+        const layer &l = net->layers[i];                  // the host copy get_network_boxes trusts follows (b200_engine_push_heads)
+        if ((l.type == YOLO || l.type == REGION || l.type == DETECTION) && l.output && l.output != in) memcpy(l.output, in, bytes);
     } else {
         B200_CHECK(cudaMemcpyAsync(e->xfer, in, bytes, cudaMemcpyHostToDevice, e->stream));
         launch_nchw_f32_to_view(e->xfer, view_of(e->L[i], batch), e->stream);
@@ -1055,6 +1057,37 @@ extern "C" int b200_engine_decode_image(b200_engine *e, network *net, int image,
 }
 
 extern "C" int b200_engine_classes(b200_engine *e) { return e->classes; }
+
+// get_network_boxes reads the heads' HOST l.output in the reference, and callers may have rewritten it since the last
+// predict (demo.c:54-83 averages the last frames into it): with head sync on, the host buffers of the first `items` batch
+// items are the truth and go back to the device before the decode.
+extern "C" void b200_engine_push_heads(b200_engine *e, network *net, int items)
+{
+    need_device(e, "get_network_boxes");
+    if (!e->head_sync) return;
+    if (items > logical_batch(e, net)) items = logical_batch(e, net);
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        if ((l.type != YOLO && l.type != REGION && l.type != DETECTION) || !e->L[i].head_out || !l.output) continue;
+        B200_CHECK(cudaMemcpyAsync(e->L[i].head_out, l.output, (size_t)items * l.outputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+}
+
+// `if (l.batch == 2) avg_flipped_yolo(l)` of get_yolo_detections (yolo_layer.c:320) and the same branch of
+// get_region_detections (region_layer.c:368-390): in place, device and (with head sync) host copy alike.
+extern "C" void b200_engine_avg_flipped(b200_engine *e, network *net)
+{
+    need_device(e, "get_network_boxes");
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        if ((l.type != YOLO && l.type != REGION) || l.batch != 2 || e->cap < 2) continue;
+        const int entries = l.type == YOLO ? l.classes + 4 + 1 : l.classes + l.coords + 1;
+        launch_avg_flipped(e->L[i].head_out, l.w, l.h, l.n, entries, l.outputs, e->stream);
+        if (e->head_sync && l.output)
+            B200_CHECK(cudaMemcpyAsync(l.output, e->L[i].head_out, (size_t)2 * l.outputs * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    }
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+}
 
 // forward (from layer `first`; first = net->n: the forward pass is already in the stream) + decode + NMS + collect, all
 // enqueued on the compute stream; `after_tail` (optional) runs once they are enqueued and before the host waits, so that the

@@ -133,3 +133,40 @@ void launch_detection_forward(const float *in, float *out, int batch, int output
         B200_LAUNCHED();
     }
 }
+
+// batch == 2 flip-averaging of `detector valid2` (avg_flipped_yolo, yolo_layer.c:290-314; the same loop inlined in
+// get_region_detections, region_layer.c:368-390), IN PLACE like the reference: item 1 (the mirrored image) is flipped back
+// horizontally, item 0 becomes the mean of the two.  The reference indexes the planes as [z][n] while l.output is laid out
+// [n][z]; both enumerate every plane once, so the flip is layout-independent, but the sign change it applies "for z == 0"
+// lands on the FIRST l.n planes of the buffer (not on each anchor's x entry) and skips the middle column of an odd width —
+// reproduced as is.  Two launches: the average reads what the flip wrote.
+__global__ void flip_item_kernel(float *__restrict__ flip, int w, int h, int planes, int neg_planes)
+{
+    const int half = w / 2;
+    const long long total = (long long)planes * h * half;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % half), j = (int)((t / half) % h), p = (int)(t / ((long long)half * h));
+        float *row = flip + ((size_t)p * h + j) * w;
+        float a = row[i], b = row[w - i - 1];
+        if (p < neg_planes) { a = -a; b = -b; }
+        row[i] = b; row[w - i - 1] = a;
+    }
+}
+
+__global__ void average_items_kernel(float *__restrict__ out, const float *__restrict__ flip, int outputs)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < outputs; i += gridDim.x * blockDim.x)
+        out[i] = (float)((double)__fadd_rn(out[i], flip[i]) / 2.);
+}
+
+void launch_avg_flipped(float *head_out, int w, int h, int anchors, int entries, int outputs, cudaStream_t s)
+{
+    const int planes = anchors * entries;
+    const long long swaps = (long long)planes * h * (w / 2);
+    if (swaps > 0) {
+        flip_item_kernel<<<(int)((swaps + kThreads - 1) / kThreads), kThreads, 0, s>>>(head_out + outputs, w, h, planes, anchors);
+        B200_LAUNCHED();
+    }
+    average_items_kernel<<<div_up(outputs, kThreads), kThreads, 0, s>>>(head_out, head_out + outputs, outputs);
+    B200_LAUNCHED();
+}

@@ -77,6 +77,8 @@ void launch_connected(const void *in, int in_dtype, int batch, int inputs, int o
 void launch_yolo_forward(TView in, float *out, int anchors, int classes, cudaStream_t s);
 void launch_region_forward(TView in, float *out, int anchors, int classes, int coords, int softmax, cudaStream_t s);
 void launch_detection_forward(const float *in, float *out, int batch, int outputs, int side, int classes, int softmax, cudaStream_t s);
+// l.batch == 2: item 0 <- mean(item 0, horizontally flipped item 1), in place (yolo_layer.c:290-314, region_layer.c:368-390)
+void launch_avg_flipped(float *head_out, int w, int h, int anchors, int entries, int outputs, cudaStream_t s);
 
 // ---- decode + NMS (decode.cu, nms.cu) --------------------------------------------------------------
 struct HeadDesc {            // one per YOLO/REGION/DETECTION layer, device-resident copy lives in the engine

@@ -15,6 +15,8 @@ int b200_engine_count_boxes(b200_engine *e, network *net, int image, float thres
 int b200_engine_decode_image(b200_engine *e, network *net, int image, int w, int h, float thresh, int relative,
                              const float **box, const float **obj, const float **prob, const int **id);
 int b200_engine_classes(b200_engine *e);
+void b200_engine_push_heads(b200_engine *e, network *net, int items);
+void b200_engine_avg_flipped(b200_engine *e, network *net);
 
 static int last_layer_classes(network *net) { return net->layers[net->n - 1].classes; }
 
@@ -36,8 +38,27 @@ static detection *alloc_dets(network *net, int nboxes)
     return dets;
 }
 
+/* l.batch == 2 on a [yolo] / [region] head: get_*_detections averages item 0 with the mirrored item 1 (`detector valid2`) */
+static int heads_flip(const network *net)
+{
+    for (int i = 0; i < net->n; ++i) {
+        const layer *l = &net->layers[i];
+        if ((l->type == YOLO || l->type == REGION) && l->batch == 2) return 1;
+    }
+    return 0;
+}
+
+/* the reference API reads the heads' HOST buffers; callers may have rewritten them since the last predict (demo.c:54-83) */
+static int push_heads(network *net)
+{
+    int flip = heads_flip(net);
+    b200_engine_push_heads(b200_engine_of(net), net, flip ? 2 : 1);
+    return flip;
+}
+
 detection *make_network_boxes(network *net, float thresh, int *num)
 {
+    push_heads(net);
     int nboxes = num_detections(net, thresh);
     if (num) *num = nboxes;
     return alloc_dets(net, nboxes);
@@ -62,7 +83,8 @@ static int fill_for_image(network *net, int image, int w, int h, float thresh, i
 
 void fill_network_boxes(network *net, int w, int h, float thresh, float hier, int *map, int relative, detection *dets)
 {
-    (void)hier; (void)map;          /* YOLO9000 hierarchy / map are outside this inference path */
+    (void)hier; (void)map;          /* YOLO9000 hierarchy / map: see get_network_boxes */
+    if (push_heads(net)) b200_engine_avg_flipped(b200_engine_of(net), net);
     fill_for_image(net, 0, w, h, thresh, relative, dets, -1);
 }
 
@@ -77,15 +99,22 @@ detection *get_network_boxes_batch(network *net, int b, int w, int h, float thre
     return dets;
 }
 
+/* network.c:559-567.  Like the reference this reads the heads' HOST buffers (a caller may have rewritten l.output since the
+ * last predict, demo.c:54-83), counts before and fills after the batch == 2 flip-average (make_network_boxes runs first,
+ * network.c:563-564; get_yolo_detections / get_region_detections average inside the fill, yolo_layer.c:320,
+ * region_layer.c:368-390): *num is the count of the un-averaged item 0 and records the averaged output no longer fills stay
+ * zero, exactly what the calloc'd reference array holds.  (Where the averaged output has MORE boxes over the threshold than
+ * were counted, the reference writes past its allocation; here the surplus is dropped.) */
 detection *get_network_boxes(network *net, int w, int h, float thresh, float hier, int *map, int relative, int *num)
 {
-    static int warned = 0;
-    if (net->layers[net->n - 1].batch == 2 && !warned) {
-        /* reference averages image + mirrored image when batch==2 (yolo_layer.c:320, region_layer.c:368-390) */
-        fprintf(stderr, "b200-darknet: note: batch==2 flip-averaging of `detector valid2` is not applied; item 0 is decoded as is\n");
-        warned = 1;
-    }
-    return get_network_boxes_batch(net, 0, w, h, thresh, hier, map, relative, num);
+    int flip = push_heads(net);
+    if (!flip) return get_network_boxes_batch(net, 0, w, h, thresh, hier, map, relative, num);
+    int nboxes = count_for_image(net, 0, thresh);
+    detection *dets = alloc_dets(net, nboxes);
+    b200_engine_avg_flipped(b200_engine_of(net), net);
+    fill_for_image(net, 0, w, h, thresh, relative, dets, nboxes);
+    if (num) *num = nboxes;
+    return dets;
 }
 
 void free_detections(detection *dets, int n)
