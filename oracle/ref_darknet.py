@@ -187,8 +187,9 @@ class RefNet:
             self.lib.free_network(self.ptr); self.ptr = None
 
 
-def ref_nms_sort_arrays(boxes, probs, thresh, objectness=None, o2=False):
-    """run the reference do_nms_sort on plain arrays -> probs after suppression, rows in INPUT order"""
+def ref_nms_sort_arrays(boxes, probs, thresh, objectness=None, o2=False, want_order=False):
+    """run the reference do_nms_sort on plain arrays -> probs after suppression, rows in INPUT order
+    (want_order: also the input row that ended up at each position of the reference's re-sorted array)"""
     path = REF_SO_O2 if o2 else REF_SO
     lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
     lib.do_nms_sort.argtypes = [POINTER(DETECTION), c_int, c_int, c_float]
@@ -206,7 +207,9 @@ def ref_nms_sort_arrays(boxes, probs, thresh, objectness=None, o2=False):
     addr_to_row = {ctypes.addressof(p): i for i, p in enumerate(keep_alive)}
     lib.do_nms_sort(arr, n, classes, thresh)
     out = np.zeros_like(probs)
+    order = []
     for j in range(n):
         row = addr_to_row[ctypes.cast(arr[j].prob, c_void_p).value]
         out[row] = np.ctypeslib.as_array(arr[j].prob, shape=(classes,))
-    return out
+        order.append(row)
+    return (out, order) if want_order else out

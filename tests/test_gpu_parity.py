@@ -620,6 +620,10 @@ def test_do_nms_sort_and_obj_through_detection_structs(dn):
             assert arr[j].objectness != 0            # objectness-0 rows were partitioned to the tail (box.c:60-70)
             live_seen += 1
     assert np.array_equal(got, P.do_nms_sort(boxes, obj, probs, .45))
+    # the array is left in the reference's order (one stable qsort per class, box.c:72-77; pinned on the reference build in
+    # tests/test_oracle.py): draw_detections prints in it
+    order = [addr[ctypes.cast(arr[j].prob, ctypes.c_void_p).value] for j in range(n)]
+    assert order == P.nms_sort_final_order(obj, probs)
     # do_nms_obj (python/darknet.py detect() uses it): class-agnostic, zeroes objectness and all probs
     arr, keep = build()
     addr = {ctypes.addressof(p): i for i, p in enumerate(keep)}

@@ -161,3 +161,18 @@ def test_reference_is_independent_of_fast_math_and_threads(workdir):
     probs = (rng.random((200, 5)) * (rng.random((200, 5)) > .5)).astype(np.float32)
     assert np.array_equal(R.ref_nms_sort_arrays(boxes, probs, .45), R.ref_nms_sort_arrays(boxes, probs, .45, o2=True))
     a.close(); b.close()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built on this box")
+def test_reference_nms_leaves_the_array_in_stable_chain_order():
+    """do_nms_sort re-sorts the struct array once per class with qsort (box.c:72-77).  On glibc that is a stable merge sort,
+    so the order a driver sees afterwards (draw_detections prints in it) is well defined: pinned here on the reference build,
+    restated by P.nms_sort_final_order and reproduced by the product's do_nms_sort (tests/test_gpu_parity.py)."""
+    rng = np.random.default_rng(12)
+    n, classes = 400, 6
+    boxes = np.concatenate([rng.random((n, 2)), rng.random((n, 2)) * .3 + .02], axis=1).astype(np.float32)
+    probs = (rng.random((n, classes)) * (rng.random((n, classes)) < .3)).astype(np.float32)       # many zero ties
+    probs[rng.random((n, classes)) < .1] = np.float32(.5)                                          # and equal non-zero scores
+    obj = (rng.random(n) > .15).astype(np.float32)
+    _, order = R.ref_nms_sort_arrays(boxes, probs, .45, obj, want_order=True)
+    assert order == P.nms_sort_final_order(obj, probs)

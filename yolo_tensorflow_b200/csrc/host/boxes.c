@@ -142,8 +142,19 @@ static int partition_live(detection *dets, int total)
     return k + 1;
 }
 
-/* stable descending order of `key` as an index permutation (bottom-up merge sort) */
-static int *stable_order_desc(const float *key, int n)
+/* stable descending order as an index permutation (bottom-up merge sort).  `key` has `stride` floats per row; rows are
+ * compared on columns ncols-1, ncols-2, ..., 0 in that order (ncols = 1: a plain sort by one value). */
+static int row_after(const float *key, int stride, int ncols, int a, int b)      /* does row b sort strictly before row a? */
+{
+    const float *ka = key + (size_t)a * stride, *kb = key + (size_t)b * stride;
+    for (int c = ncols - 1; c >= 0; --c) {
+        if (kb[c] > ka[c]) return 1;
+        if (kb[c] < ka[c]) return 0;
+    }
+    return 0;
+}
+
+static int *stable_order_desc(const float *key, int stride, int ncols, int n)
 {
     int *perm = malloc((size_t)n * sizeof(int)), *tmp = malloc((size_t)n * sizeof(int));
     for (int i = 0; i < n; ++i) perm[i] = i;
@@ -151,7 +162,7 @@ static int *stable_order_desc(const float *key, int n)
         for (int lo = 0; lo < n; lo += 2 * width) {
             int mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
             int a = lo, b = mid, o = lo;
-            while (a < mid && b < hi) tmp[o++] = key[perm[b]] > key[perm[a]] ? perm[b++] : perm[a++];
+            while (a < mid && b < hi) tmp[o++] = row_after(key, stride, ncols, perm[a], perm[b]) ? perm[b++] : perm[a++];
             while (a < mid) tmp[o++] = perm[a++];
             while (b < hi) tmp[o++] = perm[b++];
         }
@@ -175,21 +186,24 @@ void do_nms_sort(detection *dets, int total, int classes, float thresh)
     if (total <= 0 || classes <= 0) return;
     float *boxes = malloc((size_t)total * 4 * sizeof(float));
     float *probs = malloc((size_t)total * classes * sizeof(float));
-    float *key = malloc((size_t)total * sizeof(float));
+    float *key = malloc((size_t)total * classes * sizeof(float));
     for (int i = 0; i < total; ++i) {
         boxes[4 * i + 0] = dets[i].bbox.x; boxes[4 * i + 1] = dets[i].bbox.y;
         boxes[4 * i + 2] = dets[i].bbox.w; boxes[4 * i + 3] = dets[i].bbox.h;
         memcpy(probs + (size_t)i * classes, dets[i].prob, (size_t)classes * sizeof(float));
-        key[i] = dets[i].prob[classes - 1];
     }
+    memcpy(key, probs, (size_t)total * classes * sizeof(float));
     b200_nms_sort_arrays(boxes, probs, total, classes, thresh);      /* device: all classes in parallel */
     for (int i = 0; i < total; ++i) {
         memcpy(dets[i].prob, probs + (size_t)i * classes, (size_t)classes * sizeof(float));
         dets[i].sort_class = classes - 1;
     }
-    /* observable side effect of the reference: the array ends up ordered by the LAST class's score as it was
-     * before that class's suppression (box.c:72-77); prob/mask pointers travel with their structs */
-    int *perm = stable_order_desc(key, total);
+    /* observable side effect of the reference: the array is re-sorted once per class (box.c:72-77), each time by that class's
+     * score as it is BEFORE that class's suppression, and glibc's qsort is a merge sort (stable) — so the array ends up ordered
+     * by the last class's score, ties by the class before it, and so on down to class 0, then by the partitioned input order
+     * (tests/test_oracle.py pins this on the reference build).  draw_detections prints in that order.  prob/mask pointers
+     * travel with their structs. */
+    int *perm = stable_order_desc(key, classes, classes, total);
     permute_dets(dets, perm, total);
     free(perm); free(key); free(boxes); free(probs);
 }
@@ -202,7 +216,7 @@ void do_nms_obj(detection *dets, int total, int classes, float thresh)
     {
         float *key = malloc((size_t)total * sizeof(float));
         for (int i = 0; i < total; ++i) { dets[i].sort_class = -1; key[i] = dets[i].objectness; }
-        int *perm = stable_order_desc(key, total);
+        int *perm = stable_order_desc(key, 1, 1, total);
         permute_dets(dets, perm, total);
         free(perm); free(key);
     }
