@@ -45,6 +45,7 @@ b200_engine *b200_engine_create(network *net, int precision);   /* plans buffers
 void b200_engine_destroy(b200_engine *e);
 void b200_engine_upload_weights(b200_engine *e, network *net);    /* BN folding + repack (+ bf16 cast) + H2D */
 b200_engine *b200_engine_recreate(b200_engine *old, network *net); /* resize_network: re-plan, keep settings, re-upload */
+void b200_engine_unpin_host(b200_engine *e);                      /* before host code frees / re-allocates l.output buffers */
 
 /* forward_network replacement (network.c:188-211).  `input` is HOST fp32 NCHW, batch*inputs floats. */
 void b200_engine_forward(b200_engine *e, network *net, const float *input);
@@ -75,6 +76,10 @@ unsigned long long b200_launch_count(void);
 void *b200_engine_stream(network *net);
 /* average device milliseconds per layer over `iters` forwards (CUDA events between layers); ms has net->n entries */
 void b200_profile_layers(network *net, int iters, float *ms);
+
+/* device milliseconds of the forward pass exactly as the serving loop enqueues it (no per-layer brackets): ms[0] = whole pass,
+ * ms[1] = the first layer alone; averaged over `iters` after one warm-up */
+void b200_profile_forward(network *net, int iters, float *ms);
 
 /* device milliseconds of the post-network tail on the current head outputs: ms[0] decode+compaction, ms[1] NMS, ms[2] collect */
 void b200_profile_tail(network *net, int w, int h, float thresh, float nms_thresh, int iters, float *ms);
@@ -155,6 +160,23 @@ int b200_detect_batch(network *net, const float *input, int w, int h, float thre
 void b200_submit_batch(network *net, const float *input);
 int  b200_detect_submitted(network *net, const float *next_input, int w, int h, float thresh, float nms_thresh, int relative,
                            b200_det *out, int max_out, int *counts);
+
+/* ---- multi-GPU: image-sharded replicas, one process per GPU --------------------------------------------
+ * Every process parses the same cfg; rank `root` alone loads the .weights file.  NCCL is resolved at run time (dlopen of
+ * libnccl.so.2).  The 128-byte id made by b200_comm_unique_id on one rank reaches the others by any out-of-band channel
+ * (bench.py: torch.distributed's store).  No collective ever runs between layers:
+ *   b200_comm_broadcast_weights   one ncclBroadcast of the folded / repacked parameter arena (b200_weights_arena);
+ *   b200_comm_set_gather          from then on b200_detect_batch / b200_detect_submitted on `root` return the records of ALL
+ *                                 ranks — rank order, image = image_base of the producing rank + its local index — moved by
+ *                                 ncclSend/ncclRecv on the result stream beside the next batch's forward pass; the other
+ *                                 ranks keep getting their own.  slot_records = most records one rank may contribute per batch. */
+int  b200_comm_unique_id(unsigned char *id, int bytes);           /* bytes >= 128; returns the id length */
+int  b200_comm_init(network *net, const unsigned char *id, int rank, int world);
+int  b200_comm_rank(network *net);
+int  b200_comm_world(network *net);
+int  b200_comm_broadcast_weights(network *net, int root);
+int  b200_comm_set_gather(network *net, int root, int image_base, int slot_records);      /* root = -1: off */
+void b200_comm_destroy(network *net);
 
 /* device NMS on caller-provided host boxes (the kernel behind do_nms_sort); exposed for parity tests:
  * boxes[n*4] (x,y,w,h), probs[n*classes] row-major, modified in place exactly like box.c:58-89 zeroes prob[k]. */

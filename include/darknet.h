@@ -30,7 +30,7 @@ extern int gpu_index;                       /* reference darknet.h:9 — device 
 /* ---- small public records ------------------------------------------------------------------ */
 typedef struct { int classes; char **names; } metadata;                    /* ref :35-38 */
 
-typedef struct {                                                             /* ref :42-53 (YOLO9000 tree; unused here) */
+typedef struct {                                                             /* ref :42-53 (YOLO9000 WordTree: read_tree, [region] tree=) */
     int *leaf; int n; int *parent; int *child; int *group; char **name;
     int groups; int *group_size; int *group_offset;
 } tree;
@@ -180,6 +180,9 @@ void   option_unused(list *l);                                              /* o
 list  *get_paths(char *filename);                                           /* ref :762  data.c:12         */
 char **get_labels(char *filename);                                          /* ref :750  data.c:618        */
 int   *read_map(char *filename);                                            /* ref :774  utils.c:62        */
+tree  *read_tree(char *filename);                                           /* tree.c:83  (YOLO9000 WordTree, `tree=` of [region]) */
+void   hierarchy_predictions(float *predictions, int n, tree *hier, int only_leaves, int stride);   /* ref :763  tree.c:37 */
+int    hierarchy_top_prediction(float *predictions, tree *hier, float thresh, int stride);          /* tree.c:53 */
 int    find_arg(int argc, char *argv[], char *arg);                         /* ref :768  utils.c:120       */
 int    find_int_arg(int argc, char **argv, char *arg, int def);             /* ref :766  utils.c:133       */
 float  find_float_arg(int argc, char **argv, char *arg, float def);         /* ref :767  utils.c:148       */

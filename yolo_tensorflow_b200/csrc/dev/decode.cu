@@ -195,8 +195,34 @@ decode_emit_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_ima
 }
 
 // class probabilities of the survivors: one warp per survivor, lanes over classes (coalesced writes, 32 loads in flight)
+// hierarchy_top_prediction (tree.c:53-81) on absolute probabilities strided by `stride`
+__device__ int tree_top_prediction(const float *pred, const HeadDesc &hd, float thresh, int stride)
+{
+    float p = 1.f;
+    int group = 0;
+    for (;;) {
+        float best = 0.f;
+        int best_i = 0;
+        const int off = hd.tree_goff[group], sz = hd.tree_gsize[group];
+        for (int i = 0; i < sz; ++i) {
+            const float val = pred[(size_t)(off + i) * stride];
+            if (val > best) { best_i = off + i; best = val; }
+        }
+        if (__fmul_rn(p, best) > thresh) {
+            p = __fmul_rn(p, best);
+            group = hd.tree_child[best_i];
+            if (group < 0) return best_i;
+        } else if (group == 0) {
+            return best_i;
+        } else {
+            return hd.tree_parent[hd.tree_goff[group]];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
-decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, float thresh, int mode, int use_raw, CandBuffers cb)
+decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_image, float thresh, int mode, int use_raw, CandBuffers cb,
+                    float tree_thresh, const int *__restrict__ map)
 {
     const int slot = blockIdx.y, img = first_image + blockIdx.y, lane = threadIdx.x & 31;
     const int n = cb.count[slot];
@@ -208,6 +234,20 @@ decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_im
         box_keep(hd, pred, local, thresh, mode, objectness, scale, cell, a, img, use_raw);
         const int wh = hd.w * hd.h;
         float *pr = cb.prob + ((size_t)slot * cb.cap + d) * cb.classes;
+        if (hd.type == REGION && hd.tree_parent) {
+            // region_layer.c:412-424: the class entries already hold absolute probabilities (hierarchy_predictions ran); with
+            // a map the 200 mapped classes are scored like plain classes, without one the single most specific class whose
+            // path stays over tree_thresh gets the box's objectness
+            const float *cls = pred + ((size_t)a * (hd.coords + hd.classes + 1) + hd.coords + 1) * wh + cell;
+            for (int j = lane; j < hd.classes; j += 32) {
+                float p = 0.f;
+                if (map && j < 200) { p = __fmul_rn(scale, cls[(size_t)map[j] * wh]); p = p > thresh ? p : 0.f; }
+                pr[j] = p;
+            }
+            __syncwarp();
+            if (!map && lane == 0) pr[tree_top_prediction(cls, hd, tree_thresh, wh)] = scale > thresh ? scale : 0.f;
+            continue;
+        }
         for (int j = lane; j < hd.classes; j += 32) {
             float p;
             if (hd.type == YOLO) p = __fmul_rn(objectness, yolo_entry(hd, pred, img, a, 5 + j, cell, use_raw));
@@ -219,7 +259,8 @@ decode_probs_kernel(const HeadDesc *__restrict__ heads, int nheads, int first_im
 }
 
 void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s, const int *im_dims)
+                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s, const int *im_dims,
+                   float tree_thresh, const int *map_dev)
 {
     const int boxes = cb.cap;                                       // cap == anchor boxes per image
     const int words = (boxes + 31) / 32;
@@ -231,7 +272,7 @@ void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int n
     decode_emit_kernel<<<grid, 256, 0, s>>>(heads_dev, nheads, first_image, boxes, words, netw, neth, imw, imh, im_dims, thresh, relative, mode,
                                             use_raw, cb.flags, cb.offsets, cb);
     B200_LAUNCHED();
-    decode_probs_kernel<<<dim3(8, nimages), 256, 0, s>>>(heads_dev, nheads, first_image, thresh, mode, use_raw, cb);
+    decode_probs_kernel<<<dim3(8, nimages), 256, 0, s>>>(heads_dev, nheads, first_image, thresh, mode, use_raw, cb, tree_thresh, map_dev);
     B200_LAUNCHED();
 }
 

@@ -9,75 +9,9 @@
 //   * parameters   one contiguous arena: per conv [Cout_pad][ky][kx][Cin] in the activation dtype + fp32
 //                  scale/shift (inference batch-norm folded to one multiply-add per output);
 //   * candidates   SoA per image: box[cap][4], objectness[cap], prob[cap][classes], id[cap], count.
-#include "kernels.h"
-#include "b200_engine.h"
-#include <vector>
-#include <string>
+#include "engine.h"
 #include <cmath>
 #include <cstring>
-
-struct DevLayer {
-    LAYER_TYPE type;
-    TView out;                 // NHWC output view (n = planned batch capacity)
-    bool owns_out;
-    float *head_out;           // YOLO / REGION / DETECTION / CONNECTED: fp32 [batch][outputs]
-    float *fc_tmp;             // CONNECTED on tcgen05: fp32 [batch][cout_pad] (row-padded GEMM output, compacted into head_out)
-    // parameters (inside the arena)
-    void *w;
-    float *scale, *shift, *lbias;
-    size_t w_off, scale_off, shift_off, lbias_off, w_bytes;
-    int cout_pad;
-    ConvTcPlan *tc;
-    bool stem;
-    int stem_kpad;             // > 0: first layer runs as im2col (fp32 NCHW -> bf16 [pixels][kpad]) + dense tcgen05 GEMM
-    bf16 *stem_cols;
-    int fused_into;            // conv whose epilogue also performs shortcut layer `fused_into` (its own output is not materialised)
-    bool fused_away;           // shortcut executed inside the previous conv's epilogue
-    bool up_fused;             // conv that writes its result 2x upsampled straight into the following [upsample]'s buffer
-    bool up_away;              // [upsample] performed by the previous conv's store warp
-    bool pool_fused;           // stem conv whose store warp also performs the following [maxpool] 2/2 (its own output is not written)
-    bool pool_away;            // [maxpool] performed inside the stem kernel
-    bool block_head;           // 1x1 conv computed inside the following 3x3's kernel (fused residual block): launches nothing
-    std::string kernel;
-};
-
-struct b200_engine {
-    int precision, act_dtype;
-    int n, cap;                // layers, batch capacity
-    int device;
-    int conv_backend, head_sync, fusion;
-    cudaStream_t stream;
-    cudaStream_t copy_stream;  // H2D of the input batch, chunked so the first layer starts while later images are still in flight
-    cudaEvent_t copy_done[8];
-    std::vector<DevLayer> L;
-    float *d_input;            // fp32 NCHW network input [cap][inputs]
-    float *d_input_next;       // spare input buffer: b200_submit_batch copies batch k+1 here while batch k computes
-    cudaEvent_t submit_done;
-    int submitted;
-    cudaStream_t d2h_stream;   // serving loop: results of batch k are read back here while batch k+1 already computes
-    cudaEvent_t tail_done;     // decode + NMS + collect of the current batch finished (d2h_stream waits on it)
-    cudaEvent_t lb_uploaded, lb_done;   // b200_letterbox_batch*: raw images are on the device / the resize kernel has consumed them
-    int fwd_enqueued;          // the submitted batch's forward pass is already in the compute stream (b200_detect_submitted)
-    TView in_view;             // NHWC copy of the input (only when layer 0 is not a stem conv)
-    unsigned char *arena;      // parameters
-    size_t arena_bytes;
-    float *xfer;               // fp32 scratch for fetch/set (max layer size)
-    size_t xfer_floats;
-    // decode / nms
-    std::vector<HeadDesc> heads;
-    HeadDesc *d_heads;
-    int boxes_per_image, classes;
-    bool raw_decode_ok;        // every head is a [yolo] layer fed by an fp32-logit convolution: the fused path may skip yolo_forward
-    CandBuffers cand;          // device
-    int cand_slots;
-    NmsScratch nms_scratch;
-    DetRecord *d_records; int records_cap; int *d_record_count;
-    unsigned char *d_raw; size_t raw_cap;            // b200_letterbox_batch*: source images on the device
-    LetterboxItem *d_lb_items; int *d_im_dims[2];    // per-image resize geometry / original sizes (box correction):
-    int dims_cur, dims_pending;                      // [dims_cur] belongs to the batch whose forward pass was enqueued last, the other slot to the next letterbox call
-    // host staging for one image's candidates
-    float *h_box, *h_obj, *h_prob; int *h_id; int h_cap;
-};
 
 static void *dev_alloc(size_t bytes)
 {
@@ -483,12 +417,48 @@ static void build_engine_device_state(b200_engine *e, network *net)
             h.anchors[2 * a] = l.biases[2 * src];
             h.anchors[2 * a + 1] = l.biases[2 * src + 1];
         }
+        if (l.type == REGION && l.softmax_tree) {
+            const tree *t = l.softmax_tree;
+            for (int j = 0; j < t->n; ++j) {                 // the device walk keeps a path in registers
+                int depth = 0;
+                for (int c = j; c >= 0; c = t->parent[c]) if (++depth > 64) { fprintf(stderr, "b200-darknet: class tree deeper than 64 levels\n"); abort(); }
+            }
+            auto put = [&](const int *src, int count) {
+                int *d = (int *)dev_alloc((size_t)count * sizeof(int));
+                B200_CHECK(cudaMemcpy(d, src, (size_t)count * sizeof(int), cudaMemcpyHostToDevice));
+                e->tree_arrays.push_back(d);
+                return (const int *)d;
+            };
+            h.tree_parent = put(t->parent, t->n); h.tree_child = put(t->child, t->n);
+            h.tree_gsize = put(t->group_size, t->groups); h.tree_goff = put(t->group_offset, t->groups);
+            h.tree_groups = t->groups;
+            e->has_tree = true;
+        }
         h.box_base = base;
         base += l.w * l.h * l.n;
         e->heads.push_back(h);
+        if (e->classes && e->classes != l.classes) {
+            // make_network_boxes sizes every prob[] from the LAST layer's classes (network.c:528-534) and each get_*_detections
+            // writes its own l.classes of them: heads that disagree overrun the rows in the reference; rejected here
+            fprintf(stderr, "b200-darknet: detection heads with different class counts (%d and %d) are not supported\n", e->classes, l.classes);
+            abort();
+        }
         e->classes = l.classes;                  // network.c:528 takes classes from the LAST layer
     }
     e->boxes_per_image = base;
+    // the reference API moves the heads' l.output between host and device on every call (network.c:505, yolo_layer.c:359-362
+    // on the way out; get_network_boxes reads them on the way in): page-lock those host buffers while this plan lives
+    {
+        int last = net->n - 1;
+        while (last > 0 && net->layers[last].type == COST) --last;
+        for (int i = 0; i < net->n; ++i) {
+            const layer &l = net->layers[i];
+            const bool head = l.type == YOLO || l.type == REGION || l.type == DETECTION;
+            if ((!head && i != last) || !l.output || l.type == DROPOUT) continue;
+            if (cudaHostRegister(l.output, (size_t)e->cap * l.outputs * sizeof(float), cudaHostRegisterDefault) == cudaSuccess) e->pinned_host.push_back(l.output);
+            else cudaGetLastError();                       // not fatal: the copies just stay pageable
+        }
+    }
     if (!e->heads.empty()) {
         e->d_heads = (HeadDesc *)dev_alloc(e->heads.size() * sizeof(HeadDesc));
         B200_CHECK(cudaMemcpy(e->d_heads, e->heads.data(), e->heads.size() * sizeof(HeadDesc), cudaMemcpyHostToDevice));
@@ -512,10 +482,10 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
     memset(&e->cand, 0, sizeof e->cand); e->cand_slots = 0;
     memset(&e->nms_scratch, 0, sizeof e->nms_scratch);
-    e->d_records = nullptr; e->records_cap = 0; e->d_record_count = nullptr;
+    e->d_records = nullptr; e->records_cap = 0; e->d_record_count = nullptr; e->comm = nullptr;
     e->d_raw = nullptr; e->raw_cap = 0; e->d_lb_items = nullptr; e->d_im_dims[0] = e->d_im_dims[1] = nullptr; e->dims_cur = 0; e->dims_pending = 0;
     e->h_box = e->h_obj = e->h_prob = nullptr; e->h_id = nullptr; e->h_cap = 0;
-    e->boxes_per_image = 0; e->classes = 0;
+    e->boxes_per_image = 0; e->classes = 0; e->has_tree = false; e->d_map = nullptr;
     // Parsing a cfg (layer table, shapes) works on a machine without a GPU; anything that computes does not.
     if (cuda_usable()) build_engine_device_state(e, net);
     else e->device = -1;
@@ -532,12 +502,22 @@ static void need_device(const b200_engine *e, const char *what)
     B200_CHECK(cudaSetDevice(e->device));
 }
 
+// host code calls this before it frees or re-allocates layer outputs (resize_network, free_network)
+extern "C" void b200_engine_unpin_host(b200_engine *e)
+{
+    if (!e || e->device < 0) return;
+    for (void *p : e->pinned_host) if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+    e->pinned_host.clear();
+}
+
 extern "C" void b200_engine_destroy(b200_engine *e)
 {
     if (!e) return;
     if (e->device >= 0) {
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->stream);
+        if (e->comm) b200_comm_release(e);
+        b200_engine_unpin_host(e);
         for (auto &d : e->L) {
             if (d.tc) conv_tc_plan_destroy(d.tc);
             if (d.owns_out) cudaFree(d.out.p);
@@ -548,6 +528,8 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaFree(e->cand.box); cudaFree(e->cand.obj); cudaFree(e->cand.prob); cudaFree(e->cand.id); cudaFree(e->cand.count);
         cudaFree(e->cand.flags); cudaFree(e->cand.offsets); cudaFree(e->cand.cls_count);
         cudaFree(e->nms_scratch.mask); cudaFree(e->d_records); cudaFree(e->d_record_count);
+        for (int *p : e->tree_arrays) cudaFree(p);
+        cudaFree(e->d_map);
         cudaFree(e->d_raw); cudaFree(e->d_lb_items); cudaFree(e->d_im_dims[0]); cudaFree(e->d_im_dims[1]);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
         for (auto &ev : e->copy_done) cudaEventDestroy(ev);
@@ -639,12 +621,15 @@ extern "C" void b200_engine_upload_weights(b200_engine *e, network *net)
 extern "C" b200_engine *b200_engine_recreate(b200_engine *old, network *net)
 {
     const int precision = old->precision, fusion = old->fusion, head_sync = old->head_sync;
+    B200Comm *comm = old->comm;                 // the communicator belongs to the process, not to the plan
+    old->comm = nullptr;
     b200_engine_destroy(old);
     const int default_fusion = b200_get_default_fusion();
     b200_set_default_fusion(fusion);
     b200_engine *e = b200_engine_create(net, precision);
     b200_set_default_fusion(default_fusion);
     e->head_sync = head_sync;
+    e->comm = comm;
     if (e->device >= 0) b200_engine_upload_weights(e, net);
     return e;
 }
@@ -725,7 +710,12 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
         break;
     }
     case YOLO: launch_yolo_forward(in, d.head_out, l.n, l.classes, s); break;
-    case REGION: launch_region_forward(in, d.head_out, l.n, l.classes, l.coords, l.softmax, s); break;
+    case REGION:
+        if (l.softmax_tree) {
+            for (const HeadDesc &h : e->heads)
+                if (h.out == d.head_out) launch_region_tree_forward(in, d.head_out, l.n, l.classes, l.coords, h.tree_gsize, h.tree_goff, h.tree_groups, s);
+        } else launch_region_forward(in, d.head_out, l.n, l.classes, l.coords, l.softmax, s);
+        break;
     case DETECTION: launch_detection_forward(e->L[i - 1].head_out, d.head_out, batch, l.outputs, l.side, l.classes, l.softmax, s); break;
     default: break;
     }
@@ -930,7 +920,7 @@ extern "C" void b200_profile_tail(network *net, int w, int h, float thresh, floa
     ensure_candidates(e, e->cap);
     int max_out = 1 << 20;
     if (e->records_cap < max_out) { cudaFree(e->d_records); e->d_records = (DetRecord *)dev_alloc((size_t)max_out * sizeof(DetRecord)); e->records_cap = max_out; }
-    if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
+    if (!e->d_record_count) { e->d_record_count = (int *)dev_alloc(4 * sizeof(int)); B200_CHECK(cudaMemset(e->d_record_count, 0, 4 * sizeof(int))); }
     cudaEvent_t ev[4];
     for (auto &x : ev) B200_CHECK(cudaEventCreate(&x));
     for (int it = -1; it < iters; ++it) {                 // iteration -1 is an untimed warm-up (scratch allocation)
@@ -986,6 +976,40 @@ extern "C" void b200_profile_layers(network *net, int iters, float *ms)
     for (auto &x : ev) cudaEventDestroy(x);
 }
 
+// device time of the forward pass as the serving loop runs it — `iters` passes enqueued back to back (no host
+// synchronisation between them, programmatic dependent launch and all, the raw-logit decode plan when head sync is off):
+// ms[0] = (last event - first event) / iters = one whole pass, ms[1] = the first layer alone, from one event pair around it
+// inside every pass (the stem is not part of the tcgen05 convolution family whose roofline bench.py reports).
+extern "C" void b200_profile_forward(network *net, int iters, float *ms)
+{
+    b200_engine *e = b200_engine_of(net);
+    need_device(e, "b200_profile_forward");
+    const int batch = logical_batch(e, net);
+    const bool skip_yolo = !e->head_sync && e->raw_decode_ok && !e->heads.empty();
+    if (iters < 1) iters = 1;
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters + 1);
+    for (auto &x : ev) B200_CHECK(cudaEventCreate(&x));
+    auto one_pass = [&](int it) {
+        if (!e->L[0].stem) { TView v = e->in_view; v.n = batch; launch_nchw_f32_to_view(e->d_input, v, e->stream); }
+        if (it >= 0) B200_CHECK(cudaEventRecord(ev[2 * it], e->stream));
+        run_layer(e, net, 0, batch);
+        if (it >= 0) B200_CHECK(cudaEventRecord(ev[2 * it + 1], e->stream));
+        for (int i = 1; i < net->n; ++i) {
+            if (skip_yolo && net->layers[i].type == YOLO) continue;
+            run_layer(e, net, i, batch);
+        }
+    };
+    one_pass(-1);                                             // warm-up, then the timed passes without a gap
+    for (int it = 0; it < iters; ++it) one_pass(it);
+    B200_CHECK(cudaEventRecord(ev[2 * iters], e->stream));
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    float total = 0.f, first = 0.f;
+    B200_CHECK(cudaEventElapsedTime(&total, ev[0], ev[2 * iters]));
+    for (int it = 0; it < iters; ++it) { float t = 0.f; B200_CHECK(cudaEventElapsedTime(&t, ev[2 * it], ev[2 * it + 1])); first += t; }
+    ms[0] = total / iters; ms[1] = first / iters;
+    for (auto &x : ev) cudaEventDestroy(x);
+}
+
 extern "C" const char *b200_layer_kernel(network *net, int i)
 {
     b200_engine *e = b200_engine_of(net);
@@ -1035,13 +1059,40 @@ extern "C" int b200_engine_count_boxes(b200_engine *e, network *net, int image, 
     return n;
 }
 
+// hierarchy_predictions over batch item `image` of every [region] head with a WordTree (region_layer.c:412-414), in place
+// like the reference (device buffer and, with head sync, the host copy): call once per get_network_boxes
+extern "C" void b200_engine_hierarchy(b200_engine *e, network *net, int image)
+{
+    need_device(e, "get_network_boxes");
+    for (int i = 0; i < net->n; ++i) {
+        const layer &l = net->layers[i];
+        if (l.type != REGION || !l.softmax_tree) continue;
+        for (const HeadDesc &h : e->heads) {
+            if (h.out != e->L[i].head_out) continue;
+            float *item = e->L[i].head_out + (size_t)image * l.outputs;
+            launch_region_hierarchy(item, e->xfer, l.w * l.h, l.n, l.classes, l.coords, h.tree_parent, e->stream);
+            if (e->head_sync && l.output)
+                B200_CHECK(cudaMemcpyAsync(l.output + (size_t)image * l.outputs, item, (size_t)l.outputs * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        }
+    }
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" int b200_engine_has_tree(b200_engine *e) { return e->has_tree ? 1 : 0; }
+
 extern "C" int b200_engine_decode_image(b200_engine *e, network *net, int image, int w, int h, float thresh, int relative,
-                                        const float **box, const float **obj, const float **prob, const int **id)
+                                        const float **box, const float **obj, const float **prob, const int **id, float hier, const int *map)
 {
     need_device(e, "get_network_boxes");
     if (e->heads.empty()) return 0;
     ensure_candidates(e, 1);
-    launch_decode(e->d_heads, (int)e->heads.size(), image, 1, net->w, net->h, w, h, thresh, relative, 0, 0, e->cand, e->stream);
+    const int *d_map = nullptr;
+    if (map && e->has_tree) {                          // the 200 class indices of coco9k.map / inet9k.map (detector.c:392, region_layer.c:415)
+        if (!e->d_map) e->d_map = (int *)dev_alloc(200 * sizeof(int));
+        B200_CHECK(cudaMemcpyAsync(e->d_map, map, 200 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        d_map = e->d_map;
+    }
+    launch_decode(e->d_heads, (int)e->heads.size(), image, 1, net->w, net->h, w, h, thresh, relative, 0, 0, e->cand, e->stream, nullptr, hier, d_map);
     int n = 0;
     B200_CHECK(cudaMemcpyAsync(&n, e->cand.count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     B200_CHECK(cudaStreamSynchronize(e->stream));
@@ -1103,6 +1154,10 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
                        b200_det *out, int max_out, int *counts, F after_tail)
 {
     int batch = logical_batch(e, net);
+    if (e->has_tree) {
+        fprintf(stderr, "b200-darknet: networks with a class tree (YOLO9000) go through get_network_boxes + do_nms_sort; the fused batched path does not take them\n");
+        abort();
+    }
     // with head sync off nobody reads l.output of the heads: skip forward_yolo_layer and decode from the head convolutions'
     // fp32 logits (identical arithmetic: the logistic is evaluated on the fly for the objectness test and for survivors)
     const int use_raw = (!e->head_sync && e->raw_decode_ok && !e->heads.empty()) ? 1 : 0;
@@ -1115,7 +1170,7 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
         e->d_records = (DetRecord *)dev_alloc((size_t)max_out * sizeof(DetRecord));
         e->records_cap = max_out;
     }
-    if (!e->d_record_count) e->d_record_count = (int *)dev_alloc(sizeof(int));
+    if (!e->d_record_count) { e->d_record_count = (int *)dev_alloc(4 * sizeof(int)); B200_CHECK(cudaMemset(e->d_record_count, 0, 4 * sizeof(int))); }
     // w == h == 0: every image is corrected with its own original size, recorded by b200_letterbox_batch*
     const int *im_dims = (w == 0 && h == 0) ? e->d_im_dims[e->dims_cur] : nullptr;
     if (w == 0 && h == 0 && !im_dims) { fprintf(stderr, "b200-darknet: w = h = 0 needs a preceding b200_letterbox_batch call\n"); abort(); }
@@ -1126,14 +1181,20 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
     launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
                    e->d_records, max_out, e->d_record_count, e->stream);
     B200_CHECK(cudaEventRecord(e->tail_done, e->stream));
-    after_tail();
     B200_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->tail_done, 0));
+    // multi-GPU: every rank's records travel to the gather root over NCCL (send/recv on the result stream, so the transfer
+    // runs beside the next batch's forward pass like the read-back does); the root then returns all of them.  Enqueued BEFORE
+    // the next batch's kernels are submitted, so that the copy kernels are not queued behind a whole forward pass.
+    const bool gather = b200_comm_gathers(e);
+    if (gather) b200_comm_enqueue_gather(e, e->d2h_stream);
+    after_tail();
     int n = 0;
     B200_CHECK(cudaMemcpyAsync(&n, e->d_record_count, sizeof(int), cudaMemcpyDeviceToHost, e->d2h_stream));
     if (counts) B200_CHECK(cudaMemcpyAsync(counts, e->cand.count, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, e->d2h_stream));
     B200_CHECK(cudaStreamSynchronize(e->d2h_stream));
     if (n > max_out) n = max_out;
     static_assert(sizeof(DetRecord) == sizeof(b200_det), "record layouts must match");
+    if (gather && b200_comm_is_root(e)) return b200_comm_collect_gathered(e, out, max_out, n, e->d2h_stream);
     if (n > 0) {
         B200_CHECK(cudaMemcpyAsync(out, e->d_records, (size_t)n * sizeof(DetRecord), cudaMemcpyDeviceToHost, e->d2h_stream));
         B200_CHECK(cudaStreamSynchronize(e->d2h_stream));
@@ -1295,46 +1356,53 @@ extern "C" int b200_detect_submitted(network *net, const float *next_input, int 
     });
 }
 
-// device NMS on caller-provided host arrays (the kernel behind do_nms_sort / do_nms_obj)
-static cudaStream_t g_nms_stream = nullptr;
-static NmsScratch g_nms_scratch = {nullptr, 0, 0};
+// device NMS on caller-provided host arrays (the kernel behind do_nms_sort / do_nms_obj).  Stream, scratch slab and staging
+// buffers are kept per DEVICE and only ever grow: a `darknet detect`-style caller pays no cudaMalloc / cudaFree per call.
+struct NmsHostPath {
+    cudaStream_t stream;
+    NmsScratch scratch;
+    float *d_box, *d_val; int *d_cls;
+    size_t box_floats, val_floats, cls_ints;
+};
+static NmsHostPath g_nms_path[64];
 
-static void nms_prepare()
+static NmsHostPath &nms_prepare(size_t box_floats, size_t val_floats, size_t cls_ints)
 {
     if (!cuda_usable()) {
         fprintf(stderr, "b200-darknet: do_nms_sort/do_nms_obj need a CUDA device. There is no CPU fallback.\n");
         abort();
     }
-    if (!g_nms_stream) B200_CHECK(cudaStreamCreateWithFlags(&g_nms_stream, cudaStreamNonBlocking));
+    int dev = 0;
+    B200_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { fprintf(stderr, "b200-darknet: device ordinal %d out of range\n", dev); abort(); }
+    NmsHostPath &p = g_nms_path[dev];
+    if (!p.stream) B200_CHECK(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    if (p.box_floats < box_floats) { cudaFree(p.d_box); p.d_box = (float *)dev_alloc(box_floats * sizeof(float)); p.box_floats = box_floats; }
+    if (p.val_floats < val_floats) { cudaFree(p.d_val); p.d_val = (float *)dev_alloc(val_floats * sizeof(float)); p.val_floats = val_floats; }
+    if (p.cls_ints < cls_ints) { cudaFree(p.d_cls); p.d_cls = (int *)dev_alloc(cls_ints * sizeof(int)); p.cls_ints = cls_ints; }
+    return p;
 }
 
 extern "C" void b200_nms_sort_arrays(const float *boxes, float *probs, int n, int classes, float thresh)
 {
     if (n <= 0 || classes <= 0) return;
-    nms_prepare();
-    float *d_box = (float *)dev_alloc((size_t)n * 4 * sizeof(float));
-    float *d_prob = (float *)dev_alloc((size_t)n * classes * sizeof(float));
-    B200_CHECK(cudaMemcpyAsync(d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
-    B200_CHECK(cudaMemcpyAsync(d_prob, probs, (size_t)n * classes * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
-    int *d_cls = (int *)dev_alloc(((size_t)classes + 1) * sizeof(int));
-    launch_nms_sort(d_box, d_prob, nullptr, nullptr, 1, n, classes, thresh, n, &g_nms_scratch, d_cls, g_nms_stream);
-    B200_CHECK(cudaMemcpyAsync(probs, d_prob, (size_t)n * classes * sizeof(float), cudaMemcpyDeviceToHost, g_nms_stream));
-    B200_CHECK(cudaStreamSynchronize(g_nms_stream));
-    cudaFree(d_box); cudaFree(d_prob); cudaFree(d_cls);
+    NmsHostPath &p = nms_prepare((size_t)n * 4, (size_t)n * classes, (size_t)classes + 1);
+    B200_CHECK(cudaMemcpyAsync(p.d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, p.stream));
+    B200_CHECK(cudaMemcpyAsync(p.d_val, probs, (size_t)n * classes * sizeof(float), cudaMemcpyHostToDevice, p.stream));
+    launch_nms_sort(p.d_box, p.d_val, nullptr, nullptr, 1, n, classes, thresh, n, &p.scratch, p.d_cls, p.stream);
+    B200_CHECK(cudaMemcpyAsync(probs, p.d_val, (size_t)n * classes * sizeof(float), cudaMemcpyDeviceToHost, p.stream));
+    B200_CHECK(cudaStreamSynchronize(p.stream));
 }
 
 extern "C" void b200_nms_obj_arrays(const float *boxes, float *objectness, int n, float thresh, unsigned char *suppressed)
 {
     if (n <= 0) return;
-    nms_prepare();
-    float *d_box = (float *)dev_alloc((size_t)n * 4 * sizeof(float));
-    float *d_obj = (float *)dev_alloc((size_t)n * sizeof(float));
+    NmsHostPath &p = nms_prepare((size_t)n * 4, (size_t)n, 2);
     std::vector<float> before(objectness, objectness + n);
-    B200_CHECK(cudaMemcpyAsync(d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
-    B200_CHECK(cudaMemcpyAsync(d_obj, objectness, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, g_nms_stream));
-    launch_nms_obj(d_box, d_obj, nullptr, nullptr, 1, n, 1, thresh, n, &g_nms_scratch, g_nms_stream);
-    B200_CHECK(cudaMemcpyAsync(objectness, d_obj, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g_nms_stream));
-    B200_CHECK(cudaStreamSynchronize(g_nms_stream));
+    B200_CHECK(cudaMemcpyAsync(p.d_box, boxes, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, p.stream));
+    B200_CHECK(cudaMemcpyAsync(p.d_val, objectness, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, p.stream));
+    launch_nms_obj(p.d_box, p.d_val, nullptr, nullptr, 1, n, 1, thresh, n, &p.scratch, p.stream);
+    B200_CHECK(cudaMemcpyAsync(objectness, p.d_val, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, p.stream));
+    B200_CHECK(cudaStreamSynchronize(p.stream));
     if (suppressed) for (int i = 0; i < n; ++i) suppressed[i] = (before[i] != 0.f && objectness[i] == 0.f) ? 1 : 0;
-    cudaFree(d_box); cudaFree(d_obj);
 }

@@ -170,3 +170,97 @@ void launch_avg_flipped(float *head_out, int w, int h, int anchors, int entries,
     average_items_kernel<<<div_up(outputs, kThreads), kThreads, 0, s>>>(head_out, head_out + outputs, outputs);
     B200_LAUNCHED();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// YOLO9000: [region] with a WordTree.  forward_region_layer's softmax_tree branch as the reference's GPU build
+// runs it (region_layer.c:455-457 -> softmax_tree, blas_kernels.cu): per box, one softmax over every sibling group of the
+// tree at temperature 1, class entries strided by h*w.  (The reference's CPU build cannot run this branch: it divides by
+// l.temperature, which parse_region never sets — region_layer.c:179 — so every class probability comes out NaN there.)
+// One warp per box: the box's logits are contiguous in the NHWC input.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void region_tree_forward_kernel(const T *__restrict__ in, float *__restrict__ out, int N, int HW, int ld, int anchors,
+                                           int classes, int coords, const int *__restrict__ gsize, const int *__restrict__ goff, int groups)
+{
+    const int entries = coords + 1 + classes;
+    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const long long total = (long long)N * anchors * HW;
+    for (long long t = (long long)blockIdx.x * warps + (threadIdx.x >> 5); t < total; t += (long long)gridDim.x * warps) {
+        const int loc = (int)(t % HW), a = (int)((t / HW) % anchors), n = (int)(t / ((long long)HW * anchors));
+        const T *src = in + ((size_t)n * HW + loc) * ld + a * entries;
+        float *dst = out + ((size_t)n * anchors + a) * entries * HW + loc;
+        if (lane == 0) {
+            dst[0] = logistic_ref(Elem<T>::load(src + 0));
+            dst[HW] = logistic_ref(Elem<T>::load(src + 1));
+            for (int e = 2; e < coords; ++e) dst[(size_t)e * HW] = Elem<T>::load(src + e);
+            dst[(size_t)coords * HW] = logistic_ref(Elem<T>::load(src + coords));
+        }
+        for (int g = 0; g < groups; ++g) {
+            const int off = coords + 1 + goff[g], sz = gsize[g];
+            float largest = -FLT_MAX;
+            for (int j = lane; j < sz; j += 32) largest = fmaxf(largest, Elem<T>::load(src + off + j));
+            for (int o = 16; o; o >>= 1) largest = fmaxf(largest, __shfl_xor_sync(0xffffffffu, largest, o));
+            float sum = 0.f;
+            for (int j = lane; j < sz; j += 32) {
+                const float e = (float)exp((double)(Elem<T>::load(src + off + j) - largest));
+                sum += e;
+                dst[(size_t)(off + j) * HW] = e;
+            }
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            for (int j = lane; j < sz; j += 32) dst[(size_t)(off + j) * HW] /= sum;
+        }
+    }
+}
+
+void launch_region_tree_forward(TView in, float *out, int anchors, int classes, int coords, const int *gsize, const int *goff, int groups, cudaStream_t s)
+{
+    const int HW = in.h * in.w;
+    const long long boxes = (long long)in.n * anchors * HW;
+    int grid = (int)((boxes + 7) / 8);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (in.dtype == DT_F32) region_tree_forward_kernel<float><<<grid, kThreads, 0, s>>>((const float *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, gsize, goff, groups);
+    else region_tree_forward_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16 *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, gsize, goff, groups);
+    B200_LAUNCHED();
+}
+
+// hierarchy_predictions (tree.c:37-51): predictions[j] *= predictions[parent[j]] for j ascending, i.e. class j ends up as the
+// product of the conditional probabilities along its path, associated from the root down: rel[j] * (rel[parent] * (...)).
+// One thread per (box, class) walks up to the root, then multiplies back down in that association — bit-identical to the
+// serial in-place loop.  Out of place into tmp, then copied back (the walk reads the unmodified values).
+#define B200_TREE_MAX_DEPTH 64
+__global__ void region_hierarchy_kernel(const float *__restrict__ pred, float *__restrict__ tmp, int hw, int anchors, int classes, int coords,
+                                        const int *__restrict__ parent)
+{
+    const int entries = coords + 1 + classes;
+    const long long total = (long long)anchors * classes * hw;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int loc = (int)(t % hw), j = (int)((t / hw) % classes), a = (int)(t / ((long long)hw * classes));
+        const float *p = pred + ((size_t)a * entries + coords + 1) * hw + loc;
+        int chain[B200_TREE_MAX_DEPTH], depth = 0;
+        for (int c = j; c >= 0 && depth < B200_TREE_MAX_DEPTH; c = parent[c]) chain[depth++] = c;
+        float v = p[(size_t)chain[depth - 1] * hw];
+        for (int k = depth - 2; k >= 0; --k) v = __fmul_rn(p[(size_t)chain[k] * hw], v);
+        tmp[t] = v;
+    }
+}
+
+__global__ void region_hierarchy_store_kernel(float *__restrict__ pred, const float *__restrict__ tmp, int hw, int anchors, int classes, int coords)
+{
+    const int entries = coords + 1 + classes;
+    const long long total = (long long)anchors * classes * hw;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int loc = (int)(t % hw), j = (int)((t / hw) % classes), a = (int)(t / ((long long)hw * classes));
+        pred[((size_t)a * entries + coords + 1 + j) * hw + loc] = tmp[t];
+    }
+}
+
+void launch_region_hierarchy(float *item_out, float *tmp, int hw, int anchors, int classes, int coords, const int *parent, cudaStream_t s)
+{
+    const long long total = (long long)anchors * classes * hw;
+    int grid = (int)((total + kThreads - 1) / kThreads);
+    if (grid > 148 * 16) grid = 148 * 16;
+    region_hierarchy_kernel<<<grid, kThreads, 0, s>>>(item_out, tmp, hw, anchors, classes, coords, parent);
+    B200_LAUNCHED();
+    region_hierarchy_store_kernel<<<grid, kThreads, 0, s>>>(item_out, tmp, hw, anchors, classes, coords);
+    B200_LAUNCHED();
+}

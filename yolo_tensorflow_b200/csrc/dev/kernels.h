@@ -76,6 +76,11 @@ void launch_connected(const void *in, int in_dtype, int batch, int inputs, int o
 // ---- heads (heads.cu): NHWC logits -> darknet-layout fp32 l.output with the layer's activations ------
 void launch_yolo_forward(TView in, float *out, int anchors, int classes, cudaStream_t s);
 void launch_region_forward(TView in, float *out, int anchors, int classes, int coords, int softmax, cudaStream_t s);
+// [region] with tree=: logistic on x, y, objectness and one softmax per sibling group of the WordTree (temperature 1)
+void launch_region_tree_forward(TView in, float *out, int anchors, int classes, int coords, const int *gsize, const int *goff, int groups, cudaStream_t s);
+// hierarchy_predictions (tree.c:37-51) over every box of one batch item, in place: class j <- product of the conditional
+// probabilities on its path to the root.  tmp: anchors*classes*hw floats of scratch.
+void launch_region_hierarchy(float *item_out, float *tmp, int hw, int anchors, int classes, int coords, const int *parent, cudaStream_t s);
 void launch_detection_forward(const float *in, float *out, int batch, int outputs, int side, int classes, int softmax, cudaStream_t s);
 // l.batch == 2: item 0 <- mean(item 0, horizontally flipped item 1), in place (yolo_layer.c:290-314, region_layer.c:368-390)
 void launch_avg_flipped(float *head_out, int w, int h, int anchors, int entries, int outputs, cudaStream_t s);
@@ -89,6 +94,9 @@ struct HeadDesc {            // one per YOLO/REGION/DETECTION layer, device-resi
     int raw_ld;              //   detection path decode without materialising l.output (logistic applied on the fly)
     float anchors[2 * 16];   // (w,h) pairs already selected through mask[]
     int box_base;            // first global box id of this head inside an image
+    // REGION head with a WordTree (YOLO9000, `tree=`): device copies of tree.parent / child / group_size / group_offset, or NULL
+    const int *tree_parent, *tree_child, *tree_gsize, *tree_goff;
+    int tree_groups;
 };
 struct CandBuffers {
     float *box;        // [batch][cap][4]
@@ -103,8 +111,11 @@ struct CandBuffers {
 };
 // mode 0 = reference get_network_boxes semantics (yolo: obj>thresh only; region/detection: every box)
 // mode 1 = compact: additionally drops boxes whose objectness is 0 (what do_nms_sort's partition discards)
+// tree_thresh / map_dev: the `hier` and `map` arguments of get_network_boxes, used by REGION heads with a WordTree
+// (region_layer.c:412-424): map_dev = 200 class indices on the device, or NULL
 void launch_decode(const HeadDesc *heads_dev, int nheads, int first_image, int nimages, int netw, int neth,
-                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s, const int *im_dims = nullptr);
+                   int imw, int imh, float thresh, int relative, int mode, int use_raw, CandBuffers cb, cudaStream_t s, const int *im_dims = nullptr,
+                   float tree_thresh = .5f, const int *map_dev = nullptr);
 void launch_count_yolo(const HeadDesc *heads_dev, int nheads, int image, float thresh, int *count_dev, cudaStream_t s);
 
 struct NmsScratch { unsigned *mask; size_t words_per_cta; int ctas; };

@@ -383,11 +383,8 @@ static void run_nms(const float *box, float *score, const float *obj, const int 
     int ctas = units < 148 * 2 ? units : 148 * 2;
     ensure_scratch(scratch, max_count, ctas);
     size_t smem = 4096 + host_work_bytes(NMS_SMEM_M);
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // per launch, not once per process: the attribute belongs to the CURRENT device, and a process may hold networks on several
+    B200_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_kernel<<<ctas, NMS_THREADS, smem, s>>>(box, score, obj, count, images, cap, classes, stride, thresh,
                                                (unsigned char *)scratch->mask, scratch->words_per_cta, supp, cls_count, NMS_SMALL_M);
     B200_LAUNCHED();

@@ -13,7 +13,9 @@
 /* internal C ABI of the engine (dev/engine.cu) */
 int b200_engine_count_boxes(b200_engine *e, network *net, int image, float thresh);
 int b200_engine_decode_image(b200_engine *e, network *net, int image, int w, int h, float thresh, int relative,
-                             const float **box, const float **obj, const float **prob, const int **id);
+                             const float **box, const float **obj, const float **prob, const int **id, float hier, const int *map);
+void b200_engine_hierarchy(b200_engine *e, network *net, int image);
+int b200_engine_has_tree(b200_engine *e);
 int b200_engine_classes(b200_engine *e);
 void b200_engine_push_heads(b200_engine *e, network *net, int items);
 void b200_engine_avg_flipped(b200_engine *e, network *net);
@@ -64,12 +66,16 @@ detection *make_network_boxes(network *net, float thresh, int *num)
     return alloc_dets(net, nboxes);
 }
 
-static int fill_for_image(network *net, int image, int w, int h, float thresh, int relative, detection *dets, int room)
+static int fill_for_image(network *net, int image, int w, int h, float thresh, float hier, int *map, int relative, detection *dets, int room)
 {
     const float *box, *obj, *prob;
     const int *id;
     int classes = last_layer_classes(net);
-    int n = b200_engine_decode_image(b200_engine_of(net), net, image, w, h, thresh, relative, &box, &obj, &prob, &id);
+    b200_engine *e = b200_engine_of(net);
+    /* YOLO9000: get_region_detections turns the conditional class probabilities into absolute ones in place before it scores
+     * the boxes (hierarchy_predictions, region_layer.c:412-414) */
+    if (b200_engine_has_tree(e)) b200_engine_hierarchy(e, net, image);
+    int n = b200_engine_decode_image(e, net, image, w, h, thresh, relative, &box, &obj, &prob, &id, hier, map);
     if (room >= 0 && n > room) n = room;
     for (int i = 0; i < n; ++i) {
         dets[i].bbox.x = box[4 * i + 0]; dets[i].bbox.y = box[4 * i + 1];
@@ -83,17 +89,15 @@ static int fill_for_image(network *net, int image, int w, int h, float thresh, i
 
 void fill_network_boxes(network *net, int w, int h, float thresh, float hier, int *map, int relative, detection *dets)
 {
-    (void)hier; (void)map;          /* YOLO9000 hierarchy / map: see get_network_boxes */
     if (push_heads(net)) b200_engine_avg_flipped(b200_engine_of(net), net);
-    fill_for_image(net, 0, w, h, thresh, relative, dets, -1);
+    fill_for_image(net, 0, w, h, thresh, hier, map, relative, dets, -1);
 }
 
 detection *get_network_boxes_batch(network *net, int b, int w, int h, float thresh, float hier, int *map, int relative, int *num)
 {
-    (void)hier; (void)map;
     int nboxes = count_for_image(net, b, thresh);
     detection *dets = alloc_dets(net, nboxes);
-    int got = fill_for_image(net, b, w, h, thresh, relative, dets, nboxes);
+    int got = fill_for_image(net, b, w, h, thresh, hier, map, relative, dets, nboxes);
     (void)got;
     if (num) *num = nboxes;
     return dets;
@@ -112,7 +116,7 @@ detection *get_network_boxes(network *net, int w, int h, float thresh, float hie
     int nboxes = count_for_image(net, 0, thresh);
     detection *dets = alloc_dets(net, nboxes);
     b200_engine_avg_flipped(b200_engine_of(net), net);
-    fill_for_image(net, 0, w, h, thresh, relative, dets, nboxes);
+    fill_for_image(net, 0, w, h, thresh, hier, map, relative, dets, nboxes);
     if (num) *num = nboxes;
     return dets;
 }

@@ -236,6 +236,87 @@ int *read_map(char *filename)                      /* utils.c:62-77: one class i
     return map;
 }
 
+/* ---- tree.c: the WordTree of YOLO9000 (`tree=` of a [region] layer) ---------------------------------------- */
+tree *read_tree(char *filename)
+{
+    /* tree.c:83-139: one "<name> <parent index>" line per class; consecutive classes with the same parent form a group (the
+     * unit the softmax runs over); child[i] = group of i's children, or -1 */
+    FILE *fp = fopen(filename, "r");
+    if (!fp) { fprintf(stderr, "Couldn't open file: %s\n", filename); exit(0); }
+    tree *t = calloc(1, sizeof(tree));
+    int n = 0, groups = 0, group_size = 0, last_parent = -1;
+    char *line;
+    while ((line = fgetl(fp)) != NULL) {
+        char *id = calloc(256, sizeof(char));
+        int parent = -1;
+        sscanf(line, "%255s %d", id, &parent);
+        free(line);
+        t->parent = realloc(t->parent, (size_t)(n + 1) * sizeof(int));
+        t->child  = realloc(t->child,  (size_t)(n + 1) * sizeof(int));
+        t->name   = realloc(t->name,   (size_t)(n + 1) * sizeof(char *));
+        t->group  = realloc(t->group,  (size_t)(n + 1) * sizeof(int));
+        t->parent[n] = parent; t->child[n] = -1; t->name[n] = id;
+        if (parent != last_parent) {                     /* a new group starts: close the previous one */
+            ++groups;
+            t->group_offset = realloc(t->group_offset, (size_t)groups * sizeof(int));
+            t->group_size   = realloc(t->group_size,   (size_t)groups * sizeof(int));
+            t->group_offset[groups - 1] = n - group_size;
+            t->group_size[groups - 1] = group_size;
+            group_size = 0;
+            last_parent = parent;
+        }
+        t->group[n] = groups;
+        if (parent >= 0) t->child[parent] = groups;
+        ++n; ++group_size;
+    }
+    fclose(fp);
+    ++groups;
+    t->group_offset = realloc(t->group_offset, (size_t)groups * sizeof(int));
+    t->group_size   = realloc(t->group_size,   (size_t)groups * sizeof(int));
+    t->group_offset[groups - 1] = n - group_size;
+    t->group_size[groups - 1] = group_size;
+    t->n = n; t->groups = groups;
+    t->leaf = calloc(n > 0 ? n : 1, sizeof(int));
+    for (int i = 0; i < n; ++i) t->leaf[i] = 1;
+    for (int i = 0; i < n; ++i) if (t->parent[i] >= 0) t->leaf[t->parent[i]] = 0;
+    return t;
+}
+
+void hierarchy_predictions(float *predictions, int n, tree *hier, int only_leaves, int stride)
+{
+    /* tree.c:37-51, host version for drivers; the engine runs the same recurrence on the device (dev/heads.cu) */
+    for (int j = 0; j < n; ++j) {
+        int parent = hier->parent[j];
+        if (parent >= 0) predictions[j * stride] *= predictions[parent * stride];
+    }
+    if (only_leaves) for (int j = 0; j < n; ++j) if (!hier->leaf[j]) predictions[j * stride] = 0;
+}
+
+int hierarchy_top_prediction(float *predictions, tree *hier, float thresh, int stride)
+{
+    /* tree.c:53-81: walk down from the root group, always into the most probable child, while the path stays over thresh */
+    float p = 1;
+    int group = 0;
+    for (;;) {
+        float best = 0;
+        int best_i = 0;
+        for (int i = 0; i < hier->group_size[group]; ++i) {
+            int index = i + hier->group_offset[group];
+            float val = predictions[index * stride];
+            if (val > best) { best_i = index; best = val; }
+        }
+        if (p * best > thresh) {
+            p = p * best;
+            group = hier->child[best_i];
+            if (hier->child[best_i] < 0) return best_i;
+        } else if (group == 0) {
+            return best_i;
+        } else {
+            return hier->parent[hier->group_offset[group]];
+        }
+    }
+}
+
 /* ---- image.c: drawing --------------------------------------------------------------------------------------------------------- */
 static float px_get(image m, int x, int y, int c) { return m.data[((size_t)c * m.h + y) * m.w + x]; }
 static float px_get_or_zero(image m, int x, int y, int c)

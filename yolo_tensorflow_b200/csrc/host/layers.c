@@ -62,11 +62,12 @@ static int split_ints(const char *s, int **out)
     return n;
 }
 
-static void read_anchor_list(cfg_section *opt, float *dst)
+static void read_anchor_list(cfg_section *opt, float *dst, int room)
 {
     const char *a = cfg_str(opt, "anchors", 0);
     if (!a) return;
     for (int i = 0; ; ++i) {
+        if (i >= room) fatal("more anchor values than 2*num in the cfg");      /* the reference overruns l.biases here (parser.c:328-337) */
         dst[i] = (float)atof(a);
         const char *comma = strchr(a, ',');
         if (!comma) break;
@@ -337,7 +338,7 @@ static layer yolo_layer_(cfg_section *opt, shape_cursor cur)
     l.truth_thresh  = cfg_float(opt, "truth_thresh", 1);
     l.random        = cfg_int_quiet(opt, "random", 0);
     if (cfg_str(opt, "map", 0)) fatal("yolo map= files are outside the YOLO inference path");
-    read_anchor_list(opt, l.biases);
+    read_anchor_list(opt, l.biases, l.total * 2);
     return l;
 }
 
@@ -379,10 +380,17 @@ static layer region_layer_(cfg_section *opt, shape_cursor cur)
     l.mask_scale     = cfg_float(opt, "mask_scale", 1);
     l.class_scale    = cfg_float(opt, "class_scale", 1);
     l.bias_match     = cfg_int_quiet(opt, "bias_match", 0);
-    if (cfg_str(opt, "tree", 0)) fatal("region tree= (YOLO9000 hierarchy) is outside the YOLO inference path (SURVEY §8f-4)");
-    if (cfg_str(opt, "map", 0))  fatal("region map= is outside the YOLO inference path");
+    {   /* YOLO9000 (parser.c:372-375): the class WordTree and the training-time class map */
+        const char *tree_file = cfg_str(opt, "tree", 0);
+        if (tree_file) {
+            l.softmax_tree = read_tree((char *)tree_file);
+            if (l.softmax_tree->n != l.classes) fatal("region tree= file does not list `classes` entries");
+        }
+        const char *map_file = cfg_str(opt, "map", 0);
+        if (map_file) l.map = read_map((char *)map_file);
+    }
     if (l.background || l.coords != 4) fatal("region background/coords!=4 are outside the YOLO inference path");
-    read_anchor_list(opt, l.biases);
+    read_anchor_list(opt, l.biases, l.n * 2);
     return l;
 }
 

@@ -243,6 +243,17 @@ int resize_network(network *net, int w, int h)
 {
     network_box *nb = (network_box *)net;
     int cw = w, ch = h, cc = net->c;
+    /* the reference dies in error() at the first layer it cannot resize (network.c:428), after it has already resized the
+     * ones before it; here nothing is touched unless every layer can follow */
+    for (int i = 0; i < net->n; ++i) {
+        LAYER_TYPE t = net->layers[i].type;
+        if (t != CONVOLUTIONAL && t != MAXPOOL && t != UPSAMPLE && t != REORG && t != SHORTCUT && t != ROUTE && t != YOLO &&
+            t != REGION && t != DROPOUT) {
+            fprintf(stderr, "Cannot resize this type of layer\n");
+            return -1;
+        }
+    }
+    b200_engine_unpin_host(nb->engine);            /* the head outputs are page-locked while a plan lives: release before realloc */
     for (int i = 0; i < net->n; ++i) {
         layer *l = &net->layers[i];
         switch (l->type) {
@@ -312,7 +323,9 @@ int resize_network(network *net, int w, int h)
     layer out = get_network_output_layer(net);
     net->outputs = out.outputs;
     net->output = out.output;
+    net->truths = net->layers[net->n - 1].truths ? net->layers[net->n - 1].truths : out.outputs;      /* network.c:404-406 */
     net->input = regrow(net->input, (size_t)net->inputs * net->batch);
+    net->truth = regrow(net->truth, (size_t)net->truths * net->batch);
     nb->engine = b200_engine_recreate(nb->engine, net);
     return 0;
 }

@@ -10,14 +10,25 @@
  *     LOCAL         : biases[outputs], weights[size*size*c*n*locations]      (parser.c:1315-1341)
  * The fp32 arrays land in the public `layer` fields exactly as in the reference (drivers may read
  * them); the engine then folds BN, repacks for NHWC and uploads (b200_engine_upload_weights).
- * Unlike the reference fork, nothing is dumped to stdout, and short reads are fatal.
+ * Unlike the reference fork, nothing is dumped to stdout.  The reference ignores fread's result, so a file that ends at a
+ * layer boundary (a backbone-only file such as darknet53.conv.74 loaded with plain load_weights) simply leaves the remaining
+ * layers as initialised: the same here, with a notice.  A file that ends INSIDE an array is corrupt and stays fatal.
  */
 #include "darknet.h"
 #include "b200_engine.h"
 
+static int g_at_layer_start, g_file_ended;
+
 static void read_floats(float *dst, size_t n, FILE *fp, const char *what, int layer_index)
 {
+    if (g_file_ended) return;
     size_t got = fread(dst, sizeof(float), n, fp);
+    if (got == 0 && g_at_layer_start && feof(fp)) {
+        fprintf(stderr, "\nb200-darknet: weights file ends before layer %d: it and the layers after it keep their initial values\n", layer_index);
+        g_file_ended = 1;
+        return;
+    }
+    g_at_layer_start = 0;
     if (got != n) {
         fprintf(stderr, "\nb200-darknet: weights file too short: layer %d %s wanted %zu floats, got %zu\n",
                 layer_index, what, n, got);
@@ -57,10 +68,12 @@ void load_weights_upto(network *net, char *filename, int start, int cutoff)
         *net->seen = (size_t)seen;
     }
     int transpose = (major > 1000) || (minor > 1000);
+    g_file_ended = 0;
 
     for (int i = start; i < net->n && i < cutoff; ++i) {
         layer l = net->layers[i];
         if (l.dontload) continue;
+        g_at_layer_start = 1;
         if (l.type == CONVOLUTIONAL) {
             read_floats(l.biases, l.n, fp, "biases", i);
             if (l.batch_normalize && !l.dontloadscales) {

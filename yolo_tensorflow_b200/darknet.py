@@ -108,6 +108,7 @@ lib.b200_engine_input_device.argtypes = [c_void_p]; lib.b200_engine_input_device
 lib.b200_engine_sync.argtypes = [c_void_p]
 lib.b200_engine_stream.argtypes = [c_void_p]; lib.b200_engine_stream.restype = c_void_p
 lib.b200_profile_layers.argtypes = [c_void_p, c_int, POINTER(c_float)]
+lib.b200_profile_forward.argtypes = [c_void_p, c_int, POINTER(c_float)]
 lib.b200_profile_tail.argtypes = [c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(c_float)]
 lib.get_network_boxes_batch.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_float, POINTER(c_int), c_int, POINTER(c_int)]
 lib.get_network_boxes_batch.restype = POINTER(DETECTION)
@@ -116,6 +117,11 @@ lib.b200_detect_batch.restype = c_int
 lib.b200_submit_batch.argtypes = [c_void_p, c_void_p]
 lib.b200_detect_submitted.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, POINTER(B200_DET), c_int, POINTER(c_int)]
 lib.b200_detect_submitted.restype = c_int
+lib.b200_comm_unique_id.argtypes = [c_void_p, c_int]; lib.b200_comm_unique_id.restype = c_int
+lib.b200_comm_init.argtypes = [c_void_p, c_void_p, c_int, c_int]; lib.b200_comm_init.restype = c_int
+lib.b200_comm_broadcast_weights.argtypes = [c_void_p, c_int]; lib.b200_comm_broadcast_weights.restype = c_int
+lib.b200_comm_set_gather.argtypes = [c_void_p, c_int, c_int, c_int]; lib.b200_comm_set_gather.restype = c_int
+lib.b200_comm_destroy.argtypes = [c_void_p]
 lib.b200_nms_sort_arrays.argtypes = [POINTER(c_float), POINTER(c_float), c_int, c_int, c_float]
 lib.b200_nms_obj_arrays.argtypes = [POINTER(c_float), POINTER(c_float), c_int, c_float, POINTER(c_ubyte)]
 
@@ -197,6 +203,12 @@ class Network:
         ms = np.zeros(self.n, dtype=np.float32)
         lib.b200_profile_layers(self.ptr, iters, _fptr(ms))
         return ms
+
+    def profile_forward(self, iters=5):
+        """(whole forward pass ms, first layer ms) as the serving loop runs it"""
+        ms = np.zeros(2, dtype=np.float32)
+        lib.b200_profile_forward(self.ptr, iters, _fptr(ms))
+        return float(ms[0]), float(ms[1])
 
     def profile_tail(self, w, h, thresh, nms, iters=3):
         ms = np.zeros(3, dtype=np.float32)

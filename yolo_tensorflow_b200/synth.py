@@ -49,8 +49,13 @@ def make_cfg(model, out_dir, batch=1, width=None, height=None):
     os.makedirs(out_dir, exist_ok=True)
     tag = f"{model}_b{batch}" + (f"_{width}x{height}" if width else "")
     dst = os.path.join(out_dir, tag + ".cfg")
-    with open(dst, "w") as f:
+    # several ranks of one job derive the same file at the same time while others already parse it: never truncate in place
+    if os.path.exists(dst) and open(dst).read() == text:
+        return dst
+    tmp = dst + ".%d.tmp" % os.getpid()
+    with open(tmp, "w") as f:
         f.write(text)
+    os.replace(tmp, dst)
     return dst
 
 
