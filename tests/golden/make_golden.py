@@ -108,6 +108,61 @@ def build_flip(name, model, size, seed, thresh):
     print(name, "num", n, "filled", int((obj != 0).sum()) if model != "yolov2" else n, "port before/after", before, after)
 
 
+THRESH_TREE = .05
+
+
+def build_tree(name="yolo9000-small_tree"):
+    """YOLO9000 box extraction pinned on the reference: its CPU forward cannot produce class probabilities for a
+    [region] layer with tree= (softmax at l.temperature = 0, region_layer.c:179), so the head activations come from the oracle's
+    port (GPU-build semantics), are written into the reference network's l.output, and the REFERENCE's get_network_boxes —
+    hierarchy_predictions + hierarchy_top_prediction / the map branch, region_layer.c:412-424 — turns them into detections.
+    Also holds the reference's own softmax() (blas.c:305) on every sibling group of one box, which pins the port's group softmax."""
+    import ctypes
+    from oracle import np_darknet as P
+    tree_path = os.path.join(HERE, "wordtree_240.tree")
+    cfg = synth.make_tree_cfg(WORK, tree_path, batch=1, size=32)
+    wpath = os.path.join(WORK, "yolo9000-small.weights")
+    synth.write_weights(cfg, wpath, seed=0, damp_heads=True)
+    port = P.Net(cfg, wpath)
+    x = synth.make_images(1, 3, 32, 32, 1009)
+    outs = port.forward(x)
+    L = port.layers[-1]
+    head = outs[-1].reshape(1, -1).astype(np.float32)
+    d = dict(seed=1009, size=32, thresh=THRESH_TREE, head=head, logits=outs[-2].reshape(1, -1))
+    print("objectness quantiles", np.quantile(head.reshape(L.n, -1, L.h * L.w)[:, 4], [.5, .9, .99, 1.]))
+    # the reference's softmax() on the sibling groups of box (anchor 1, cell 37)
+    ref = R.RefNet(cfg, wpath)
+    ref.lib.softmax.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    hw = L.h * L.w
+    logit = outs[-2].reshape(L.n, L.coords + L.classes + 1, hw)[1, L.coords + 1:, 37].astype(np.float32).copy()
+    sm = np.zeros_like(logit)
+    for g in range(L.tree.groups):
+        a, n = L.tree.group_offset[g], L.tree.group_size[g]
+        if n:
+            ref.lib.softmax(logit[a:].ctypes.data_as(ctypes.POINTER(ctypes.c_float)), n, 1.0, 1, sm[a:].ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    d["box_logits"], d["box_softmax"] = logit, sm
+    rng = np.random.default_rng(8)
+    cmap = rng.integers(0, L.classes, 200).astype(np.int32)
+    d["map"] = cmap
+    ref.predict(x)
+    i = ref.n - 1
+    for tag, hier, mp in (("top", .5, None), ("top_lo", .1, None), ("map", .5, cmap)):
+        buf = np.ctypeslib.as_array(ctypes.cast(ref.layer_output_ptr(i), ctypes.POINTER(ctypes.c_float)), shape=(head.size,))
+        buf[:] = head.ravel()                                        # hierarchy_predictions works in place: start from fresh activations
+        num = ctypes.c_int(0)
+        mptr = mp.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if mp is not None else None
+        dets = ref.lib.get_network_boxes(ref.ptr, 32, 32, ctypes.c_float(THRESH_TREE), ctypes.c_float(hier), mptr, 1, ctypes.byref(num))
+        boxes, obj, probs = ref.dets_arrays(dets, num.value)
+        nz = np.nonzero(probs)
+        d[f"{tag}_boxes"], d[f"{tag}_obj"], d[f"{tag}_num"] = boxes, obj, num.value
+        d[f"{tag}_prob_rc"] = np.stack(nz).astype(np.int32); d[f"{tag}_prob_v"] = probs[nz]
+        d[f"{tag}_head_after"] = buf.copy().reshape(1, -1)
+        ref.free_dets(dets, num.value)
+        print(name, tag, "boxes", num.value, "with a class", len(set(nz[0].tolist())), "distinct classes", len(set(nz[1].tolist())))
+    ref.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+
+
 def calibrate():
     for model, seed in (("yolov3-tiny", 1000), ("yolov3", 1002), ("yolov2", 1001), ("yolov1", 1004)):
         cfg = synth.make_cfg(model, WORK, batch=1)
@@ -131,3 +186,5 @@ if __name__ == "__main__":
         for c in FLIP_CASES:
             if not only or c[0] in only:
                 build_flip(*c)
+        if not only or "yolo9000-small_tree" in only:
+            build_tree()

@@ -767,6 +767,51 @@ def test_resize_network_matches_the_reference_resize(dn, model, workdir):
 
 
 # ---------------------------------------------------------------------------------------------------
+# YOLO9000: [region] with a class WordTree
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_wordtree_region_head(dn, prec, workdir):
+    """forward: logistic + one softmax per sibling group (the reference GPU build's semantics; its CPU build divides by an unset
+    temperature) against the oracle; box extraction: hierarchy_predictions in place + hierarchy_top_prediction / the `map`
+    argument against the REFERENCE's get_network_boxes on the same head activations (golden); do_nms_sort over 240 classes"""
+    from test_oracle import tree_golden_arrays, tree_model
+    g = load_golden("yolo9000-small_tree")
+    cfg, wpath = tree_model(workdir)
+    fd = os.dup(2); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 2)
+    try:
+        net = dn.Network(cfg, wpath, precision=dn.PREC_FP32 if prec == "fp32" else dn.PREC_BF16)
+    finally:
+        os.dup2(fd, 2); os.close(fd); os.close(devnull)
+    last = net.n - 1
+    net.predict(synth.make_images(1, 3, 32, 32, int(g["seed"])))
+    a, r = net.layer_output(last), g["head"]
+    assert np.abs(a - r).max() <= (FP32_TOL if prec == "fp32" else BF16_LAYER_TOL) * np.abs(r).max()
+    # the region forward alone, teacher-forced with the oracle's logits: fp32 arithmetic in both precisions
+    net.set_layer_output(last - 1, g["logits"])
+    net.run_layers(last, last + 1)
+    assert np.abs(net.layer_output(last) - r).max() <= 1e-6
+    thresh, classes = float(g["thresh"]), 240
+    for tag, hier, cmap in (("top", .5, None), ("top_lo", .1, None), ("map", .5, g["map"])):
+        net.set_layer_output(last, r)
+        num = ctypes.c_int(0)
+        mptr = np.ascontiguousarray(cmap, np.int32).ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if cmap is not None else None
+        dets = dn.get_network_boxes(net.ptr, 32, 32, thresh, hier, mptr, 1, ctypes.byref(num))
+        boxes, obj, probs = dn.dets_to_arrays(dets, num.value, classes)
+        gb, go, gp = tree_golden_arrays(g, tag, classes)
+        assert num.value == int(g[f"{tag}_num"])
+        np.testing.assert_allclose(boxes, gb, rtol=DECODE_TOL, atol=1e-9)
+        assert np.array_equal(obj, go) and np.array_equal(probs, gp)
+        assert np.array_equal(net.layer_output(last), g[f"{tag}_head_after"])            # l.output rewritten in place like the reference
+        dn.do_nms_sort(dets, num.value, classes, .45)
+        _, _, after = dn.dets_to_arrays(dets, num.value, classes)
+        dn.free_detections(dets, num.value)
+        # identity through the prob pointers is lost in dets_to_arrays after the re-sort: compare the multiset of kept scores
+        want = P.do_nms_sort(gb, go, gp, .45)
+        assert sorted(after[after > 0].tolist()) == sorted(want[want > 0].tolist())
+    net.close()
+
+
+# ---------------------------------------------------------------------------------------------------
 # NMS stress configuration (SURVEY §8d): undamped head weights (thousands of candidates per image) and thresh .005
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("model,size,damp,thresh,e2e", [("yolov3", 416, False, .5, False), ("yolov3", 416, True, .005, True),
@@ -938,8 +983,9 @@ def test_validate_images_batched_driver(dn, workdir, tmp_path):
 
 
 def test_get_network_boxes_reads_batch_item_zero(dn, workdir):
-    net, _, _ = open_net(dn, "yolov3-tiny", 2, 160, workdir, dn.PREC_FP32)
-    x = synth.make_images(2, 3, 160, 160, 41)
+    # batch 3: with a batch of exactly 2 the reference averages item 0 with the mirrored item 1 (test_batch2_flip_average_*)
+    net, _, _ = open_net(dn, "yolov3-tiny", 3, 160, workdir, dn.PREC_FP32)
+    x = synth.make_images(3, 3, 160, 160, 41)
     net.predict(x)
     num = ctypes.c_int(0)
     dets = dn.get_network_boxes(net.ptr, 160, 160, .3, .5, None, 1, ctypes.byref(num))

@@ -176,3 +176,47 @@ def test_reference_nms_leaves_the_array_in_stable_chain_order():
     obj = (rng.random(n) > .15).astype(np.float32)
     _, order = R.ref_nms_sort_arrays(boxes, probs, .45, obj, want_order=True)
     assert order == P.nms_sort_final_order(obj, probs)
+
+
+def tree_model(workdir, batch=1):
+    """the small YOLO9000-style network of the tree golden: cfg (with the repo's WordTree fixture as tree=) and seeded weights"""
+    tree_path = os.path.join(REPO, "tests", "golden", "wordtree_240.tree")
+    cfg = synth.make_tree_cfg(workdir, tree_path, batch=batch, size=32)
+    wpath = os.path.join(workdir, "yolo9000-small.weights")
+    if not os.path.exists(wpath):
+        tmp = wpath + ".tmp%d" % os.getpid()
+        synth.write_weights(cfg, tmp, seed=0, damp_heads=True)
+        os.replace(tmp, wpath)
+    return cfg, wpath
+
+
+def tree_golden_arrays(g, tag, classes):
+    n = int(g[f"{tag}_num"])
+    probs = np.zeros((n, classes), np.float32)
+    probs[g[f"{tag}_prob_rc"][0], g[f"{tag}_prob_rc"][1]] = g[f"{tag}_prob_v"]
+    return g[f"{tag}_boxes"], g[f"{tag}_obj"], probs
+
+
+def test_port_wordtree_matches_reference_golden(workdir):
+    """YOLO9000: the port's per-group softmax against the reference's own softmax() (blas.c:305) and the port's
+    hierarchy_predictions / hierarchy_top_prediction / map branch against the reference's get_network_boxes
+    (region_layer.c:412-424, tree.c:37-81) on the same head activations"""
+    g = load_golden("yolo9000-small_tree")
+    cfg, wpath = tree_model(workdir)
+    net = P.Net(cfg, wpath)
+    L = net.layers[-1]
+    assert L.tree.n == 240 and L.tree.groups == 73
+    outs = net.forward(synth.make_images(1, 3, 32, 32, int(g["seed"])))
+    assert np.abs(outs[-1].reshape(1, -1) - g["head"]).max() <= 1e-6
+    got = outs[-1].reshape(L.n, L.coords + L.classes + 1, L.h * L.w)[1, L.coords + 1:, 37]
+    assert np.abs(got - g["box_softmax"]).max() <= 1e-6                      # the reference's softmax() on every sibling group
+    thresh = float(g["thresh"])
+    for tag, hier, cmap in (("top", .5, None), ("top_lo", .1, None), ("map", .5, g["map"])):
+        o = [None] * (len(net.layers) - 1) + [g["head"].copy()]
+        o = P.hierarchy_predictions(net, o)
+        assert np.array_equal(o[-1], g[f"{tag}_head_after"])                 # in place, bit for bit
+        boxes, obj, probs, _ = P.get_network_boxes(net, o, 0, 32, 32, thresh, hier=hier, map=cmap)
+        gb, go, gp = tree_golden_arrays(g, tag, L.classes)
+        assert len(obj) == int(g[f"{tag}_num"])
+        np.testing.assert_allclose(boxes, gb, rtol=1e-5, atol=1e-7)
+        assert np.array_equal(obj, go) and np.array_equal(probs, gp)

@@ -162,7 +162,7 @@ static void build_engine_device_state(b200_engine *e, network *net)
             const layer &sl = net->layers[sidx];
             bool ok = place_route[sidx] < 0 && coff % align == 0 && sl.out_c % 16 == 0 &&
                       (sl.type == CONVOLUTIONAL || sl.type == UPSAMPLE || sl.type == SHORTCUT || sl.type == MAXPOOL || sl.type == REORG);
-            if (sl.type == CONVOLUTIONAL && (e->L[sidx].fused_into >= 0 || (sidx == 0 && e->L[0].stem_kpad))) ok = false;
+            if (sl.type == CONVOLUTIONAL && e->L[sidx].fused_into >= 0) ok = false;
             for (int c : cons[sidx]) {
                 LAYER_TYPE ct = net->layers[c].type;
                 if (ct == CONNECTED || ct == YOLO || ct == REGION || ct == DETECTION) ok = false;     // these read dense buffers
@@ -254,13 +254,7 @@ static void build_engine_device_state(b200_engine *e, network *net)
         DevLayer &d = e->L[i];
         if (l.type == CONVOLUTIONAL) {
             d.cout_pad = (int)align_up(l.n, 16);
-            // experimental: first layer as im2col + dense tcgen05 GEMM (B200_STEM_TC=1).  Measured slower than the
-            // specialised CUDA-core kernel on YOLOv3-416 b64 (1.25 + 0.61 ms vs 0.83 ms), so it is off by default.
-            if (i == 0 && d.stem && e->precision == B200_PREC_BF16 && getenv("B200_STEM_TC")) {
-                int kpad = (int)align_up(l.size * l.size * l.c, 32);
-                if (kpad <= 160) d.stem_kpad = kpad;
-            }
-            d.w_bytes = (size_t)d.cout_pad * (d.stem_kpad ? d.stem_kpad : l.size * l.size * l.c) * esize;
+            d.w_bytes = (size_t)d.cout_pad * l.size * l.size * l.c * esize;
             d.w_off = off; off = align_up(off + d.w_bytes, 256);
             d.scale_off = off; off = align_up(off + d.cout_pad * sizeof(float), 256);
             d.shift_off = off; off = align_up(off + d.cout_pad * sizeof(float), 256);
@@ -300,14 +294,6 @@ static void build_engine_device_state(b200_engine *e, network *net)
                 abort();
             }
             d.kernel = d.stem ? "conv_stem" : "conv_simt";
-            if (d.stem && d.stem_kpad) {
-                d.stem_cols = (bf16 *)dev_alloc((size_t)e->cap * l.out_h * l.out_w * d.stem_kpad * sizeof(bf16));
-                TView cols{d.stem_cols, e->cap, l.out_h, l.out_w, d.stem_kpad, d.stem_kpad, DT_BF16};
-                ConvParams p1{1, 1, 0, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
-                d.tc = conv_tc_plan_create(cols, d.out, p1, nullptr, 1.f, 1.f);
-                if (d.tc) d.kernel = "im2col+conv_tc";
-                else { cudaFree(d.stem_cols); d.stem_cols = nullptr; d.stem_kpad = -1; }   // -1: weights already sized for kpad; not reachable in practice
-            }
             if (!d.stem && e->precision == B200_PREC_BF16) {
                 ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
                 if (d.block_head) { d.kernel = "conv_tc(block)"; break; }          // computed by the next layer's kernel
@@ -342,7 +328,7 @@ static void build_engine_device_state(b200_engine *e, network *net)
         case MAXPOOL: {
             d.kernel = "maxpool";
             // stem -> [maxpool] size 2 stride 2 (YOLOv2, YOLOv3-tiny): pooled by the stem kernel's store warp
-            if (i == 1 && e->fusion && e->precision == B200_PREC_BF16 && e->L[0].stem && !e->L[0].stem_kpad && cons[0].size() == 1 &&
+            if (i == 1 && e->fusion && e->precision == B200_PREC_BF16 && e->L[0].stem && cons[0].size() == 1 &&
                 l.size == 2 && l.stride == 2 && l.out_w * 2 == l.w && l.out_h * 2 == l.h && d.out.ld == d.out.c) {
                 const layer &c0 = net->layers[0];
                 ConvParams p0{c0.size, c0.stride, c0.pad, act_id(c0.activation), e->L[0].w, e->L[0].scale, e->L[0].shift, e->L[0].cout_pad};
@@ -476,7 +462,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.stem_kpad = 0; d.stem_cols = nullptr; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; d.fc_tmp = nullptr; d.pool_fused = false; d.pool_away = false; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; d.fc_tmp = nullptr; d.pool_fused = false; d.pool_away = false; }
     e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->d_input_next = nullptr; e->submitted = 0; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
@@ -521,7 +507,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         for (auto &d : e->L) {
             if (d.tc) conv_tc_plan_destroy(d.tc);
             if (d.owns_out) cudaFree(d.out.p);
-            cudaFree(d.stem_cols); cudaFree(d.fc_tmp);
+            cudaFree(d.fc_tmp);
             if (d.head_out && d.type != DROPOUT) cudaFree(d.head_out);
         }
         cudaFree(e->d_input); cudaFree(e->d_input_next); cudaEventDestroy(e->submit_done); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
@@ -571,7 +557,7 @@ extern "C" void b200_engine_upload_weights(b200_engine *e, network *net)
         const layer &l = net->layers[i];
         DevLayer &d = e->L[i];
         if (l.type == CONVOLUTIONAL) {
-            const int K = d.stem_kpad > 0 ? d.stem_kpad : l.size * l.size * l.c;      // the im2col stem pads K with zeros
+            const int K = l.size * l.size * l.c;
             unsigned char *w = host.data() + d.w_off;
             for (int o = 0; o < l.n; ++o)
                 for (int c = 0; c < l.c; ++c)
@@ -655,10 +641,7 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
     case CONVOLUTIONAL: {
         ConvParams p{l.size, l.stride, l.pad, act_id(l.activation), d.w, d.scale, d.shift, d.cout_pad};
         if (d.block_head) break;                                   // computed inside the next layer's fused block kernel
-        if (d.stem && d.tc && e->conv_backend == 0) {
-            launch_stem_im2col(e->d_input, batch, l.h, l.w, l.c, d.stem_cols, l.out_h, l.out_w, d.stem_kpad, l.size, l.stride, l.pad, s);
-            launch_conv_tc(d.tc, s);
-        } else if (d.stem) {
+        if (d.stem) {
             TView pool = d.pool_fused ? view_of(e->L[1], batch) : TView{nullptr, 0, 0, 0, 0, 0, 0};
             launch_conv_stem(e->d_input, batch, l.h, l.w, l.c, out, p, s, d.pool_fused && e->conv_backend == 0 ? &pool : nullptr);
         }
@@ -752,7 +735,7 @@ static int stage_input(b200_engine *e, network *net, const float *input)
     const layer &l0 = net->layers[0];
     DevLayer &d0 = e->L[0];
     int chunks = 1;
-    if (d0.stem && !(d0.tc && e->conv_backend == 0) && !getenv("B200_NO_COPY_OVERLAP")) {
+    if (d0.stem && !getenv("B200_NO_COPY_OVERLAP")) {
         if (batch % 8 == 0 && batch >= 16) chunks = 8;
         else if (batch % 4 == 0 && batch >= 8) chunks = 4;
         else if (batch % 2 == 0 && batch >= 4) chunks = 2;
@@ -824,7 +807,7 @@ extern "C" void b200_set_conv_backend(network *net, int backend)
 {
     b200_engine *e = b200_engine_of(net);
     for (auto &d : e->L)
-        if (backend != 0 && (d.fused_into >= 0 || d.stem_kpad > 0 || d.block_head || d.up_fused || d.pool_fused)) {
+        if (backend != 0 && (d.fused_into >= 0 || d.block_head || d.up_fused || d.pool_fused)) {
             fprintf(stderr, "b200-darknet: the CUDA-core conv backend needs an unfused plan (parse with B200_FUSE=0 B200_STEM_SIMT=1)\n");
             abort();
         }

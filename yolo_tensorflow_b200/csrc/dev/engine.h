@@ -21,8 +21,6 @@ struct DevLayer {
     int cout_pad;
     ConvTcPlan *tc;
     bool stem;
-    int stem_kpad;             // > 0: first layer runs as im2col (fp32 NCHW -> bf16 [pixels][kpad]) + dense tcgen05 GEMM
-    bf16 *stem_cols;
     int fused_into;            // conv whose epilogue also performs shortcut layer `fused_into` (its own output is not materialised)
     bool fused_away;           // shortcut executed inside the previous conv's epilogue
     bool up_fused;             // conv that writes its result 2x upsampled straight into the following [upsample]'s buffer

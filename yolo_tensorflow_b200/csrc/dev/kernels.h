@@ -25,8 +25,6 @@ void launch_upsample(TView in, TView out, int stride, float scale, cudaStream_t 
 void launch_shortcut(TView in, TView add, TView out, float alpha, float beta, int act, cudaStream_t s);
 void launch_copy_channels(TView in, TView out, cudaStream_t s);               // out view already offset to its slice
 void launch_reorg(TView in, TView out, int stride, cudaStream_t s);
-void launch_stem_im2col(const float *in_nchw, int n, int h, int w, int c, bf16 *cols, int oh, int ow, int kpad, int size, int stride,
-                        int pad, cudaStream_t s);
 
 // ---- convolution family ------------------------------------------------------------------------------
 struct ConvParams {

@@ -332,47 +332,6 @@ void launch_reorg(TView in, TView out, int stride, cudaStream_t s)
     B200_LAUNCHED();
 }
 
-// ---------------------------------------------------------------------------------------------------
-// first-layer im2col: fp32 NCHW image -> bf16 [pixels][KPAD] patch matrix (K = size*size*C in (ky,kx,c) order,
-// zero padded to KPAD).  With C = 3 the patch of a 3x3 stem is 27 values = one 64-byte row, which turns the stem
-// into a dense [pixels x 32] x [32 x filters] GEMM for the tcgen05 kernel (no CUDA-core convolution in the bf16 path).
-// One thread per (pixel, 8-value group): 16-byte coalesced stores; the image reads hit L1 (each value is reused size^2 times).
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-stem_im2col_kernel(const float *__restrict__ in, int N, int H, int W, int C, bf16 *__restrict__ cols, int OH, int OW, int KPAD,
-                   int size, int stride, int pad)
-{
-    const int groups = KPAD / 8;
-    const long long total = (long long)N * OH * OW * groups;
-    const int K = size * size * C;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(t % groups);
-        const long long pix = t / groups;
-        const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = g * 8 + j;
-            float x = 0.f;
-            if (k < K) {
-                const int tap = k / C, c = k - tap * C;
-                const int ky = tap / size, kx = tap - ky * size;
-                const int y = oy * stride + ky - pad, xx = ox * stride + kx - pad;
-                if (y >= 0 && y < H && xx >= 0 && xx < W) x = __ldg(in + (((size_t)n * C + c) * H + y) * W + xx);
-            }
-            v[j] = x;
-        }
-        store_vec<bf16>(cols + pix * KPAD + g * 8, v);
-    }
-}
-
-void launch_stem_im2col(const float *in_nchw, int n, int h, int w, int c, bf16 *cols, int oh, int ow, int kpad, int size, int stride,
-                        int pad, cudaStream_t s)
-{
-    long long total = (long long)n * oh * ow * (kpad / 8);
-    stem_im2col_kernel<<<grid_for(total), kThreads, 0, s>>>(in_nchw, n, h, w, c, cols, oh, ow, kpad, size, stride, pad);
-    B200_LAUNCHED();
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Device-side preprocessing: letterbox_image (image.c:960-979) = aspect-preserving resize_image

@@ -59,6 +59,25 @@ def make_cfg(model, out_dir, batch=1, width=None, height=None):
     return dst
 
 
+def make_tree_cfg(out_dir, tree_path, batch=1, size=64, classes=240, num=3):
+    """a small YOLO9000-style network: two conv/maxpool stages and a [region] head with a class WordTree (`tree=`)"""
+    text = (f"[net]\nbatch={batch}\nsubdivisions=1\nheight={size}\nwidth={size}\nchannels=3\nmomentum=0.9\ndecay=0.0005\n"
+            "learning_rate=0.001\nmax_batches=1\npolicy=constant\n"
+            "[convolutional]\nbatch_normalize=1\nfilters=16\nsize=3\nstride=1\npad=1\nactivation=leaky\n[maxpool]\nsize=2\nstride=2\n"
+            "[convolutional]\nbatch_normalize=1\nfilters=64\nsize=3\nstride=1\npad=1\nactivation=leaky\n[maxpool]\nsize=2\nstride=2\n"
+            f"[convolutional]\nfilters={num * (classes + 5)}\nsize=1\nstride=1\npad=1\nactivation=linear\n"
+            f"[region]\nanchors=0.77,1.02,2.3,1.9,3.9,4.4\nbias_match=1\nclasses={classes}\ncoords=4\nnum={num}\nsoftmax=1\njitter=.2\n"
+            f"rescore=1\nthresh=.6\ntree={tree_path}\n")
+    os.makedirs(out_dir, exist_ok=True)
+    dst = os.path.join(out_dir, f"yolo9000-small_b{batch}_{size}.cfg")
+    if not (os.path.exists(dst) and open(dst).read() == text):
+        tmp = dst + ".%d.tmp" % os.getpid()
+        with open(tmp, "w") as f:
+            f.write(text)
+        os.replace(tmp, dst)
+    return dst
+
+
 def walk_shapes(cfg_path):
     """minimal shape walk of the inference layer types -> list of dicts (type, c,h,w in, out_c,out_h,out_w, params...)"""
     secs = read_cfg(cfg_path)
