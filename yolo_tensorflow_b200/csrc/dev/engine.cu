@@ -102,6 +102,8 @@ static void build_engine_device_state(b200_engine *e, network *net)
     B200_CHECK(cudaEventCreateWithFlags(&e->submit_done, cudaEventDisableTiming));
     B200_CHECK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
     B200_CHECK(cudaEventCreateWithFlags(&e->tail_done, cudaEventDisableTiming));
+    B200_CHECK(cudaStreamCreateWithFlags(&e->tail_stream, cudaStreamNonBlocking));
+    B200_CHECK(cudaEventCreateWithFlags(&e->fwd_done, cudaEventDisableTiming));
     B200_CHECK(cudaEventCreateWithFlags(&e->lb_uploaded, cudaEventDisableTiming));
     B200_CHECK(cudaEventCreateWithFlags(&e->lb_done, cudaEventDisableTiming));
     e->fwd_enqueued = 0;
@@ -432,6 +434,16 @@ static void build_engine_device_state(b200_engine *e, network *net)
         e->classes = l.classes;                  // network.c:528 takes classes from the LAST layer
     }
     e->boxes_per_image = base;
+    // the detection tail of batch k may still run (on its own stream) while batch k+1's forward pass starts: the first layer
+    // that overwrites a buffer the tail reads — a head's l.output or the logits of the convolution feeding it — waits for it
+    e->tail_guard_layer = net->n;
+    for (int i = 0; i < net->n; ++i) {
+        const LAYER_TYPE t = net->layers[i].type;
+        if (t != YOLO && t != REGION && t != DETECTION) continue;
+        int feeder = i > 0 ? i - 1 : 0;                      // the layer whose output the head (and the raw-logit decode) reads
+        while (feeder > 0 && net->layers[feeder].type == DROPOUT) --feeder;
+        if (feeder < e->tail_guard_layer) e->tail_guard_layer = feeder;
+    }
     // the reference API moves the heads' l.output between host and device on every call (network.c:505, yolo_layer.c:359-362
     // on the way out; get_network_boxes reads them on the way in): page-lock those host buffers while this plan lives
     {
@@ -519,7 +531,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaFree(e->d_raw); cudaFree(e->d_lb_items); cudaFree(e->d_im_dims[0]); cudaFree(e->d_im_dims[1]);
         cudaFreeHost(e->h_box); cudaFreeHost(e->h_obj); cudaFreeHost(e->h_prob); cudaFreeHost(e->h_id);
         for (auto &ev : e->copy_done) cudaEventDestroy(ev);
-        cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaEventDestroy(e->tail_done); cudaEventDestroy(e->lb_uploaded); cudaEventDestroy(e->lb_done);
+        cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaStreamDestroy(e->tail_stream); cudaEventDestroy(e->fwd_done); cudaEventDestroy(e->tail_done); cudaEventDestroy(e->lb_uploaded); cudaEventDestroy(e->lb_done);
         cudaStreamDestroy(e->stream);
     }
     delete e;
@@ -722,6 +734,7 @@ static void forward_layers(b200_engine *e, network *net, int start, int end, boo
     }
     for (int i = start; i < end; ++i) {
         if (skip_yolo_forward && net->layers[i].type == YOLO) continue;   // the fused detection path decodes from the raw logits
+        if (i == e->tail_guard_layer) B200_CHECK(cudaStreamWaitEvent(e->stream, e->tail_done, 0));   // no-op unless a tail is in flight
         run_layer(e, net, i, batch);
     }
 }
@@ -1157,13 +1170,22 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
     // w == h == 0: every image is corrected with its own original size, recorded by b200_letterbox_batch*
     const int *im_dims = (w == 0 && h == 0) ? e->d_im_dims[e->dims_cur] : nullptr;
     if (w == 0 && h == 0 && !im_dims) { fprintf(stderr, "b200-darknet: w = h = 0 needs a preceding b200_letterbox_batch call\n"); abort(); }
-    launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, use_raw, e->cand, e->stream, im_dims);
+    // decode + NMS + collect go to their own stream behind the forward pass: in the serving loop the next batch's forward pass
+    // is enqueued right after (after_tail), and these small latency-bound kernels then run beside its first, bandwidth-bound
+    // layers instead of in front of them (B200_NO_TAIL_OVERLAP=1 keeps everything on one stream: the A/B switch)
+    static const bool tail_overlap = getenv("B200_NO_TAIL_OVERLAP") == nullptr;
+    cudaStream_t ts = tail_overlap ? e->tail_stream : e->stream;
+    if (tail_overlap) {
+        B200_CHECK(cudaEventRecord(e->fwd_done, e->stream));
+        B200_CHECK(cudaStreamWaitEvent(ts, e->fwd_done, 0));
+    }
+    launch_decode(e->d_heads, (int)e->heads.size(), 0, batch, net->w, net->h, w, h, thresh, relative, 1, use_raw, e->cand, ts, im_dims);
     launch_nms_sort(e->cand.box, e->cand.prob, e->cand.obj, e->cand.count, batch, e->cand.cap, e->classes, nms_thresh,
-                    e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, e->stream);
-    B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), e->stream));
+                    e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, ts);
+    B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), ts));
     launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
-                   e->d_records, max_out, e->d_record_count, e->stream);
-    B200_CHECK(cudaEventRecord(e->tail_done, e->stream));
+                   e->d_records, max_out, e->d_record_count, ts);
+    B200_CHECK(cudaEventRecord(e->tail_done, ts));
     B200_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->tail_done, 0));
     // multi-GPU: every rank's records travel to the gather root over NCCL (send/recv on the result stream, so the transfer
     // runs beside the next batch's forward pass like the read-back does); the root then returns all of them.  Enqueued BEFORE

@@ -46,6 +46,9 @@ struct b200_engine {
     int submitted;
     cudaStream_t d2h_stream;   // serving loop: results of batch k are read back here while batch k+1 already computes
     cudaEvent_t tail_done;     // decode + NMS + collect of the current batch finished (d2h_stream waits on it)
+    cudaStream_t tail_stream;  // serving loop: decode + NMS + collect of batch k run here, beside the first layers of batch k+1
+    cudaEvent_t fwd_done;      // the forward pass of the current batch is complete (tail_stream waits on it)
+    int tail_guard_layer;      // first layer that overwrites something the tail reads (head logits / l.output): it waits for tail_done
     cudaEvent_t lb_uploaded, lb_done;   // b200_letterbox_batch*: raw images are on the device / the resize kernel has consumed them
     int fwd_enqueued;          // the submitted batch's forward pass is already in the compute stream (b200_detect_submitted)
     TView in_view;             // NHWC copy of the input (only when layer 0 is not a stem conv)

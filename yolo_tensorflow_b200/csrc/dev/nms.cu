@@ -18,42 +18,58 @@
 
 #define NMS_THREADS 1024                     // the general kernel serves the few very heavy classes (thousands of survivors): one unit per CTA, so CTA width is what parallelises it
 #define NMS_SMEM_M 512                       // survivors per class whose IoU bit-matrix lives in shared memory
-#define host_smem_work_bytes (512 * 28 + 512 * 16 * 4 + 64)   // == host_work_bytes(NMS_SMEM_M): size of the smem work area
+#define host_smem_work_bytes (512 * 32 + 512 * 16 * 4 + 64)   // == host_work_bytes(NMS_SMEM_M): size of the smem work area
 
-__device__ __forceinline__ float overlap_ref(float x1, float w1, float x2, float w2)
-{
-    // w/2 == w*0.5f exactly in binary floating point (no IEEE division subroutine needed)
-    const float h1 = __fmul_rn(w1, 0.5f), h2 = __fmul_rn(w2, 0.5f);
-    float l1 = __fsub_rn(x1, h1), l2 = __fsub_rn(x2, h2);
-    float left = l1 > l2 ? l1 : l2;
-    float r1 = __fadd_rn(x1, h1), r2 = __fadd_rn(x2, h2);
-    float right = r1 < r2 ? r1 : r2;
-    return __fsub_rn(right, left);
-}
+// box_iou(a,b) > thresh (box.c:152-182), bit-exact, on PRECOMPUTED per-box values: corners (l, r, t, b) = (x - w/2, x + w/2,
+// y - h/2, y + h/2) and area = w*h, each rounded exactly as the reference rounds them inside overlap() / box_union() (w/2 ==
+// w*0.5f exactly in binary floating point), so the pair test costs ~20 instructions.  Boxes that do not intersect are decided
+// without a division: the reference computes 0/union = 0 (or 0/0 = NaN) there, and neither exceeds a non-negative threshold.
+// Otherwise box_iou > thresh <=> inter > thresh * union for a positive finite union: the product decides every pair that is
+// not within 1e-5 of the threshold, the rest (and every non-finite case: the NMS stress configuration has boxes of infinite
+// size) take the reference's own IEEE division.
+struct NmsBox { float l, r, t, b; };
 
-__device__ __forceinline__ float iou_ref(float4 a, float4 b)      // (x,y,w,h) centre + size
+// the same decision straight from (x, y, w, h) records: what the small-unit kernel uses (one 16-byte shared-memory read per
+// box; measured there, the extra read of a precomputed area costs more than the arithmetic it saves)
+__device__ __forceinline__ bool suppresses_xywh(float4 a, float4 b, float thresh)
 {
-    float w = overlap_ref(a.x, a.z, b.x, b.z);
-    float h = overlap_ref(a.y, a.w, b.y, b.w);
-    float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
-    float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
-    return __fdiv_rn(inter, uni);
-}
-
-// box_iou(a,b) > thresh, bit-exact, without paying for the division when the boxes do not intersect: then the
-// reference computes 0/union = 0 (or 0/0 = NaN), and neither exceeds a non-negative threshold.
-__device__ __forceinline__ bool suppresses(float4 a, float4 b, float thresh)
-{
-    float w = overlap_ref(a.x, a.z, b.x, b.z);
-    float h = overlap_ref(a.y, a.w, b.y, b.w);
+    const float ahw = __fmul_rn(a.z, 0.5f), bhw = __fmul_rn(b.z, 0.5f), ahh = __fmul_rn(a.w, 0.5f), bhh = __fmul_rn(b.w, 0.5f);
+    const float l1 = __fsub_rn(a.x, ahw), l2 = __fsub_rn(b.x, bhw), r1 = __fadd_rn(a.x, ahw), r2 = __fadd_rn(b.x, bhw);
+    const float t1 = __fsub_rn(a.y, ahh), t2 = __fsub_rn(b.y, bhh), b1 = __fadd_rn(a.y, ahh), b2 = __fadd_rn(b.y, bhh);
+    const float w = __fsub_rn(r1 < r2 ? r1 : r2, l1 > l2 ? l1 : l2), h = __fsub_rn(b1 < b2 ? b1 : b2, t1 > t2 ? t1 : t2);
     if (thresh >= 0.f && (w < 0 || h < 0 || w == 0.f || h == 0.f)) return false;
-    float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
-    float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    const float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
     // the fast approximate quotient (<= 2 ulp off) decides every pair that is not within a hair of the threshold;
     // only those few take the IEEE division the reference performs, so the decision is still bit-exact
-    float q = __fdividef(inter, uni);
+    const float q = __fdividef(inter, uni);
     if (q > thresh * 1.00001f + 1e-30f && q < 3.0e38f) return true;
     if (q < thresh * 0.99999f - 1e-30f) return false;
+    return __fdiv_rn(inter, uni) > thresh;
+}
+
+__device__ __forceinline__ NmsBox nms_corners(float4 v)          // v = (x, y, w, h)
+{
+    const float hw = __fmul_rn(v.z, 0.5f), hh = __fmul_rn(v.w, 0.5f);
+    NmsBox c;
+    c.l = __fsub_rn(v.x, hw); c.r = __fadd_rn(v.x, hw);
+    c.t = __fsub_rn(v.y, hh); c.b = __fadd_rn(v.y, hh);
+    return c;
+}
+
+__device__ __forceinline__ bool suppresses_c(NmsBox a, float area_a, NmsBox b, float area_b, float thresh)
+{
+    const float left = a.l > b.l ? a.l : b.l, right = a.r < b.r ? a.r : b.r;       // the reference's ternaries (NaN falls to b)
+    const float top = a.t > b.t ? a.t : b.t, bottom = a.b < b.b ? a.b : b.b;
+    const float w = __fsub_rn(right, left), h = __fsub_rn(bottom, top);
+    if (thresh >= 0.f && (w < 0 || h < 0 || w == 0.f || h == 0.f)) return false;   // 0 / union (or 0 / 0) never exceeds thresh >= 0
+    const float inter = (w < 0 || h < 0) ? 0.f : __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    if (uni > 0.f && uni < 3.0e38f && inter < 3.0e38f) {
+        const float tu = __fmul_rn(thresh, uni);
+        if (inter > __fmaf_rn(fabsf(tu), 1e-5f, tu) + 1e-30f) return true;
+        if (inter < __fmaf_rn(fabsf(tu), -1e-5f, tu) - 1e-30f) return false;
+    }
     return __fdiv_rn(inter, uni) > thresh;
 }
 
@@ -62,14 +78,15 @@ struct NmsWork {
     float *score;      // [m] gathered scores, original order
     int *src;          // [m] original detection index, original order
     int *order;        // [m] original detection index, sorted order
-    float4 *sbox;      // [m] boxes, sorted order
+    float4 *sbox;      // [m] box corners (l, r, t, b), sorted order
+    float *area;       // [m] w*h, sorted order
     unsigned *mask;    // [m][words]
 };
 
 __device__ __forceinline__ size_t work_bytes(int m)
 {
     size_t words = (m + 31) / 32;
-    return (size_t)m * (4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
+    return (size_t)m * (4 + 4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
 }
 
 __device__ __forceinline__ NmsWork carve(unsigned char *base, int m)
@@ -80,6 +97,7 @@ __device__ __forceinline__ NmsWork carve(unsigned char *base, int m)
     w.score = (float *)(base + off); off += (size_t)m * 4;
     w.src = (int *)(base + off); off += (size_t)m * 4;
     w.order = (int *)(base + off); off += (size_t)m * 4;
+    w.area = (float *)(base + off); off += (size_t)m * 4;
     off = (off + 15) & ~(size_t)15;
     w.mask = (unsigned *)(base + off);
     return w;
@@ -129,12 +147,12 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
         }
         NmsWork wk = carve(base, m);
         // slab path: only the bit-matrix has to live in HBM; scores / indices / sorted boxes stay in shared memory when they
-        // fit (28 bytes per survivor), which turns the m^2 box reads of the IoU pass into LDS instead of L1/L2 traffic
+        // fit (32 bytes per survivor), which turns the m^2 box reads of the IoU pass into LDS instead of L1/L2 traffic
         size_t lists_bytes = 0;
-        if (m > NMS_SMEM_M && (size_t)m * 28 + 64 + 8192 <= (size_t)host_smem_work_bytes) {
+        if (m > NMS_SMEM_M && (size_t)m * 32 + 64 + 8192 <= (size_t)host_smem_work_bytes) {
             NmsWork in_smem = carve(smem_work, m);
-            wk.sbox = in_smem.sbox; wk.score = in_smem.score; wk.src = in_smem.src; wk.order = in_smem.order;
-            lists_bytes = ((size_t)m * 28 + 64 + 15) & ~(size_t)15;
+            wk.sbox = in_smem.sbox; wk.score = in_smem.score; wk.src = in_smem.src; wk.order = in_smem.order; wk.area = in_smem.area;
+            lists_bytes = ((size_t)m * 32 + 64 + 15) & ~(size_t)15;
         }
         const int words = (m + 31) / 32;
 
@@ -164,25 +182,42 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
             }
             int d = wk.src[i];
             wk.order[rank] = d;
-            wk.sbox[rank] = *reinterpret_cast<const float4 *>(ubox + (size_t)d * 4);
+            const float4 v = *reinterpret_cast<const float4 *>(ubox + (size_t)d * 4);
+            const NmsBox c = nms_corners(v);
+            wk.sbox[rank] = make_float4(c.l, c.r, c.t, c.b);
+            wk.area[rank] = __fmul_rn(v.z, v.w);
         }
         for (int w = threadIdx.x; w < words; w += NMS_THREADS) removed[w] = 0u;
         __syncthreads();
 
-        // ---- IoU bit-matrix: word (i, wj) covers j in [32*wj, 32*wj+32), only j > i matters
-        for (long long t = threadIdx.x; t < (long long)m * words; t += NMS_THREADS) {
-            int i = (int)(t / words), wj = (int)(t % words);
-            unsigned bits = 0u;
-            if (wj * 32 + 31 > i) {
-                float4 a = wk.sbox[i];
-                int j0 = wj * 32;
+        // ---- IoU bit-matrix: word (i, wj) covers j in [32*wj, 32*wj+32), only j > i matters.  One warp per word: lane b
+        // tests the pair (i, 32*wj + b) — box i is a broadcast read, boxes j are 32 consecutive entries (no bank conflicts; a
+        // thread walking its own 32 j's made every lane of a warp hit the same bank) — and a ballot assembles the word.  A warp
+        // takes 32 consecutive words at a time so that the store is one coalesced line.
+        {
+            const int total_words = m * words;                              // m <= 32768, words <= 1024: fits an int
+            const int nwarps = NMS_THREADS / 32;
+            for (int t0 = warp * 32; t0 < total_words; t0 += nwarps * 32) {
+                unsigned mine = 0u;
+                const int kmax = (total_words - t0) < 32 ? (total_words - t0) : 32;
 #pragma unroll 4
-                for (int b = 0; b < 32; ++b) {
-                    int j = j0 + b;
-                    if (j > i && j < m && suppresses(a, wk.sbox[j], thresh)) bits |= 1u << b;
+                for (int k = 0; k < kmax; ++k) {
+                    const int t = t0 + k;
+                    const int i = t / words, wj = t % words;
+                    unsigned bits = 0u;
+                    if (wj * 32 + 31 > i) {                                  // warp-uniform
+                        const int j = wj * 32 + lane;
+                        bool sup = false;
+                        if (j > i && j < m) {
+                            const float4 av = wk.sbox[i], bv = wk.sbox[j];
+                            sup = suppresses_c(NmsBox{av.x, av.y, av.z, av.w}, wk.area[i], NmsBox{bv.x, bv.y, bv.z, bv.w}, wk.area[j], thresh);
+                        }
+                        bits = __ballot_sync(0xffffffffu, sup);
+                    }
+                    if (lane == k) mine = bits;
                 }
+                if (lane < kmax) wk.mask[t0 + lane] = mine;
             }
-            wk.mask[(size_t)i * words + wj] = bits;
         }
         __syncthreads();
 
@@ -190,15 +225,45 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
         // staged through shared memory a chunk at a time by the whole CTA (one L2 round trip per chunk instead of one
         // per row; the dependent walk inside a chunk then runs at shared-memory latency).
         if (m <= NMS_SMEM_M) {
+            // words <= 16: the removed set lives in one register per lane, row i+1 is fetched while row i is decided, so a step of
+            // the (inherently serial) scan costs a shuffle, a test and an OR instead of a shared-memory round trip
             if (warp == 0) {
+                unsigned rem = 0u;
+                unsigned nxt = lane < words ? wk.mask[lane] : 0u;
                 for (int i = 0; i < m; ++i) {
-                    unsigned r = removed[i >> 5];
-                    if (!((r >> (i & 31)) & 1u)) {
-                        for (int w = (i >> 5) + lane; w < words; w += 32) removed[w] |= wk.mask[(size_t)i * words + w];
-                    }
-                    __syncwarp();
+                    const unsigned cur = nxt;
+                    if (i + 1 < m) nxt = lane < words ? wk.mask[(size_t)(i + 1) * words + lane] : 0u;
+                    const unsigned r = __shfl_sync(0xffffffffu, rem, i >> 5);
+                    if (!((r >> (i & 31)) & 1u)) rem |= cur;
                 }
+                if (lane < words) removed[lane] = rem;
             }
+            __syncthreads();
+        } else if (words <= 32) {
+            // the same register-resident scan for up to 1024 survivors, rows staged from the HBM slab a chunk at a time
+            unsigned *stage = (unsigned *)(smem_work + lists_bytes);
+            const int stage_words = (int)(((size_t)host_smem_work_bytes - lists_bytes) / 4);
+            int rows_per_chunk = stage_words / words;
+            if (rows_per_chunk > 128) rows_per_chunk = 128;
+            if (rows_per_chunk < 1) rows_per_chunk = 1;
+            unsigned rem = 0u;                                            // meaningful in warp 0 only
+            for (int i0 = 0; i0 < m; i0 += rows_per_chunk) {
+                const int rows = (m - i0) < rows_per_chunk ? (m - i0) : rows_per_chunk;
+                for (int t = threadIdx.x; t < rows * words; t += NMS_THREADS) stage[t] = wk.mask[(size_t)i0 * words + t];
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned nxt = lane < words ? stage[lane] : 0u;
+                    for (int rr = 0; rr < rows; ++rr) {
+                        const int i = i0 + rr;
+                        const unsigned cur = nxt;
+                        if (rr + 1 < rows) nxt = lane < words ? stage[(rr + 1) * words + lane] : 0u;
+                        const unsigned r = __shfl_sync(0xffffffffu, rem, i >> 5);
+                        if (!((r >> (i & 31)) & 1u)) rem |= cur;
+                    }
+                }
+                __syncthreads();
+            }
+            if (warp == 0 && lane < words) removed[lane] = rem;
             __syncthreads();
         } else {
             unsigned *stage = (unsigned *)(smem_work + lists_bytes);  // what is left of the smem work area in the slab path
@@ -320,14 +385,16 @@ nms_small_kernel(const float *__restrict__ box, float *__restrict__ score, const
     if (threadIdx.x < NMS_SMALL_M / 32) s_removed[threadIdx.x] = 0u;
     __syncthreads();
     const int words = (m + 31) / 32;
+    // one thread per word: its 32 pair tests are independent, which is what hides the shared-memory latency in these small
+    // CTAs (measured: a warp per word with a ballot, the mapping of the general kernel, is 30 % slower here)
     for (int t = threadIdx.x; t < m * words; t += NMS_SMALL_THREADS) {
-        int i = t / words, wj = t % words;
+        const int i = t / words, wj = t % words;
         unsigned bits = 0u;
         if (wj * 32 + 31 > i) {
-            float4 a = s_box[i];
+            const float4 a = s_box[i];
             for (int b = 0; b < 32; ++b) {
-                int j = wj * 32 + b;
-                if (j > i && j < m && suppresses(a, s_box[j], thresh)) bits |= 1u << b;
+                const int j = wj * 32 + b;
+                if (j > i && j < m && suppresses_xywh(a, s_box[j], thresh)) bits |= 1u << b;
             }
         }
         s_mask[i][wj] = bits;
@@ -354,7 +421,7 @@ nms_small_kernel(const float *__restrict__ box, float *__restrict__ score, const
 static size_t host_work_bytes(int m)
 {
     size_t words = (m + 31) / 32;
-    return (size_t)m * (4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
+    return (size_t)m * (4 + 4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
 }
 
 static void ensure_scratch(NmsScratch *sc, int max_count, int ctas)
