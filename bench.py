@@ -239,7 +239,9 @@ class Runner:
         # slot of a rank and the result buffer are sized from these with head-room
         self.slot_per_image = 2048 if self.size <= 416 else 10240
         self.max_out = max(1 << 20, self.slot_per_image * batch * (world if comm_root(rank) else 1))
-        self.out = (dn.B200_DET * self.max_out)()
+        # page-locked result buffer: the records of a step (up to 59 MB at 608x608 x 256 images) come back by DMA, not through a staging copy
+        self.out_pinned = torch.empty(self.max_out * ctypes.sizeof(dn.B200_DET), dtype=torch.uint8).pin_memory()
+        self.out = ctypes.cast(self.out_pinned.data_ptr(), ctypes.POINTER(dn.B200_DET))
         self.counts = (dn.c_int * batch)()
         self.primed = False
         self.comm = False

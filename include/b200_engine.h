@@ -166,10 +166,11 @@ int  b200_detect_submitted(network *net, const float *next_input, int w, int h, 
  * libnccl.so.2).  The 128-byte id made by b200_comm_unique_id on one rank reaches the others by any out-of-band channel
  * (bench.py: torch.distributed's store).  No collective ever runs between layers:
  *   b200_comm_broadcast_weights   one ncclBroadcast of the folded / repacked parameter arena (b200_weights_arena);
- *   b200_comm_set_gather          from then on b200_detect_batch / b200_detect_submitted on `root` return the records of ALL
- *                                 ranks — rank order, image = image_base of the producing rank + its local index — moved by
- *                                 ncclSend/ncclRecv on the result stream beside the next batch's forward pass; the other
- *                                 ranks keep getting their own.  slot_records = most records one rank may contribute per batch. */
+ *   b200_comm_set_gather          from then on records carry GLOBAL image numbers (image_base of the producing rank + its local
+ *                                 index) and b200_detect_batch / b200_detect_submitted on `root` return the records of ALL
+ *                                 ranks, in rank order — moved by ncclSend/ncclRecv on the result stream beside the next batch's
+ *                                 forward pass; the other ranks keep getting their own.  slot_records = most records one rank
+ *                                 may contribute per batch. */
 int  b200_comm_unique_id(unsigned char *id, int bytes);           /* bytes >= 128; returns the id length */
 int  b200_comm_init(network *net, const unsigned char *id, int rank, int world);
 int  b200_comm_rank(network *net);

@@ -150,8 +150,8 @@ extern "C" int b200_comm_broadcast_weights(network *net, int root)
     return 0;
 }
 
-// From now on b200_detect_batch / b200_detect_submitted on `root` return the records of ALL ranks (image numbers global:
-// image_base + local index, ranks in order), the other ranks keep returning their own.  slot_records bounds what one rank can
+// From now on every rank's records carry GLOBAL image numbers (image_base + local index) and b200_detect_batch /
+// b200_detect_submitted on `root` return the records of ALL ranks, in rank order; the other ranks keep returning their own.  slot_records bounds what one rank can
 // contribute per batch (records beyond it are dropped and reported on stderr by the root).  root = -1 switches it off.
 extern "C" int b200_comm_set_gather(network *net, int root, int image_base, int slot_records)
 {
@@ -183,6 +183,7 @@ extern "C" int b200_comm_set_gather(network *net, int root, int image_base, int 
 
 bool b200_comm_gathers(const b200_engine *e) { return e->comm && e->comm->gather_root >= 0 && e->comm->world > 1; }
 bool b200_comm_is_root(const b200_engine *e) { return e->comm && e->comm->rank == e->comm->gather_root; }
+int  b200_comm_image_base(const b200_engine *e) { return b200_comm_gathers(e) ? e->comm->image_base : 0; }
 
 void b200_comm_enqueue_gather(b200_engine *e, cudaStream_t s)
 {
@@ -210,26 +211,20 @@ int b200_comm_collect_gathered(b200_engine *e, b200_det *out, int max_out, int o
     B200_CHECK(cudaMemcpyAsync(c->h_headers, c->d_headers, (size_t)c->world * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CHECK(cudaStreamSynchronize(s));
     int total = 0;
-    int first[1024], count[1024];
-    for (int r = 0; r < c->world && r < 1024; ++r) {
+    for (int r = 0; r < c->world; ++r) {
         int n = r == c->rank ? own_count : c->h_headers[4 * r];
         if (n > c->slot_records && r != c->rank) {
             fprintf(stderr, "b200-darknet: rank %d produced %d records, its gather slot holds %d: the rest is dropped\n", r, n, c->slot_records);
             n = c->slot_records;
         }
         if (total + n > max_out) n = max_out - total;
-        first[r] = total; count[r] = n;
-        if (n > 0) {
+        if (n > 0) {                                   // image numbers are already global: every rank's collect kernel adds its base
             const DetRecord *src = r == c->rank ? e->d_records : c->d_slots + (size_t)r * c->slot_records;
             B200_CHECK(cudaMemcpyAsync(out + total, src, (size_t)n * sizeof(DetRecord), cudaMemcpyDeviceToHost, s));
         }
         total += n;
     }
     B200_CHECK(cudaStreamSynchronize(s));
-    for (int r = 0; r < c->world && r < 1024; ++r) {
-        const int base = r == c->rank ? c->image_base : c->h_headers[4 * r + 1];
-        if (base) for (int i = 0; i < count[r]; ++i) out[first[r] + i].image += base;
-    }
     return total;
 }
 

@@ -1184,7 +1184,7 @@ static int detect_core(b200_engine *e, network *net, int first, int w, int h, fl
                     e->boxes_per_image, &e->nms_scratch, e->cand.cls_count, ts);
     B200_CHECK(cudaMemsetAsync(e->d_record_count, 0, sizeof(int), ts));
     launch_collect(e->cand.box, e->cand.prob, e->cand.obj, e->cand.id, e->cand.count, batch, e->cand.cap, e->classes,
-                   e->d_records, max_out, e->d_record_count, ts);
+                   e->d_records, max_out, e->d_record_count, ts, b200_comm_image_base(e));
     B200_CHECK(cudaEventRecord(e->tail_done, ts));
     B200_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->tail_done, 0));
     // multi-GPU: every rank's records travel to the gather root over NCCL (send/recv on the result stream, so the transfer

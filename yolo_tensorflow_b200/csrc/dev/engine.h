@@ -83,4 +83,5 @@ void b200_comm_enqueue_gather(b200_engine *e, cudaStream_t s);
 // root, after the stream has been synchronised: copy every rank's records to `out` (global image numbers); returns the count
 int  b200_comm_collect_gathered(b200_engine *e, b200_det *out, int max_out, int own_count, cudaStream_t s);
 bool b200_comm_is_root(const b200_engine *e);
+int  b200_comm_image_base(const b200_engine *e);                    // global number of this rank's image 0 while a gather is set, else 0
 void b200_comm_release(b200_engine *e);

@@ -48,52 +48,6 @@ void launch_yolo_forward(TView in, float *out, int anchors, int classes, cudaStr
     B200_LAUNCHED();
 }
 
-// region: thread per (image, anchor, cell); walks the entries of its box so the softmax needs no communication
-template <typename T>
-__global__ void region_forward_kernel(const T *__restrict__ in, float *__restrict__ out, int N, int HW, int ld,
-                                      int anchors, int classes, int coords, int softmax)
-{
-    const int entries = coords + 1 + classes;
-    const long long total = (long long)N * anchors * HW;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        int loc = (int)(t % HW);
-        int a = (int)((t / HW) % anchors);
-        int n = (int)(t / ((long long)HW * anchors));
-        const T *src = in + ((size_t)n * HW + loc) * ld + a * entries;
-        float *dst = out + ((size_t)n * anchors + a) * entries * HW + loc;
-        dst[0 * HW] = logistic_ref(Elem<T>::load(src + 0));
-        dst[1 * HW] = logistic_ref(Elem<T>::load(src + 1));
-        for (int e = 2; e < coords; ++e) dst[(size_t)e * HW] = Elem<T>::load(src + e);
-        dst[(size_t)coords * HW] = logistic_ref(Elem<T>::load(src + coords));
-        if (!softmax) {
-            for (int j = 0; j < classes; ++j) dst[(size_t)(coords + 1 + j) * HW] = logistic_ref(Elem<T>::load(src + coords + 1 + j));
-        } else {
-            // blas.c:305-321 softmax(input, n, temp=1, stride, output)
-            float largest = -FLT_MAX;
-            for (int j = 0; j < classes; ++j) { float v = Elem<T>::load(src + coords + 1 + j); if (v > largest) largest = v; }
-            float sum = 0;
-            for (int j = 0; j < classes; ++j) {
-                float v = Elem<T>::load(src + coords + 1 + j);
-                float e = (float)exp((double)(v / 1.f - largest / 1.f));
-                sum += e;
-                dst[(size_t)(coords + 1 + j) * HW] = e;
-            }
-            for (int j = 0; j < classes; ++j) dst[(size_t)(coords + 1 + j) * HW] /= sum;
-        }
-    }
-}
-
-void launch_region_forward(TView in, float *out, int anchors, int classes, int coords, int softmax, cudaStream_t s)
-{
-    int HW = in.h * in.w;
-    long long total = (long long)in.n * anchors * HW;
-    int grid = (int)((total + kThreads - 1) / kThreads);
-    if (grid > 148 * 16) grid = 148 * 16;
-    if (in.dtype == DT_F32) region_forward_kernel<float><<<grid, kThreads, 0, s>>>((const float *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, softmax);
-    else region_forward_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16 *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, softmax);
-    B200_LAUNCHED();
-}
-
 // detection (YOLOv1): plain copy of the connected layer's fp32 output, optional per-cell class softmax
 __global__ void detection_forward_kernel(const float *__restrict__ in, float *__restrict__ out, int batch, int outputs,
                                          int side, int classes, int softmax)
@@ -178,9 +132,12 @@ void launch_avg_flipped(float *head_out, int w, int h, int anchors, int entries,
 // l.temperature, which parse_region never sets — region_layer.c:179 — so every class probability comes out NaN there.)
 // One warp per box: the box's logits are contiguous in the NHWC input.
 // ---------------------------------------------------------------------------------------------------
+// The same kernel serves the plain region head (gsize == nullptr): one group over all classes when softmax = 1
+// (region_layer.c:182-185 -> blas.c:305-321), a logistic on every class otherwise (:171).
 template <typename T>
-__global__ void region_tree_forward_kernel(const T *__restrict__ in, float *__restrict__ out, int N, int HW, int ld, int anchors,
-                                           int classes, int coords, const int *__restrict__ gsize, const int *__restrict__ goff, int groups)
+__global__ void region_forward_kernel(const T *__restrict__ in, float *__restrict__ out, int N, int HW, int ld, int anchors,
+                                           int classes, int coords, const int *__restrict__ gsize, const int *__restrict__ goff, int groups,
+                                           int softmax)
 {
     const int entries = coords + 1 + classes;
     const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
@@ -195,8 +152,12 @@ __global__ void region_tree_forward_kernel(const T *__restrict__ in, float *__re
             for (int e = 2; e < coords; ++e) dst[(size_t)e * HW] = Elem<T>::load(src + e);
             dst[(size_t)coords * HW] = logistic_ref(Elem<T>::load(src + coords));
         }
+        if (!softmax) {
+            for (int j = lane; j < classes; j += 32) dst[(size_t)(coords + 1 + j) * HW] = logistic_ref(Elem<T>::load(src + coords + 1 + j));
+            continue;
+        }
         for (int g = 0; g < groups; ++g) {
-            const int off = coords + 1 + goff[g], sz = gsize[g];
+            const int off = coords + 1 + (gsize ? goff[g] : 0), sz = gsize ? gsize[g] : classes;
             float largest = -FLT_MAX;
             for (int j = lane; j < sz; j += 32) largest = fmaxf(largest, Elem<T>::load(src + off + j));
             for (int o = 16; o; o >>= 1) largest = fmaxf(largest, __shfl_xor_sync(0xffffffffu, largest, o));
@@ -218,8 +179,22 @@ void launch_region_tree_forward(TView in, float *out, int anchors, int classes, 
     const long long boxes = (long long)in.n * anchors * HW;
     int grid = (int)((boxes + 7) / 8);
     if (grid > 148 * 16) grid = 148 * 16;
-    if (in.dtype == DT_F32) region_tree_forward_kernel<float><<<grid, kThreads, 0, s>>>((const float *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, gsize, goff, groups);
-    else region_tree_forward_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16 *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, gsize, goff, groups);
+    if (in.dtype == DT_F32) region_forward_kernel<float><<<grid, kThreads, 0, s>>>((const float *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, gsize, goff, groups, 1);
+    else region_forward_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16 *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, gsize, goff, groups, 1);
+    B200_LAUNCHED();
+}
+
+// plain [region] head (YOLOv2): one warp per box — the box's logits are contiguous in the NHWC input, so the reads coalesce and
+// 54 080 warps (416x416 b64) are in flight instead of 54 080 threads (ncu, round 2: the thread-per-box version took 69 us for
+// 37 MB); max and sum of the softmax are warp reductions
+void launch_region_forward(TView in, float *out, int anchors, int classes, int coords, int softmax, cudaStream_t s)
+{
+    const int HW = in.h * in.w;
+    const long long boxes = (long long)in.n * anchors * HW;
+    int grid = (int)((boxes + 7) / 8);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (in.dtype == DT_F32) region_forward_kernel<float><<<grid, kThreads, 0, s>>>((const float *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, nullptr, nullptr, 1, softmax);
+    else region_forward_kernel<bf16><<<grid, kThreads, 0, s>>>((const bf16 *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, nullptr, nullptr, 1, softmax);
     B200_LAUNCHED();
 }
 

@@ -124,4 +124,4 @@ void launch_nms_obj(const float *box, float *obj, float *prob, const int *count,
 // gathers surviving (box,class) pairs into compact records; returns via counter
 struct DetRecord { int image, cls, box_id; float prob, objectness, x, y, w, h; };
 void launch_collect(const float *box, const float *prob, const float *obj, const int *id, const int *count, int images,
-                    int cap, int classes, DetRecord *out, int max_out, int *out_count, cudaStream_t s);
+                    int cap, int classes, DetRecord *out, int max_out, int *out_count, cudaStream_t s, int image_base = 0);   // image_base: added to every record's image number (multi-GPU shards)

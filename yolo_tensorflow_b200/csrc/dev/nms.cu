@@ -501,7 +501,7 @@ void launch_nms_obj(const float *box, float *obj, float *prob, const int *count,
 __global__ void __launch_bounds__(256)
 collect_kernel(const float *__restrict__ box, const float *__restrict__ prob, const float *__restrict__ obj,
                const int *__restrict__ id, const int *__restrict__ count, int images, int cap, int classes,
-               DetRecord *__restrict__ out, int max_out, int *__restrict__ out_count)
+               DetRecord *__restrict__ out, int max_out, int *__restrict__ out_count, int image_base)
 {
     // grid = (slices, images): only the count[img] live candidates of an image are visited
     const int img = blockIdx.y, lane = threadIdx.x & 31;
@@ -526,7 +526,7 @@ collect_kernel(const float *__restrict__ box, const float *__restrict__ prob, co
             if (slot < max_out) {
                 size_t d = (size_t)img * cap + i;
                 DetRecord r;
-                r.image = img; r.cls = k; r.box_id = id[d]; r.prob = p; r.objectness = obj[d];
+                r.image = img + image_base; r.cls = k; r.box_id = id[d]; r.prob = p; r.objectness = obj[d];
                 r.x = box[d * 4 + 0]; r.y = box[d * 4 + 1]; r.w = box[d * 4 + 2]; r.h = box[d * 4 + 3];
                 out[slot] = r;
             }
@@ -535,10 +535,10 @@ collect_kernel(const float *__restrict__ box, const float *__restrict__ prob, co
 }
 
 void launch_collect(const float *box, const float *prob, const float *obj, const int *id, const int *count, int images,
-                    int cap, int classes, DetRecord *out, int max_out, int *out_count, cudaStream_t s)
+                    int cap, int classes, DetRecord *out, int max_out, int *out_count, cudaStream_t s, int image_base)
 {
     if (images < 1) return;
     dim3 grid(8, images);
-    collect_kernel<<<grid, 256, 0, s>>>(box, prob, obj, id, count, images, cap, classes, out, max_out, out_count);
+    collect_kernel<<<grid, 256, 0, s>>>(box, prob, obj, id, count, images, cap, classes, out, max_out, out_count, image_base);
     B200_LAUNCHED();
 }
