@@ -574,6 +574,25 @@ def test_nms_sort_bit_exact(dn, n, classes):
     assert np.array_equal(dn.nms_sort_arrays(boxes, got, .45), got)
 
 
+def test_nms_beyond_32768_survivors_of_one_class(dn):
+    """40 000 survivors in ONE class (a YOLOv3 input of 736 x 736 and more has over 32 768 anchors): the removed bitset no
+    longer fits the kernel's shared memory and the lists live in the HBM slab.  The expected keep-list is known by
+    construction, so no m x m oracle is needed: 20 000 disjoint clusters of two identical boxes, scores strictly descending
+    with the index -> every even box is kept, every odd one suppressed by its twin."""
+    n = 40000
+    k = np.arange(n)
+    c = k // 2
+    boxes = np.stack([(c % 200) * .005 + .0025, (c // 200) * .005 + .0025, np.full(n, .004), np.full(n, .004)], axis=1).astype(np.float32)
+    probs = (1. - k * 1e-5).astype(np.float32).reshape(n, 1)
+    out = dn.nms_sort_arrays(boxes, probs, .45)
+    assert np.array_equal(out[0::2, 0], probs[0::2, 0]) and not out[1::2].any()
+    # and one unit just over the limits of the other paths: 1025 survivors (lists leave shared memory), 513 (matrix leaves it)
+    for m in (513, 1025, 2049):
+        bx, pr = random_dets(np.random.default_rng(m), m, 1, density=1.)
+        pr[pr == 0] = .5
+        assert np.array_equal(dn.nms_sort_arrays(bx, pr, .45), P.do_nms_sort(bx, np.ones(m, np.float32), pr, .45))
+
+
 def test_nms_edge_cases(dn):
     # empty
     assert dn.nms_sort_arrays(np.zeros((0, 4), np.float32), np.zeros((0, 3), np.float32), .45).shape == (0, 3)

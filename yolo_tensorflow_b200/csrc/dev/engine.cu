@@ -343,7 +343,17 @@ static void build_engine_device_state(b200_engine *e, network *net)
         }
         case UPSAMPLE: d.kernel = d.up_away ? "fused" : "upsample"; break;
         case SHORTCUT: d.kernel = d.fused_away ? "fused" : "shortcut"; break;
-        case REORG: d.kernel = "reorg"; break;
+        case REORG: {
+            d.kernel = "reorg";
+            const DevLayer &pd = e->L[i - 1];
+            if (!l.reverse && (size_t)l.h * l.w * l.c * dt_size(pd.out.dtype) <= 200 * 1024) {
+                std::vector<int> table(2 * (size_t)l.out_h * l.out_w * l.out_c);
+                reorg_build_table(l.h, l.w, l.c, l.out_h, l.out_w, l.out_c, d.out.ld, l.stride, table.data());
+                d.reorg_table = (int *)dev_alloc(table.size() * sizeof(int));
+                B200_CHECK(cudaMemcpy(d.reorg_table, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+            break;
+        }
         case ROUTE: {
             bool all_placed = l.n > 1;
             for (int j = 0; j < l.n && l.n > 1; ++j) if (place_route[l.input_layers[j]] != i) all_placed = false;
@@ -474,7 +484,7 @@ extern "C" b200_engine *b200_engine_create(network *net, int precision)
     e->conv_backend = 0;
     e->head_sync = 1;
     e->L.resize(net->n);
-    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; d.fc_tmp = nullptr; d.pool_fused = false; d.pool_away = false; }
+    for (auto &d : e->L) { d = DevLayer(); d.tc = nullptr; d.head_out = nullptr; d.w = nullptr; d.stem = false; d.owns_out = false; d.fused_into = -1; d.fused_away = false; d.block_head = false; d.up_fused = false; d.up_away = false; d.fc_tmp = nullptr; d.pool_fused = false; d.pool_away = false; d.reorg_table = nullptr; }
     e->fusion = b200_get_default_fusion();
     e->stream = nullptr; e->d_input = nullptr; e->d_input_next = nullptr; e->submitted = 0; e->arena = nullptr; e->xfer = nullptr; e->d_heads = nullptr;
     e->in_view = TView{nullptr, 0, 0, 0, 0, 0, 0};
@@ -519,7 +529,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         for (auto &d : e->L) {
             if (d.tc) conv_tc_plan_destroy(d.tc);
             if (d.owns_out) cudaFree(d.out.p);
-            cudaFree(d.fc_tmp);
+            cudaFree(d.fc_tmp); cudaFree(d.reorg_table);
             if (d.head_out && d.type != DROPOUT) cudaFree(d.head_out);
         }
         cudaFree(e->d_input); cudaFree(e->d_input_next); cudaEventDestroy(e->submit_done); cudaFree(e->in_view.p); cudaFree(e->arena); cudaFree(e->xfer); cudaFree(e->d_heads);
@@ -672,7 +682,7 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
         break;
     case REORG:
         if (l.reverse) { fprintf(stderr, "b200-darknet: reorg reverse=1 is outside the YOLO inference path\n"); abort(); }
-        launch_reorg(in, out, l.stride, s);
+        launch_reorg(in, out, l.stride, s, d.reorg_table);
         break;
     case ROUTE:
         if (l.n > 1) {

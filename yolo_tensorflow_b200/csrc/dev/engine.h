@@ -28,6 +28,7 @@ struct DevLayer {
     bool pool_fused;           // stem conv whose store warp also performs the following [maxpool] 2/2 (its own output is not written)
     bool pool_away;            // [maxpool] performed inside the stem kernel
     bool block_head;           // 1x1 conv computed inside the following 3x3's kernel (fused residual block): launches nothing
+    int *reorg_table;          // [reorg]: the per-image permutation as (source, destination) offset pairs on the device
     std::string kernel;
 };
 

@@ -173,8 +173,75 @@ __global__ void region_forward_kernel(const T *__restrict__ in, float *__restric
     }
 }
 
+
+// Tiled variant for heads whose entries fit shared memory (YOLOv2: 85 per box): a CTA takes 32 consecutive cells of one (image,
+// anchor); each warp reads its boxes' logits coalesced (lanes over entries), the activations go into a [entries][32 cells] tile,
+// and the tile leaves with lanes over CELLS, i.e. as full 128-byte lines of the darknet layout.  (ncu, round 2: thread-per-box
+// reads were uncoalesced, 69 us for 37 MB; warp-per-box with direct stores wrote one sector per lane, 148 us.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+region_forward_tiled_kernel(const T *__restrict__ in, float *__restrict__ out, int N, int HW, int ld, int anchors, int classes, int coords,
+                            const int *__restrict__ gsize, const int *__restrict__ goff, int groups, int softmax, int tiles_per_plane)
+{
+    extern __shared__ float tile[];                              // [entries][33]
+    const int entries = coords + 1 + classes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)N * anchors * tiles_per_plane;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        const int tl = (int)(t % tiles_per_plane), a = (int)((t / tiles_per_plane) % anchors), n = (int)(t / ((long long)tiles_per_plane * anchors));
+        const int loc0 = tl * 32, cells = (HW - loc0) < 32 ? (HW - loc0) : 32;
+        for (int b = warp; b < cells; b += 8) {
+            const T *src = in + ((size_t)n * HW + loc0 + b) * ld + a * entries;
+            for (int e = lane; e <= coords; e += 32) {
+                const float v = Elem<T>::load(src + e);
+                tile[e * 33 + b] = (e < 2 || e == coords) ? logistic_ref(v) : v;
+            }
+            if (!softmax) {
+                for (int j = lane; j < classes; j += 32) tile[(coords + 1 + j) * 33 + b] = logistic_ref(Elem<T>::load(src + coords + 1 + j));
+                continue;
+            }
+            for (int g = 0; g < groups; ++g) {
+                const int off = coords + 1 + (gsize ? goff[g] : 0), sz = gsize ? gsize[g] : classes;
+                float largest = -FLT_MAX;
+                for (int j = lane; j < sz; j += 32) largest = fmaxf(largest, Elem<T>::load(src + off + j));
+                for (int o = 16; o; o >>= 1) largest = fmaxf(largest, __shfl_xor_sync(0xffffffffu, largest, o));
+                float sum = 0.f;
+                for (int j = lane; j < sz; j += 32) {
+                    const float e = (float)exp((double)(Elem<T>::load(src + off + j) - largest));
+                    sum += e;
+                    tile[(off + j) * 33 + b] = e;
+                }
+                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                for (int j = lane; j < sz; j += 32) tile[(off + j) * 33 + b] /= sum;
+            }
+        }
+        __syncthreads();
+        float *dst = out + ((size_t)n * anchors + a) * entries * HW + loc0;
+        for (int e = warp; e < entries; e += 8)
+            if (lane < cells) dst[(size_t)e * HW + lane] = tile[e * 33 + lane];
+        __syncthreads();
+    }
+}
+
+template <typename T>
+static bool region_forward_tiled(TView in, float *out, int anchors, int classes, int coords, const int *gsize, const int *goff, int groups,
+                                 int softmax, cudaStream_t s)
+{
+    const int entries = coords + 1 + classes;
+    const size_t smem = (size_t)entries * 33 * sizeof(float);
+    if (smem > 48 * 1024) return false;                          // YOLO9000-sized heads keep the direct-store kernel
+    const int HW = in.h * in.w, tiles = (HW + 31) / 32;
+    long long total = (long long)in.n * anchors * tiles;
+    int grid = (int)(total < 148 * 8 ? total : 148 * 8);
+    region_forward_tiled_kernel<T><<<grid, 256, smem, s>>>((const T *)in.p, out, in.n, HW, in.ld, anchors, classes, coords, gsize, goff, groups, softmax, tiles);
+    B200_LAUNCHED();
+    return true;
+}
+
 void launch_region_tree_forward(TView in, float *out, int anchors, int classes, int coords, const int *gsize, const int *goff, int groups, cudaStream_t s)
 {
+    if (in.dtype == DT_F32 ? region_forward_tiled<float>(in, out, anchors, classes, coords, gsize, goff, groups, 1, s)
+                           : region_forward_tiled<bf16>(in, out, anchors, classes, coords, gsize, goff, groups, 1, s)) return;
     const int HW = in.h * in.w;
     const long long boxes = (long long)in.n * anchors * HW;
     int grid = (int)((boxes + 7) / 8);
@@ -184,11 +251,11 @@ void launch_region_tree_forward(TView in, float *out, int anchors, int classes, 
     B200_LAUNCHED();
 }
 
-// plain [region] head (YOLOv2): one warp per box — the box's logits are contiguous in the NHWC input, so the reads coalesce and
-// 54 080 warps (416x416 b64) are in flight instead of 54 080 threads (ncu, round 2: the thread-per-box version took 69 us for
-// 37 MB); max and sum of the softmax are warp reductions
+// plain [region] head (YOLOv2): the tiled kernel above; the direct-store warp-per-box kernel only for heads too wide for a tile
 void launch_region_forward(TView in, float *out, int anchors, int classes, int coords, int softmax, cudaStream_t s)
 {
+    if (in.dtype == DT_F32 ? region_forward_tiled<float>(in, out, anchors, classes, coords, nullptr, nullptr, 1, softmax, s)
+                           : region_forward_tiled<bf16>(in, out, anchors, classes, coords, nullptr, nullptr, 1, softmax, s)) return;
     const int HW = in.h * in.w;
     const long long boxes = (long long)in.n * anchors * HW;
     int grid = (int)((boxes + 7) / 8);

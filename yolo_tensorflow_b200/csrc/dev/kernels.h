@@ -24,7 +24,8 @@ void launch_maxpool(TView in, TView out, int size, int stride, int pad, cudaStre
 void launch_upsample(TView in, TView out, int stride, float scale, cudaStream_t s);
 void launch_shortcut(TView in, TView add, TView out, float alpha, float beta, int act, cudaStream_t s);
 void launch_copy_channels(TView in, TView out, cudaStream_t s);               // out view already offset to its slice
-void launch_reorg(TView in, TView out, int stride, cudaStream_t s);
+void launch_reorg(TView in, TView out, int stride, cudaStream_t s, const int *table_dev = nullptr);   // table_dev: reorg_build_table's pairs on the device (optional)
+void reorg_build_table(int h, int w, int c, int oh, int ow, int oc, int ldo, int s, int *table_xy);   // host: 2 ints per output element
 
 // ---- convolution family ------------------------------------------------------------------------------
 struct ConvParams {

@@ -83,12 +83,6 @@ struct NmsWork {
     unsigned *mask;    // [m][words]
 };
 
-__device__ __forceinline__ size_t work_bytes(int m)
-{
-    size_t words = (m + 31) / 32;
-    return (size_t)m * (4 + 4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
-}
-
 __device__ __forceinline__ NmsWork carve(unsigned char *base, int m)
 {
     NmsWork w;
@@ -112,8 +106,7 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int warp_totals[NMS_THREADS / 32];
-    // removed bitset for up to 32768 candidates lives at the front of dynamic smem (4 KB)
-    unsigned *removed = (unsigned *)smem;
+    unsigned *removed = (unsigned *)smem;       // bitset of suppressed survivors (see below)
     unsigned char *smem_work = smem + 4096;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -140,21 +133,27 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
         int m = cls_count[unit];
         if (m <= small_limit) continue;
         if (m <= 1) continue;                                   // nothing can be suppressed
-        unsigned char *base = (m <= NMS_SMEM_M) ? smem_work : slab + (size_t)blockIdx.x * slab_bytes;
-        if (m > NMS_SMEM_M && work_bytes(m) > slab_bytes) {     // cannot happen: host sizes the slab from max_count
-            if (threadIdx.x == 0) printf("b200-darknet: nms slab too small (m=%d)\n", m);
-            __trap();
-        }
-        NmsWork wk = carve(base, m);
-        // slab path: only the bit-matrix has to live in HBM; scores / indices / sorted boxes stay in shared memory when they
-        // fit (32 bytes per survivor), which turns the m^2 box reads of the IoU pass into LDS instead of L1/L2 traffic
-        size_t lists_bytes = 0;
-        if (m > NMS_SMEM_M && (size_t)m * 32 + 64 + 8192 <= (size_t)host_smem_work_bytes) {
-            NmsWork in_smem = carve(smem_work, m);
-            wk.sbox = in_smem.sbox; wk.score = in_smem.score; wk.src = in_smem.src; wk.order = in_smem.order; wk.area = in_smem.area;
-            lists_bytes = ((size_t)m * 32 + 64 + 15) & ~(size_t)15;
-        }
+        // m <= NMS_SMEM_M: lists AND the whole IoU bit-matrix live in shared memory.  Larger units keep only the lists — in shared
+        // memory when they fit (32 bytes per survivor), else in this CTA's HBM slab — and never materialise the m x m matrix:
+        // its rows are produced a chunk at a time into a double-buffered shared-memory stage (below).  The removed bitset sits
+        // at the front of dynamic smem (4 KB = 32768 survivors) and moves behind the lists in the slab for anything larger.
         const int words = (m + 31) / 32;
+        unsigned char *slab_cta = slab + (size_t)blockIdx.x * slab_bytes;
+        size_t lists_bytes = 0;                                  // bytes of the smem work area taken by the lists (chunked path)
+        NmsWork wk;
+        if (m <= NMS_SMEM_M) wk = carve(smem_work, m);
+        else if ((size_t)m * 32 + 64 + 16384 <= (size_t)host_smem_work_bytes) {
+            wk = carve(smem_work, m);
+            lists_bytes = ((size_t)m * 32 + 64 + 15) & ~(size_t)15;
+        } else {
+            if ((size_t)m * 32 + 64 + (size_t)words * 4 > slab_bytes) {     // cannot happen: host sizes the slab from max_count
+                if (threadIdx.x == 0) printf("b200-darknet: nms slab too small (m=%d)\n", m);
+                __trap();
+            }
+            wk = carve(slab_cta, m);
+        }
+        if (m > 32768) removed = (unsigned *)(slab_cta + (((size_t)m * 32 + 64 + 15) & ~(size_t)15));
+        else removed = (unsigned *)smem;
 
         // ---- pass B: ordered gather
         int written = 0;
@@ -190,43 +189,34 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
         for (int w = threadIdx.x; w < words; w += NMS_THREADS) removed[w] = 0u;
         __syncthreads();
 
-        // ---- IoU bit-matrix: word (i, wj) covers j in [32*wj, 32*wj+32), only j > i matters.  One warp per word: lane b
-        // tests the pair (i, 32*wj + b) — box i is a broadcast read, boxes j are 32 consecutive entries (no bank conflicts; a
-        // thread walking its own 32 j's made every lane of a warp hit the same bank) — and a ballot assembles the word.  A warp
-        // takes 32 consecutive words at a time so that the store is one coalesced line.
-        {
-            const int total_words = m * words;                              // m <= 32768, words <= 1024: fits an int
-            const int nwarps = NMS_THREADS / 32;
-            for (int t0 = warp * 32; t0 < total_words; t0 += nwarps * 32) {
+        // ---- IoU bit-matrix + greedy scan.  Word (i, wj) of the matrix covers j in [32*wj, 32*wj+32); only j > i matters.  A word is
+        // produced by one WARP: lane b tests the pair (i, 32*wj + b) — box i is a broadcast read, boxes j are 32 consecutive
+        // entries (no bank conflicts) — and a ballot assembles it.  The scan walks the rows in order, OR-ing the row of every
+        // still-alive box into the removed set.
+        auto pair_word = [&](int i, int wj) -> unsigned {
+            const int j = wj * 32 + lane;
+            bool sup = false;
+            if (j > i && j < m) {
+                const float4 av = wk.sbox[i], bv = wk.sbox[j];
+                sup = suppresses_c(NmsBox{av.x, av.y, av.z, av.w}, wk.area[i], NmsBox{bv.x, bv.y, bv.z, bv.w}, wk.area[j], thresh);
+            }
+            return __ballot_sync(0xffffffffu, sup);
+        };
+        if (m <= NMS_SMEM_M) {
+            // whole matrix in shared memory (a warp takes 32 consecutive words at a time so that the store is one line), then the
+            // scan with the removed set in one register per lane (words <= 16) and row i+1 fetched while row i is decided
+            const int total_words = m * words;
+            for (int t0 = warp * 32; t0 < total_words; t0 += (NMS_THREADS / 32) * 32) {
                 unsigned mine = 0u;
                 const int kmax = (total_words - t0) < 32 ? (total_words - t0) : 32;
-#pragma unroll 4
                 for (int k = 0; k < kmax; ++k) {
-                    const int t = t0 + k;
-                    const int i = t / words, wj = t % words;
-                    unsigned bits = 0u;
-                    if (wj * 32 + 31 > i) {                                  // warp-uniform
-                        const int j = wj * 32 + lane;
-                        bool sup = false;
-                        if (j > i && j < m) {
-                            const float4 av = wk.sbox[i], bv = wk.sbox[j];
-                            sup = suppresses_c(NmsBox{av.x, av.y, av.z, av.w}, wk.area[i], NmsBox{bv.x, bv.y, bv.z, bv.w}, wk.area[j], thresh);
-                        }
-                        bits = __ballot_sync(0xffffffffu, sup);
-                    }
+                    const int t = t0 + k, i = t / words, wj = t % words;
+                    const unsigned bits = (wj * 32 + 31 > i) ? pair_word(i, wj) : 0u;       // warp-uniform condition
                     if (lane == k) mine = bits;
                 }
                 if (lane < kmax) wk.mask[t0 + lane] = mine;
             }
-        }
-        __syncthreads();
-
-        // ---- greedy scan.  Shared-memory masks: warp 0 walks the rows directly.  HBM-slab masks (m > NMS_SMEM_M): rows are
-        // staged through shared memory a chunk at a time by the whole CTA (one L2 round trip per chunk instead of one
-        // per row; the dependent walk inside a chunk then runs at shared-memory latency).
-        if (m <= NMS_SMEM_M) {
-            // words <= 16: the removed set lives in one register per lane, row i+1 is fetched while row i is decided, so a step of
-            // the (inherently serial) scan costs a shuffle, a test and an OR instead of a shared-memory round trip
+            __syncthreads();
             if (warp == 0) {
                 unsigned rem = 0u;
                 unsigned nxt = lane < words ? wk.mask[lane] : 0u;
@@ -239,59 +229,64 @@ nms_kernel(const float *__restrict__ box, float *__restrict__ score, const float
                 if (lane < words) removed[lane] = rem;
             }
             __syncthreads();
-        } else if (words <= 32) {
-            // the same register-resident scan for up to 1024 survivors, rows staged from the HBM slab a chunk at a time
-            unsigned *stage = (unsigned *)(smem_work + lists_bytes);
-            const int stage_words = (int)(((size_t)host_smem_work_bytes - lists_bytes) / 4);
-            int rows_per_chunk = stage_words / words;
-            if (rows_per_chunk > 128) rows_per_chunk = 128;
-            if (rows_per_chunk < 1) rows_per_chunk = 1;
-            unsigned rem = 0u;                                            // meaningful in warp 0 only
-            for (int i0 = 0; i0 < m; i0 += rows_per_chunk) {
-                const int rows = (m - i0) < rows_per_chunk ? (m - i0) : rows_per_chunk;
-                for (int t = threadIdx.x; t < rows * words; t += NMS_THREADS) stage[t] = wk.mask[(size_t)i0 * words + t];
-                __syncthreads();
-                if (warp == 0) {
-                    unsigned nxt = lane < words ? stage[lane] : 0u;
-                    for (int rr = 0; rr < rows; ++rr) {
-                        const int i = i0 + rr;
-                        const unsigned cur = nxt;
-                        if (rr + 1 < rows) nxt = lane < words ? stage[(rr + 1) * words + lane] : 0u;
-                        const unsigned r = __shfl_sync(0xffffffffu, rem, i >> 5);
-                        if (!((r >> (i & 31)) & 1u)) rem |= cur;
-                    }
-                }
-                __syncthreads();
-            }
-            if (warp == 0 && lane < words) removed[lane] = rem;
-            __syncthreads();
         } else {
-            unsigned *stage = (unsigned *)(smem_work + lists_bytes);  // what is left of the smem work area in the slab path
-            const int stage_words = (int)(((size_t)host_smem_work_bytes - lists_bytes) / 4);
-            int rows_per_chunk = stage_words / words;
-            if (rows_per_chunk > 64) rows_per_chunk = 64;
-            if (rows_per_chunk < 1) rows_per_chunk = 1;
-            for (int i0 = 0; i0 < m; i0 += rows_per_chunk) {
-                const int rows = (m - i0) < rows_per_chunk ? (m - i0) : rows_per_chunk;
-                const int w_lo = i0 >> 5;                            // words left of the diagonal are never read
-                const int span = words - w_lo;
-                for (int t = threadIdx.x; t < rows * span; t += NMS_THREADS) {
-                    int rr = t / span, w = w_lo + t % span;
-                    stage[rr * span + (w - w_lo)] = wk.mask[(size_t)(i0 + rr) * words + w];
+            // chunked: R rows of the matrix at a time, in one of two shared-memory buffers; while warp 0 scans chunk c, warps 1-31
+            // already produce chunk c+1 (the rows do not depend on the scan), so the serial scan hides behind the pair tests and
+            // no m x m slab exists (round 1 sized one from the anchor count: 19 GB at 608 x 608)
+            unsigned *stage = (unsigned *)(smem_work + lists_bytes);
+            const int half_words = (int)(((size_t)host_smem_work_bytes - lists_bytes) / 8);     // words per buffer
+            int R = half_words / words;
+            if (R > 256) R = 256;
+            if (R < 1) {                                            // a single row does not fit (m > ~300k): not reachable with cap checks on the host
+                if (threadIdx.x == 0) printf("b200-darknet: nms unit too large (m=%d)\n", m);
+                __trap();
+            }
+            const int nchunks = (m + R - 1) / R;
+            auto produce = [&](int c, int first_warp) {             // rows [c*R, c*R+rows) x words [w_lo, words) -> buffer c & 1
+                const int i0 = c * R, rows = (m - i0) < R ? (m - i0) : R;
+                const int w_lo = i0 >> 5, span = words - w_lo;
+                unsigned *buf = stage + (size_t)(c & 1) * half_words;
+                const int nw = NMS_THREADS / 32 - first_warp;
+                for (int t = warp - first_warp; t < rows * span; t += nw) {
+                    const int rr = t / span, wj = w_lo + t % span, i = i0 + rr;
+                    const unsigned bits = (wj * 32 + 31 > i) ? pair_word(i, wj) : 0u;
+                    if (lane == 0) buf[rr * span + (wj - w_lo)] = bits;
                 }
-                __syncthreads();
-                if (warp == 0) {
-                    for (int rr = 0; rr < rows; ++rr) {
-                        const int i = i0 + rr;
-                        unsigned r = removed[i >> 5];
-                        if (!((r >> (i & 31)) & 1u)) {
-                            for (int w = (i >> 5) + lane; w < words; w += 32) removed[w] |= stage[rr * span + (w - w_lo)];
+            };
+            for (int w = threadIdx.x; w < words; w += NMS_THREADS) removed[w] = 0u;
+            produce(0, 0);
+            __syncthreads();
+            unsigned rem = 0u;                                      // words <= 32: removed set in registers of warp 0
+            for (int c = 0; c < nchunks; ++c) {
+                if (warp > 0) {
+                    if (c + 1 < nchunks) produce(c + 1, 1);
+                } else {
+                    const int i0 = c * R, rows = (m - i0) < R ? (m - i0) : R;
+                    const int w_lo = i0 >> 5, span = words - w_lo;
+                    const unsigned *buf = stage + (size_t)(c & 1) * half_words;
+                    if (words <= 32) {
+                        unsigned nxt = (lane >= w_lo && lane < words) ? buf[lane - w_lo] : 0u;
+                        for (int rr = 0; rr < rows; ++rr) {
+                            const int i = i0 + rr;
+                            const unsigned cur = nxt;
+                            if (rr + 1 < rows) nxt = (lane >= w_lo && lane < words) ? buf[(rr + 1) * span + (lane - w_lo)] : 0u;
+                            const unsigned r = __shfl_sync(0xffffffffu, rem, i >> 5);
+                            if (!((r >> (i & 31)) & 1u)) rem |= cur;
                         }
-                        __syncwarp();
+                    } else {
+                        for (int rr = 0; rr < rows; ++rr) {
+                            const int i = i0 + rr;
+                            const unsigned r = removed[i >> 5];
+                            if (!((r >> (i & 31)) & 1u))
+                                for (int w = (i >> 5) + lane; w < words; w += 32) removed[w] |= buf[rr * span + (w - w_lo)];
+                            __syncwarp();
+                        }
                     }
                 }
                 __syncthreads();
             }
+            if (words <= 32 && warp == 0 && lane < words) removed[lane] = rem;
+            __syncthreads();
         }
 
         // ---- write back
@@ -424,9 +419,20 @@ static size_t host_work_bytes(int m)
     return (size_t)m * (4 + 4 + 4 + 4 + 16) + (size_t)m * words * 4 + 64;
 }
 
+// per-CTA HBM slab of the general kernel: the LISTS of a unit too large for shared memory (32 bytes per survivor, > 1024
+// survivors) and, beyond 32768 survivors, its removed bitset.  The IoU matrix is never materialised (chunked in shared memory),
+// so the slab is linear in the anchor count: 0.73 MB per CTA at 608 x 608 (22 743 anchors), 216 MB for 296 CTAs.
+static size_t slab_bytes_for(int max_count)
+{
+    if (max_count <= 1024) return 0;
+    const size_t lists = ((size_t)max_count * 32 + 64 + 15) & ~(size_t)15;
+    const size_t bitset = ((size_t)(max_count + 31) / 32) * 4;
+    return (lists + bitset + 255) / 256 * 256;
+}
+
 static void ensure_scratch(NmsScratch *sc, int max_count, int ctas)
 {
-    size_t need = max_count > NMS_SMEM_M ? (host_work_bytes(max_count) + 255) / 256 * 256 : 0;
+    const size_t need = slab_bytes_for(max_count);
     if (need * ctas > sc->words_per_cta * (size_t)sc->ctas || (need && !sc->mask)) {
         if (sc->mask) B200_CHECK(cudaFree(sc->mask));
         B200_CHECK(cudaMalloc((void **)&sc->mask, need * ctas));
@@ -438,7 +444,6 @@ static void ensure_scratch(NmsScratch *sc, int max_count, int ctas)
 static void run_nms(const float *box, float *score, const float *obj, const int *count, int images, int cap, int classes,
                     int stride, float thresh, int max_count, NmsScratch *scratch, unsigned char *supp, int *cls_count, cudaStream_t s)
 {
-    if (max_count > 32768) { fprintf(stderr, "b200-darknet: nms supports at most 32768 candidates per image\n"); abort(); }
     int units = images * classes;
     if (units < 1) return;
     B200_CHECK(cudaMemsetAsync(cls_count, 0, ((size_t)units + 1) * sizeof(int), s));      // class counts + the work counter
