@@ -1,13 +1,12 @@
 #!/usr/bin/env python3
 """Fixed versus per-tile cost of one tcgen05 convolution launch: a single layer (stem + the layer under test) timed at
-growing batch sizes, i.e. a growing number of tile waves, with CUDA events around 50 back-to-back launches of the layer.
+growing batch sizes, i.e. a growing number of tile waves, with CUDA events around the layer (b200_profile_layers, 20 passes).
 T(batch) = fixed + per_wave * waves: the intercept is what every one of the 74 launches of a YOLOv3 step pays for pipeline
 fill, drain and the kernel boundary.  Usage: launch_anatomy.py"""
 import ctypes, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yolo_tensorflow_b200 import synth, darknet as dn
-import torch
 
 WORK = "/tmp/b200_anatomy"
 os.makedirs(WORK, exist_ok=True)
@@ -41,13 +40,8 @@ for name, hw, c, filters, size in CASES:
         finally:
             os.dup2(fd, 2); os.close(fd); os.close(dv)
         net.predict(synth.make_images(batch, 3, hw, hw, 3))
-        stream = torch.cuda.ExternalStream(net.stream_ptr())
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        lib = dn.lib
-        # b200_run_layers synchronises after every call: use the profiler entry point's building block instead — enqueue the layer
-        # 50 times through run_layers' asynchronous sibling (profile_layers runs whole passes); here: whole 2-layer passes minus the stem
         ms = net.profile_layers(20)
-        plan = lib.b200_layer_plan(net.ptr, 1).decode()
+        plan = dn.lib.b200_layer_plan(net.ptr, 1).decode()
         flops = 2.0 * filters * size * size * c * hw * hw * batch
         rows.append((batch, float(ms[1]) * 1e3, flops / (float(ms[1]) * 1e-3) / 1e12, plan.split("smem")[0][-70:]))
         net.close()
