@@ -1,5 +1,5 @@
 import os, sys, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yolo_tensorflow_b200 import synth, darknet as dn
 work = "/tmp/b200_san"; os.makedirs(work, exist_ok=True)
 for model, size, batch in (("yolov3", 160, 2), ("yolov3-tiny", 96, 3), ("yolov2", 160, 2)):
@@ -19,3 +19,45 @@ for model, size, batch in (("yolov3", 160, 2), ("yolov3-tiny", 96, 3), ("yolov2"
     n = net.validate_images(imgs, ["im_%d.jpg" % i for i in range(len(imgs))], "coco", tempfile.mkdtemp(), thresh=.3)
     print(" validate driver (pipelined, short last batch)", n)
     net.close()
+
+# ---- round 2: the reference-API extras and the restructured NMS -------------------------------------------------------------
+import ctypes
+# batch == 2 flip-average through get_network_boxes; get_network_boxes after the host rewrote l.output
+cfg = synth.make_cfg("yolov3-tiny", work, batch=2, width=105, height=105)
+net = dn.Network(cfg, os.path.join(work, "yolov3-tiny.weights"), precision=dn.PREC_FP32)
+x0 = synth.make_images(1, 3, 105, 105, 5)
+net.predict(np.ascontiguousarray(np.concatenate([x0, x0[..., ::-1]])))
+num = ctypes.c_int(0)
+dets = dn.get_network_boxes(net.ptr, 105, 105, .2, .5, None, 1, ctypes.byref(num))
+dn.do_nms_sort(dets, num.value, 80, .45)
+dn.free_detections(dets, num.value)
+print("flip-average", num.value)
+net.close()
+# YOLO9000-style head: softmax per sibling group, hierarchy_predictions, top prediction and map
+tree = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "wordtree_240.tree")
+cfg = synth.make_tree_cfg(work, tree, batch=2, size=32)
+w9 = os.path.join(work, "y9k.weights"); synth.write_weights(cfg, w9, seed=0, damp_heads=True)
+net = dn.Network(cfg, w9, precision=dn.PREC_BF16)
+net.predict(synth.make_images(2, 3, 32, 32, 6))
+cmap = (np.arange(200) % 240).astype(np.int32)
+for mp in (None, cmap.ctypes.data_as(ctypes.POINTER(ctypes.c_int))):
+    dets = dn.get_network_boxes(net.ptr, 32, 32, .05, .5, mp, 1, ctypes.byref(num))
+    dn.do_nms_sort(dets, num.value, 240, .45)
+    dn.free_detections(dets, num.value)
+print("wordtree", num.value)
+net.close()
+# NMS: every path of the general kernel — matrix in shared memory (<= 512 survivors), lists in shared memory + chunked rows
+# (<= 1024), lists in the HBM slab, more than 32 words per row, more than 32768 survivors (removed set in the slab)
+rng = np.random.default_rng(1)
+for n, classes in ((300, 3), (513, 1), (1025, 1), (2049, 2), (5000, 1), (33000, 1)):
+    boxes = np.concatenate([rng.random((n, 2)), rng.random((n, 2)) * (.05 if n > 4000 else .3) + .01], axis=1).astype(np.float32)
+    probs = (rng.random((n, classes)) + .01).astype(np.float32)
+    out = dn.nms_sort_arrays(boxes, probs, .45)
+    print("nms", n, classes, int((out > 0).sum()))
+# resize_network + reorg table + tiled region head
+cfg = synth.make_cfg("yolov2", work, batch=2, width=160, height=160)
+net = dn.Network(cfg, os.path.join(work, "yolov2.weights"), precision=dn.PREC_BF16)
+net.resize(224, 192)
+rec, counts = net.detect_batch(synth.make_images(2, 3, 192, 224, 7), 224, 192, .3, .45)
+print("resized yolov2", len(rec))
+net.close()

@@ -476,7 +476,9 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
         p->grid = 2 * (pair_tiles < 74 ? pair_tiles : 74);
         a.vtiles = pair_tiles;
         // tail splitting: when the last wave would keep at most half of the 74 pairs busy, its tiles are cut into 2 or 4
-        // filter slices (>= 64 filters each) so that all pairs share it: e.g. 184 tiles = 2 waves + 36 -> 2 waves + 72 halves
+        // filter slices (>= 64 filters each) so that all pairs share it: e.g. 184 tiles = 2 waves + 36 -> 2 waves + 72 halves.
+        // MEASURED (round 2): splitting fuller tails does not pay — 338 tiles = 4 waves + 42 cut into 168 quarters (0.75 of a
+        // wave by the arithmetic) ran at 0.099 ms against 0.079 unsplit: every slice re-reads its A tile and pays its own fill.
         const int rem = pair_tiles > 74 ? pair_tiles % 74 : 0;
         if (a.ring && rem > 0 && 2 * rem <= 74 && !getenv("B200_NO_TAIL_SPLIT")) {
             int sp = (4 * rem <= 74 && a.block_n % 256 == 0) ? 4 : 2;
