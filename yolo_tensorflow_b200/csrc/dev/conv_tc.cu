@@ -33,6 +33,20 @@
 // convolutional_layer.c:325).
 #include "conv_tc_plan.h"
 
+// im2col-mode A tiles: tile m covers output pixels [128 m, 128 m + 128) in (n, oy, ox) order; the load starts at the input
+// position of the first pixel's tap origin.  A phantom tile (second CTA of an odd pair count) re-reads the last real one.
+__device__ __forceinline__ void im2col_origin(const ConvTcArgs &args, int m_tile, int &w0, int &h0, int &n0)
+{
+    if (m_tile >= args.m_tiles) m_tile = args.m_tiles - 1;
+    const int per_image = args.OH * args.OW;
+    const int p0 = m_tile * 128;
+    n0 = p0 / per_image;
+    const int r = p0 - n0 * per_image;
+    const int oy = r / args.OW;
+    h0 = oy * args.stride - args.pad;
+    w0 = (r - oy * args.OW) * args.stride - args.pad;
+}
+
 template <int BLOCK_K, typename OutT, bool RING>      // RING: ring epilogue roles (384 threads); else the serial epilogue (192)
 __global__ void __launch_bounds__(RING ? kTcRingThreads : kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
@@ -99,13 +113,15 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs args)
                 if (args.mode == 1) {
                     int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
                     ox0 = tx * args.TW; oy0 = ty * args.TH; n0 = tn * args.TN;
-                }
+                } else if (args.im2col) im2col_origin(args, m_tile, ox0, oy0, n0);
                 for (int kb = 0; kb < args.num_kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], tx_bytes);
                     const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
                     void *dstA = sA + (size_t)stage * A_BYTES;
-                    if (args.mode == 0) {
+                    if (args.im2col) {
+                        tma_load_im2col_4d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, ox0, oy0, n0, tap % args.size, tap / args.size);
+                    } else if (args.mode == 0) {
                         tma_load_2d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, m_tile * 128);
                     } else {
                         const int ky = tap / args.size, kx = tap - ky * args.size;
@@ -244,13 +260,15 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                 if (args.mode == 1) {
                     int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
                     ox0 = tx * args.TW; oy0 = ty * args.TH; n0 = tn * args.TN;      // a phantom last tile lands past the batch: TMA zero-fills
-                }
+                } else if (args.im2col) im2col_origin(args, m_tile, ox0, oy0, n0);
                 for (int kb = 0; kb < args.num_kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (leader) mbar_expect_tx(&full[stage], tx_bytes);
                     const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
                     void *dstA = sA + (size_t)stage * A_BYTES;
-                    if (args.mode == 0) {
+                    if (args.im2col) {
+                        tma2_load_im2col_4d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, ox0, oy0, n0, tap % args.size, tap / args.size);
+                    } else if (args.mode == 0) {
                         tma2_load_2d(&maps.a[0], dstA, &full[stage], cb * BLOCK_K, m_tile * 128);
                     } else {
                         const int ky = tap / args.size, kx = tap - ky * args.size;

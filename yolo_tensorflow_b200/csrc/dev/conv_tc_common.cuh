@@ -11,7 +11,7 @@
 // kernel arguments
 // ---------------------------------------------------------------------------------------------------
 struct alignas(64) ConvTcMaps {
-    CUtensorMap a[4];        // mode 0: a[0] dense [pixels][C]; mode 1: a[py*2+px] parity-phase views (stride 1 uses a[0])
+    CUtensorMap a[4];        // mode 0: a[0] dense [pixels][C] (or the im2col-mode map of the NHWC input); mode 1: a[py*2+px] parity-phase views (stride 1 uses a[0])
     CUtensorMap b;           // weights [cout_pad][K]
     CUtensorMap c;           // output tile store (staged epilogue): same pixel-tile geometry as A, 64-channel boxes
     CUtensorMap r;           // residual tile load (fused shortcut), same geometry
@@ -20,7 +20,8 @@ struct alignas(64) ConvTcMaps {
 };
 
 struct ConvTcArgs {
-    int mode;                // 0 = dense rows (1x1), 1 = spatial tiles
+    int mode;                // 0 = dense rows (1x1, or any filter size through TMA im2col-mode loads), 1 = spatial tiles
+    int im2col;              // mode 0 with size > 1: A tiles = 128 consecutive output pixels gathered per tap by an im2col-mode TMA load
     int batch, OH, OW, cout_pad, ldo;
     int size, stride, pad, cin_blocks;
     int TW, TH, TN, tiles_x, tiles_y;

@@ -22,6 +22,23 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const int *, const int *, cuuint32_t, cuuint32_t, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn encode_im2col_fn()
+{
+    static EncodeIm2colFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        B200_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { fprintf(stderr, "b200-darknet: cuTensorMapEncodeIm2col unavailable\n"); abort(); }
+        fn = (EncodeIm2colFn)p;
+    }
+    return fn;
+}
+
 static CUtensorMapSwizzle swizzle_for(int block_k)
 {
     return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -37,6 +54,26 @@ static void encode(CUtensorMap *map, void *base, int rank, const cuuint64_t *dim
     if (r != CUDA_SUCCESS) {
         fprintf(stderr, "b200-darknet: cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu box %u %u\n", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        abort();
+    }
+}
+
+// im2col-mode view of an NHWC bf16 activation for a size x size convolution (stride, pad as in convolutional_layer.c:325-335):
+// one load gathers `block_k` channels of 128 consecutive output pixels for one filter tap.  The bounding box [-pad, W-1+pad-(size-1)]
+// holds the tap origins of all output positions; the traversal stride is the convolution's.
+static void encode_im2col(CUtensorMap *map, const TView &in, int size, int stride, int pad, int block_k)
+{
+    const cuuint64_t esz = 2;
+    cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+    cuuint64_t strides[3] = {(cuuint64_t)in.ld * esz, (cuuint64_t)in.w * in.ld * esz, (cuuint64_t)in.h * in.w * in.ld * esz};
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (size - 1), pad - (size - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = encode_im2col_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in.p, dims, strides, lower, upper, (cuuint32_t)block_k, 128, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "b200-darknet: cuTensorMapEncodeIm2col failed (%d) %dx%dx%dx%d size %d stride %d pad %d\n", (int)r, in.n, in.h, in.w, in.c, size, stride, pad);
         abort();
     }
 }
@@ -373,6 +410,20 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
             }
         }
     }
+    // ---- TMA im2col mode: every other filter size > 1 --------------------------------------------------------------------
+    // The tile becomes ANY 128 consecutive output pixels (no rectangle has to divide the map: 13 x 13 maps lose no MMA rows,
+    // 85 instead of 91 tiles at batch 64), stride 2 needs no parity-phase views, and the output / residual tiles are the dense
+    // 2-D boxes of the 1x1 layers.  A fused upsample and the unshared (local) layers keep their spatial tiles.
+    if (a.mode == 1 && !local && !up_out && !getenv("B200_NO_IM2COL") && cp.pad < 128 && cp.size - 1 - cp.pad < 128 &&
+        (long long)out.h * out.w * in.n < (1LL << 31) - 256 && out.h == (in.h + 2 * cp.pad - cp.size) / cp.stride + 1 &&
+        out.w == (in.w + 2 * cp.pad - cp.size) / cp.stride + 1) {
+        a.mode = 0; a.im2col = 1;
+        a.TW = a.TH = a.TN = 0; a.tiles_x = a.tiles_y = 1;
+        a.a_rows = 128;
+        a.m_tiles = (int)((a.npix + 127) / 128);
+        memset(&p->maps.a, 0, sizeof p->maps.a);
+        encode_im2col(&p->maps.a[0], in, cp.size, cp.stride, cp.pad, block_k);
+    }
     // ---- epilogue staging / weight residency / CTA pairing -------------------------------------------------
     // staged epilogue (TMEM -> registers -> swizzled smem tile -> TMA store, residual TMA-loaded into the same tile) is used
     // where a shortcut is fused: the per-row residual reads of the direct epilogue are what made fused layers slow.
@@ -498,6 +549,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
              a.pair ? " PAIR(cta_group::2)" : (a.resident_b ? " residentB" : ""), a.res ? " +residual" : "");
 
     p->desc = buf;
+    if (a.im2col) p->desc += " im2colTMA";
     if (a.ring) p->desc += " ringEpilogue(" + std::to_string(a.c_bufs) + ")";
     else if (a.staged) p->desc += " stagedEpilogue";
     if (a.upsample) p->desc += " +upsample2x";

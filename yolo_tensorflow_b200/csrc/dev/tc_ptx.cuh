@@ -127,6 +127,20 @@ __device__ __forceinline__ void tma2_load_4d(const CUtensorMap *map, void *dst, 
     asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// ---- TMA im2col mode (cuTensorMapEncodeIm2col): `pixelsPerColumn` consecutive OUTPUT pixels of a convolution, starting at
+// the input position (w, h, n) of the first one's filter-tap origin and walking W, then H, then N inside the bounding box the
+// map was encoded with (traversal stride = convolution stride); {kx, ky} select the filter tap.  Positions outside the tensor
+// are zero-filled: im2col.c:16-39 (im2col_get_pixel returns 0 outside the image) performed by the copy engine.
+__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap *map, void *dst, uint64_t *bar, int c, int w, int h, int n, int kx, int ky)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)kx), "h"((uint16_t)ky) : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(const CUtensorMap *map, void *dst, uint64_t *bar, int c, int w, int h, int n, int kx, int ky)
+{
+    asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)kx), "h"((uint16_t)ky) : "memory");
+}
 __device__ __forceinline__ void tc2_commit_both(uint64_t *bar)      // arrives on `bar` in BOTH CTAs of the pair
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
