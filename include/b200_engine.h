@@ -36,6 +36,22 @@ void b200_set_conv_backend(network *net, int backend);
  * (network.c:505, yolo_layer.c:359-362: heads are valid host fp32 NCHW after every predict). */
 void b200_set_head_sync(network *net, int on);
 
+/* Flows (planned only when env B200_FLOW=1 is set while the network is parsed): runs of tcgen05 convolution layers executed by
+ * ONE persistent kernel in which a tile of layer n+1 starts as soon as the tiles of layer n it reads are stored, instead of at
+ * a kernel boundary (csrc/dev/conv_tc_flow.cu).  Results are bit-identical to one launch per layer; on a power-managed B200 it
+ * measured 1-3 % slower, which is why it is opt-in.  b200_set_flow(net, 0) runs a planned flow's layers
+ * one launch each.  b200_flow_desc: plan text of flow k and the first / last layer index it covers. */
+void b200_set_flow(network *net, int on);
+int  b200_flow_count(network *net);
+const char *b200_flow_desc(network *net, int k, int *first, int *last);
+/* profiling, 5 values: {ns the flows' TMA producers waited on dependencies, ns their residual loaders did, number of waits that
+ * blocked} summed over all launches since the previous call; under B200_FLOW_TRACE=1 also {SM clock cycles, ns} of the first
+ * flow's last launch (their ratio = the SM clock while it ran) */
+void b200_flow_stats(network *net, unsigned long long *out5);
+/* profiling (flows planned under B200_FLOW_TRACE=1 only, else returns 0): 5 values per item of flow k's last launch — device-clock
+ * stamps (ns) inputs complete, first operands landed, last MMA issued, tile stored, then pair | position in its list << 16 — and the first item number of each member layer */
+int  b200_flow_trace(network *net, int k, unsigned long long *out, int max_items, int *item0, int max_layers);
+
 /* ---- opaque engine, one per network -------------------------------------------------------------- */
 typedef struct b200_engine b200_engine;
 b200_engine *b200_engine_of(const network *net);

@@ -1188,3 +1188,55 @@ def test_python_wrapper_detect_on_ppm(dn, workdir, tmp_path):
     o2, p2 = P.do_nms_obj(pb, po, pp, .45)
     assert len(res) == int((p2 > 0).sum())
     dn.free_image(im); dn.free_image(boxed)
+
+
+# ---------------------------------------------------------------------------------------------------
+# flows (opt-in, B200_FLOW=1): runs of convolutions as one persistent kernel with tile-level dependencies
+# ---------------------------------------------------------------------------------------------------
+def open_net_with_flows(dn, model, batch, size, workdir):
+    os.environ["B200_FLOW"] = "1"
+    try:
+        return open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
+    finally:
+        os.environ.pop("B200_FLOW", None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,size,batch", [("yolov3", 416, 64), ("yolov3", 160, 3), ("yolov3", 608, 4), ("yolov2", 416, 8)])
+def test_flow_kernel_is_bit_identical_to_one_launch_per_layer(dn, model, size, batch, workdir):
+    """conv_tc_flow_kernel (a tile starts when the counters of the tiles it reads say so, not at a kernel boundary) against the
+    same layers launched one by one: every materialised layer output bit for bit, over several passes (a dependency missed once
+    in a while would show as a stale tile), and the fused detection path's records."""
+    net, cfg, wpath = open_net_with_flows(dn, model, batch, size, workdir)
+    flows = net.flows()
+    assert flows, "no flow planned"
+    if model == "yolov3":
+        assert max(b - a for a, b, _ in flows) >= 60                 # the Darknet-53 body from the 52x52 maps on is one flow
+    x = synth.make_images(batch, 3, size, size, 2024)
+    layers = [i for i in range(net.n) if net.kernel(i) not in NOT_MATERIALISED and net.layers[i]["type_name"] in ("CONVOLUTIONAL", "SHORTCUT", "YOLO", "REGION")]
+    net.set_flow(0); net.predict(x)
+    ref = {i: net.layer_output(i).copy() for i in layers}
+    rec_ref, _ = net.detect_batch(x, size, size, .5, .45)
+    net.set_flow(1)
+    for p in range(3):
+        net.predict(x)
+        for i in layers:
+            assert np.array_equal(net.layer_output(i), ref[i]), (p, i, net.kernel(i))
+    rec, _ = net.detect_batch(x, size, size, .5, .45)
+    def ordered(r):                                                    # the collect kernel hands out record slots in arrival order
+        return r[np.lexsort((r["cls"], r["box_id"], r["image"]))].tobytes()
+    assert len(rec) == len(rec_ref) and ordered(rec) == ordered(rec_ref)
+    x2 = synth.make_images(batch, 3, size, size, 2025)                # a second input: counters carry on from the previous launches
+    net.predict(x2)
+    got = {i: net.layer_output(i).copy() for i in layers}
+    net.set_flow(0); net.predict(x2)
+    for i in layers:
+        assert np.array_equal(got[i], net.layer_output(i)), (i, net.kernel(i))
+    net.close()
+
+
+@pytest.mark.gpu
+def test_flows_are_opt_in(dn, workdir):
+    net, _, _ = open_net(dn, "yolov3", 2, 160, workdir, dn.PREC_BF16)
+    assert net.flows() == []
+    net.close()

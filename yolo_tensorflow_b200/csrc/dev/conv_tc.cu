@@ -263,6 +263,23 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                 } else if (args.im2col) im2col_origin(args, m_tile, ox0, oy0, n0);
                 for (int kb = 0; kb < args.num_kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
+#ifdef B200_EXPERIMENTS                            // make EXPERIMENTS=1: scripts/operand_traffic_probe.py
+                    if (args.exp) {               // timing experiment: skip operand loads once every stage holds something
+                        const bool warm = vt != pair_id || kb >= stages;
+                        const bool skip_b = warm && (args.exp & 1), skip_a = warm && (args.exp & 2);
+                        const uint32_t bytes = 2u * (uint32_t)((skip_a ? 0 : args.a_rows * BLOCK_K * 2) + (skip_b ? 0 : half_w * BLOCK_K * 2));
+                        if (leader) { if (bytes) mbar_expect_tx(&full[stage], bytes); else mbar_arrive(&full[stage]); }
+                        const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
+                        if (!skip_a) {
+                            if (args.im2col) tma2_load_im2col_4d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, ox0, oy0, n0, tap % args.size, tap / args.size);
+                            else if (args.mode == 0) tma2_load_2d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, m_tile * 128);
+                            else tma2_load_4d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, ox0 + tap % args.size - args.pad, oy0 + tap / args.size - args.pad, n0);
+                        }
+                        if (!skip_b) tma2_load_2d(bmap, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n + v.col_off + (int)rank * half_w);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+#endif
                     if (leader) mbar_expect_tx(&full[stage], tx_bytes);
                     const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
                     void *dstA = sA + (size_t)stage * A_BYTES;

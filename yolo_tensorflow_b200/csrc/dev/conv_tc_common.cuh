@@ -21,6 +21,8 @@ struct alignas(64) ConvTcMaps {
 
 struct ConvTcArgs {
     int mode;                // 0 = dense rows (1x1, or any filter size through TMA im2col-mode loads), 1 = spatial tiles
+    int exp;                 // TIMING EXPERIMENTS ONLY (env B200_EXP at plan time; results are wrong): bit 0 = the pair kernel re-uses stale weight
+                             // stages instead of loading them, bit 1 = stale activation stages (what does operand traffic cost?)
     int im2col;              // mode 0 with size > 1: A tiles = 128 consecutive output pixels gathered per tap by an im2col-mode TMA load
     int batch, OH, OW, cout_pad, ldo;
     int size, stride, pad, cin_blocks;

@@ -1,6 +1,7 @@
 // conv_tc_plan.cu — host side of the tcgen05 convolution family (overview in conv_tc.cu): TMA tensor maps, the per-layer planner
 // (tile shape, kernel variant, pipeline depth, epilogue, tail splitting) and the launch dispatch.
 #include "conv_tc_plan.h"
+#include <vector>
 
 // ---------------------------------------------------------------------------------------------------
 // host side: tensor maps + plan
@@ -231,6 +232,8 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     p->block_k = block_k;
     p->out_dtype = out.dtype;
     const int K = cp.size * cp.size * C;
+    p->in = in; p->out = out; p->res = residual ? *residual : TView{nullptr, 0, 0, 0, 0, 0, 0};
+    p->w = cp.w; p->K = K; p->flow_ok = false;
     a.batch = in.n; a.OH = out.h; a.OW = out.w; a.cout_pad = cp.cout_pad; a.ldo = out.ld;
     a.size = cp.size; a.stride = cp.stride; a.pad = cp.pad; a.cin_blocks = C / block_k;
     a.num_kblocks = cp.size * cp.size * a.cin_blocks;
@@ -436,6 +439,9 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     const bool stageable32 = !residual && a.block_n % 32 == 0 && cp.cout_pad % 32 == 0 && (out.c == cp.cout_pad || out.ld == cp.cout_pad) &&
                              a.mode != 2;
     const bool stageable = stageable64 || stageable32;
+    // (items shorter than 4 k-blocks of 128 filters are all per-item overhead: those layers keep their own kernels)
+    p->flow_ok = block_k == 64 && a.mode == 0 && !local && !up_out && stageable64 && (cp.cout_pad <= 256 || cp.cout_pad % 256 == 0) &&
+                 out.ld % 8 == 0 && (!residual || residual->ld % 8 == 0) && a.num_kblocks * (cp.cout_pad < 256 ? cp.cout_pad : 256) >= 4 * 128;
     // MEASURED (YOLOv3-416 b64): the ring epilogue wins on every stageable layer (1x1 layers -10..-20 %, fused shortcuts
     // -8 %) except the stride-2 3x3 layers without a residual, which lose the pipeline stage the ring's slots cost (+3 %).
     const bool ring_pays = residual || !(cp.size == 3 && cp.stride == 2 && a.block_n == 256);
@@ -489,6 +495,9 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     } else {
         stages = budget / (a_bytes + a.b_stage_bytes);
         if (stages > 8) stages = 8;
+#ifdef B200_EXPERIMENTS
+        if (getenv("B200_EXP_STAGES") && atoi(getenv("B200_EXP_STAGES")) < stages) stages = atoi(getenv("B200_EXP_STAGES"));   // timing experiment
+#endif
         if (stages < 2) { delete p; return nullptr; }
         p->smem_bytes = (size_t)stages * (a_bytes + a.b_stage_bytes) + (a.staged ? sc_bytes : 0) + aux_bytes + 1024;
     }
@@ -542,6 +551,9 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
             }
         }
     }
+#ifdef B200_EXPERIMENTS
+    if (getenv("B200_EXP") && a.pair && (a.mode == 0 || cp.stride == 1)) a.exp = atoi(getenv("B200_EXP"));
+#endif
     p->flops = 2.0 * (double)a.npix * out.c * K;
     char buf[256];
     snprintf(buf, sizeof buf, "conv_tc mode%d k%d n%d tile %dx%dx%d rows %d m_tiles %d n_tiles %d stages %d smem %zu grid %d%s%s",
@@ -556,4 +568,206 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     if (a.local) p->desc += " unshared(local)";
     if (a.split > 1) p->desc += " tailSplit(" + std::to_string(a.split) + "x" + std::to_string(a.vtiles - a.split_from) + ")";
     return p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// flows (kernel in conv_tc_flow.cu)
+// ---------------------------------------------------------------------------------------------------
+// Flows are planned only on request (env B200_FLOW=1 when the network is parsed).  MEASURED (round 2, YOLOv3-416 batch 64, one
+// B200): bit-identical results, tensor-issue busy 73 -> 82 % inside the flow, yet the forward pass is 1-3 % SLOWER than one
+// launch per layer (4.78 vs 4.68 ms cold, 5.30 vs 5.17 ms sustained): the chip is power-managed at sub-millisecond scale, the SM
+// clock inside the flow reads 1660-1750 MHz against ~1920 in the per-layer kernels, i.e. the idle tails the flow removes are
+// what lets the per-layer kernels boost (profiles/r2_flow_*.txt).
+bool conv_tc_plan_flow_ok(const ConvTcPlan *p)
+{
+    const char *on = getenv("B200_FLOW");
+    return p && p->flow_ok && on && atoi(on) != 0 && !getenv("B200_DISABLE_TC");
+}
+const char *conv_tc_flow_desc(ConvTcFlow *f) { return f->desc.c_str(); }
+// profiling: the 4 stamps (+ pair | position << 16) per item of the last launch (nullptr / 0 unless the flow was planned under B200_FLOW_TRACE=1) and the
+// first item number of every member layer (n + 1 entries)
+int conv_tc_flow_trace(ConvTcFlow *f, unsigned long long *out, int max_items, int *item0, int max_layers)
+{
+    if (!f->fp.trace) return 0;
+    const int n = f->fp.total_items < max_items ? f->fp.total_items : max_items;
+    B200_CHECK(cudaMemcpy(out, f->fp.trace, (size_t)n * 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < (int)f->item0.size() && k < max_layers; ++k) item0[k] = f->item0[k];
+    return n;
+}
+void conv_tc_flow_read_stats(ConvTcFlow *f, unsigned long long *out3)
+{
+    B200_CHECK(cudaMemcpy(out3, f->fp.stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    B200_CHECK(cudaMemset(f->fp.stats, 0, 3 * sizeof(unsigned long long)));
+}
+void conv_tc_flow_destroy(ConvTcFlow *f)
+{
+    if (!f) return;
+    if (f->blob) cudaFree(f->blob);
+    delete f;
+}
+
+ConvTcFlow *conv_tc_flow_create(const ConvTcFlowMember *members, int n)
+{
+    if (n < 2 || n > kFlowMaxLayers) return nullptr;
+    std::vector<FlowLayerArgs> L(n);
+    std::vector<CUtensorMap> maps(4 * (size_t)n);
+    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    int item = 0, ctr = 0;
+    double flops = 0;
+    for (int k = 0; k < n; ++k) {
+        const ConvTcPlan *p = members[k].plan;
+        if (!p || !p->flow_ok) return nullptr;
+        const ConvTcArgs &pa = p->args;
+        FlowLayerArgs &a = L[k];
+        memset(&a, 0, sizeof a);
+        a.block_n = pa.cout_pad < 256 ? pa.cout_pad : 256;
+        a.n_tiles = pa.cout_pad / a.block_n;
+        a.m_tiles = (int)((pa.npix + 127) / 128);
+        const int m_pairs = (a.m_tiles + 1) / 2;
+        a.item0 = item; a.items = m_pairs * a.n_tiles; item += a.items;
+        a.num_kblocks = pa.num_kblocks; a.cin_blocks = pa.cin_blocks;
+        a.im2col = pa.im2col; a.size = pa.size; a.stride = pa.stride; a.pad = pa.pad; a.OW = pa.OW; a.OH = pa.OH; a.npix = (int)pa.npix;
+        a.in_W = p->in.w; a.in_H = p->in.h;
+        a.act = pa.act; a.has_res = p->res.p ? 1 : 0; a.res_alpha = pa.res_alpha; a.res_beta = pa.res_beta;
+        a.scale = pa.scale; a.shift = pa.shift;
+        a.done_off = ctr; ctr += m_pairs;
+        a.dep = members[k].dep; a.res_dep = a.has_res ? members[k].res_dep : -1;
+        if (a.dep >= k || a.res_dep >= k) return nullptr;                  // producers come first: the item order is the dependency order
+        if (a.dep >= 0) {
+            const FlowLayerArgs &d = L[a.dep];
+            if ((long long)d.npix != (long long)p->in.n * p->in.h * p->in.w) return nullptr;
+            a.dep_off = d.done_off; a.dep_unit = 2 * d.n_tiles;
+        }
+        if (a.res_dep >= 0) {
+            const FlowLayerArgs &d = L[a.res_dep];
+            if (d.npix != a.npix) return nullptr;
+            a.res_off = d.done_off; a.res_unit = 2 * d.n_tiles;
+        }
+        // A: the plan's own view (dense 2-D rows or the im2col-mode map); B: half a filter tile per CTA of the pair
+        maps[4 * k + 0] = p->maps.a[0];
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)p->K, (cuuint64_t)pa.cout_pad};
+            cuuint64_t strides[1] = {(cuuint64_t)p->K * 2};
+            cuuint32_t box[2] = {64, (cuuint32_t)(a.block_n / 2)};
+            encode(&maps[4 * k + 1], (void *)p->w, 2, dims, strides, box, 64);
+        }
+        ConvTcArgs dense; memset(&dense, 0, sizeof dense); dense.mode = 0; dense.npix = pa.npix;
+        encode_tile_view(&maps[4 * k + 2], p->out, pa.cout_pad, dense, 64);
+        if (a.has_res) encode_tile_view(&maps[4 * k + 3], p->res, pa.cout_pad, dense, 64);
+        flops += p->flops;
+    }
+    // ---- the schedule: list scheduling of all items on the 74 pairs in simulated time ------------------------------------
+    // A free pair takes the oldest item whose inputs are complete (or, if none is, the one that completes first).  Item cost
+    // model: tensor time 0.375 us per 256 x 256 x 64 k-block (measured marginal rate of the pair kernel) against the bytes
+    // the item moves at 1/74 of the HBM rate, plus 0.5 us.  The model only shapes the lists; correctness never depends on it.
+    const int pairs = 74;
+    const int total_items = item;
+    std::vector<unsigned> sched;
+    std::vector<int> sched_off(pairs + 1, 0);
+    double makespan = 0, work = 0;
+    {
+        std::vector<double> dur(n);
+        for (int k = 0; k < n; ++k) {
+            const FlowLayerArgs &a = L[k];
+            const double t_mma = a.num_kblocks * (a.block_n / 256.0) * 0.375;
+            const double bytes = 256.0 * a.cin_blocks * 64 * 2 + 256.0 * a.block_n * 2 * (1 + a.has_res);
+            const double t_mem = bytes / 88.0e3;
+            dur[k] = (t_mma > t_mem ? t_mma : t_mem) + 0.5;
+            work += dur[k] * a.items;
+        }
+        std::vector<unsigned short> layer_of(total_items);
+        for (int k = 0; k < n; ++k) for (int t = 0; t < L[k].items; ++t) layer_of[L[k].item0 + t] = (unsigned short)k;
+        std::vector<double> ctr_done(ctr, 0.0);
+        std::vector<int> ctr_left(ctr);
+        for (int k = 0; k < n; ++k) for (int mp = 0; mp < L[k].items / L[k].n_tiles; ++mp) ctr_left[L[k].done_off + mp] = L[k].n_tiles;
+        std::vector<char> taken(total_items, 0);
+        std::vector<double> pair_free(pairs, 0.0);
+        std::vector<std::vector<unsigned>> lists(pairs);
+        auto ready = [&](int id, double &rt) {
+            const int k = layer_of[id];
+            const FlowLayerArgs &a = L[k];
+            const int mp = (id - a.item0) / a.n_tiles;
+            rt = 0;
+            if (a.dep >= 0) {
+                int jlo, jhi;
+                flow_dep_range(a, mp, jlo, jhi);
+                for (int j = jlo; j <= jhi; ++j) {
+                    if (ctr_left[a.dep_off + j] > 0) return false;
+                    if (ctr_done[a.dep_off + j] > rt) rt = ctr_done[a.dep_off + j];
+                }
+            }
+            if (a.res_dep >= 0) {
+                if (ctr_left[a.res_off + mp] > 0) return false;
+                if (ctr_done[a.res_off + mp] > rt) rt = ctr_done[a.res_off + mp];
+            }
+            return true;
+        };
+        int cursor = 0;
+        const int window = 2048;
+        for (int done = 0; done < total_items; ++done) {
+            int p = 0;
+            for (int q = 1; q < pairs; ++q) if (pair_free[q] < pair_free[p]) p = q;
+            const double T = pair_free[p];
+            while (cursor < total_items && taken[cursor]) ++cursor;
+            int best = -1; double best_rt = 1e300;
+            for (int id = cursor; id < total_items && id < cursor + window; ++id) {
+                if (taken[id]) continue;
+                double rt;
+                if (!ready(id, rt)) continue;
+                if (rt <= T) { best = id; best_rt = rt; break; }
+                if (rt < best_rt) { best = id; best_rt = rt; }
+            }
+            if (best < 0) { fprintf(stderr, "b200-darknet: internal error: flow schedule has no runnable item\n"); abort(); }
+            const int k = layer_of[best];
+            const FlowLayerArgs &a = L[k];
+            const double start = T > best_rt ? T : best_rt, fin = start + dur[k];
+            taken[best] = 1;
+            lists[p].push_back(((unsigned)k << 24) | (unsigned)(best - a.item0));
+            pair_free[p] = fin;
+            const int c = a.done_off + (best - a.item0) / a.n_tiles;
+            if (fin > ctr_done[c]) ctr_done[c] = fin;
+            --ctr_left[c];
+            if (fin > makespan) makespan = fin;
+        }
+        for (int q = 0; q < pairs; ++q) {
+            sched_off[q] = (int)sched.size();
+            sched.insert(sched.end(), lists[q].begin(), lists[q].end());
+        }
+        sched_off[pairs] = (int)sched.size();
+    }
+    for (int k = 0; k < n; ++k) if (L[k].items >= (1 << 24)) return nullptr;
+
+    ConvTcFlow *f = new ConvTcFlow();
+    const size_t maps_bytes = maps.size() * sizeof(CUtensorMap), layers_bytes = (size_t)n * sizeof(FlowLayerArgs);
+    const size_t layers_off = (maps_bytes + 255) / 256 * 256, done_off = (layers_off + layers_bytes + 255) / 256 * 256;
+    const size_t sched_at = (done_off + (size_t)ctr * sizeof(unsigned) + 255) / 256 * 256;
+    const size_t off_at = (sched_at + sched.size() * sizeof(unsigned) + 255) / 256 * 256;
+    const size_t stats_at = (off_at + sched_off.size() * sizeof(int) + 255) / 256 * 256;
+    const bool tracing = getenv("B200_FLOW_TRACE") != nullptr;
+    const size_t trace_at = stats_at + 8 * sizeof(unsigned long long);
+    const size_t total = trace_at + (tracing ? (size_t)item * 5 * sizeof(unsigned long long) : 0);
+    B200_CHECK(cudaMalloc(&f->blob, total));
+    B200_CHECK(cudaMemset(f->blob, 0, total));
+    B200_CHECK(cudaMemcpy(f->blob, maps.data(), maps_bytes, cudaMemcpyHostToDevice));
+    B200_CHECK(cudaMemcpy((unsigned char *)f->blob + layers_off, L.data(), layers_bytes, cudaMemcpyHostToDevice));
+    B200_CHECK(cudaMemcpy((unsigned char *)f->blob + sched_at, sched.data(), sched.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    B200_CHECK(cudaMemcpy((unsigned char *)f->blob + off_at, sched_off.data(), sched_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    f->fp.maps = (const CUtensorMap *)f->blob;
+    f->fp.layers = (const FlowLayerArgs *)((unsigned char *)f->blob + layers_off);
+    f->fp.done = (unsigned *)((unsigned char *)f->blob + done_off);
+    f->fp.sched = (const unsigned *)((unsigned char *)f->blob + sched_at);
+    f->fp.sched_off = (const int *)((unsigned char *)f->blob + off_at);
+    f->fp.stats = (unsigned long long *)((unsigned char *)f->blob + stats_at);
+    f->fp.trace = tracing ? (unsigned long long *)((unsigned char *)f->blob + trace_at) : nullptr;
+    f->item0.resize(n + 1);
+    for (int k = 0; k < n; ++k) f->item0[k] = L[k].item0;
+    f->item0[n] = item;
+    f->fp.nl = n; f->fp.total_items = item; f->fp.epoch = 0;
+    f->smem_bytes = (size_t)kFlowStages * 32768 + (size_t)kFlowRing * 16384 + 512 + (size_t)kFlowMaxLayers * sizeof(FlowLayerArgs) + 1024;
+    f->flops = flops;
+    char buf[200];
+    snprintf(buf, sizeof buf, "conv_tc FLOW %d layers %d pair tiles %d counters stages %d smem %zu grid 148 model %.0f us (%.0f us of work per pair)",
+             n, item, ctr, kFlowStages, f->smem_bytes, makespan, work / pairs);
+    f->desc = buf;
+    return f;
 }

@@ -87,6 +87,41 @@ static std::vector<std::vector<int>> consumers_of(const network *net)
     return c;
 }
 
+// does layer j enqueue a kernel of its own (fused-away layers, aliases and in-place concatenations do not)
+static bool layer_launches(const b200_engine *e, const network *net, int j)
+{
+    const layer &l = net->layers[j];
+    const DevLayer &d = e->L[j];
+    switch (l.type) {
+    case CONVOLUTIONAL: return !d.block_head;
+    case SHORTCUT: return !d.fused_away;
+    case UPSAMPLE: return !d.up_away;
+    case MAXPOOL: return !d.pool_away;
+    case ROUTE: return d.kernel == "route_copy";
+    case DROPOUT: return false;
+    default: return true;
+    }
+}
+
+// the layers whose kernels write the buffer that consumers of layer j read (through aliases and fused producers)
+static void writers_of(const b200_engine *e, const network *net, int j, std::vector<int> &out)
+{
+    const layer &l = net->layers[j];
+    const DevLayer &d = e->L[j];
+    switch (l.type) {
+    case SHORTCUT: if (d.fused_away) { out.push_back(j - 1); return; } break;
+    case UPSAMPLE: if (d.up_away) { out.push_back(j - 1); return; } break;
+    case MAXPOOL: if (d.pool_away) { out.push_back(j - 1); return; } break;
+    case DROPOUT: if (j > 0) { writers_of(e, net, j - 1, out); return; } break;
+    case ROUTE:
+        for (int k = 0; k < l.n; ++k) writers_of(e, net, l.input_layers[k], out);
+        if (d.kernel == "route_copy") out.push_back(j);
+        return;
+    default: break;
+    }
+    out.push_back(j);
+}
+
 static void build_engine_device_state(b200_engine *e, network *net)
 {
     require_device(net->gpu_index);
@@ -394,6 +429,47 @@ static void build_engine_device_state(b200_engine *e, network *net)
         }
     }
 
+    // ---- flows: maximal runs of flow-capable convolutions (nothing else launching in between) become ONE persistent kernel ----
+    e->flow_at.assign(net->n, -1);
+    e->flow_on = 1;
+    for (int i = 1; i < net->n && e->precision == B200_PREC_BF16;) {
+        std::vector<ConvTcFlowMember> mem;
+        std::vector<int> mem_layer;
+        auto member_of = [&](int layer_idx) { for (size_t k = 0; k < mem_layer.size(); ++k) if (mem_layer[k] == layer_idx) return (int)k; return -1; };
+        // producer inside the candidate run -> member index; all producers before the run -> -1; anything else -> -2
+        auto resolve = [&](int src) {
+            std::vector<int> w;
+            writers_of(e, net, src, w);
+            int inside = 0;
+            for (int x : w) if (x >= i) ++inside;
+            if (!inside) return -1;
+            if (w.size() != 1) return -2;
+            const int k = member_of(w[0]);
+            return k >= 0 ? k : -2;
+        };
+        int j = i;
+        bool restart_here = false;
+        for (; j < net->n; ++j) {
+            const layer &l = net->layers[j];
+            DevLayer &d = e->L[j];
+            if (!layer_launches(e, net, j)) continue;
+            if (l.type != CONVOLUTIONAL || !d.tc || !conv_tc_plan_flow_ok(d.tc)) break;
+            const int dep = resolve(j - 1);
+            const int res_dep = d.fused_into >= 0 ? resolve(net->layers[d.fused_into].index) : -1;
+            if (dep == -2 || res_dep == -2) { restart_here = !mem.empty(); break; }
+            mem.push_back(ConvTcFlowMember{d.tc, dep, res_dep});
+            mem_layer.push_back(j);
+        }
+        if (mem.size() >= 2) {
+            ConvTcFlow *f = conv_tc_flow_create(mem.data(), (int)mem.size());
+            if (f) {
+                e->flow_at[mem_layer.front()] = (int)e->flows.size();
+                e->flows.push_back(b200_engine::FlowRun{mem_layer.front(), mem_layer.back(), f});
+            }
+        }
+        i = restart_here ? j : j + 1;
+    }
+
     // ---- heads for decode ---------------------------------------------------------------------------------------
     int base = 0;
     e->raw_decode_ok = !getenv("B200_NO_RAW_DECODE");
@@ -526,6 +602,7 @@ extern "C" void b200_engine_destroy(b200_engine *e)
         cudaStreamSynchronize(e->stream);
         if (e->comm) b200_comm_release(e);
         b200_engine_unpin_host(e);
+        for (auto &f : e->flows) conv_tc_flow_destroy(f.flow);
         for (auto &d : e->L) {
             if (d.tc) conv_tc_plan_destroy(d.tc);
             if (d.owns_out) cudaFree(d.out.p);
@@ -726,6 +803,20 @@ static void run_layer(b200_engine *e, network *net, int i, int batch)
     }
 }
 
+// runs layer i — or, when i opens a flow that ends before `end`, the whole flow in one launch; returns the last layer done
+static int run_layer_or_flow(b200_engine *e, network *net, int i, int end, int batch)
+{
+    const int fi = e->flow_at[i];
+    if (fi >= 0 && e->flow_on && e->conv_backend == 0 && e->flows[fi].last < end) {
+        const b200_engine::FlowRun &f = e->flows[fi];
+        if (e->tail_guard_layer > i && e->tail_guard_layer <= f.last) B200_CHECK(cudaStreamWaitEvent(e->stream, e->tail_done, 0));
+        launch_conv_tc_flow(f.flow, e->stream);
+        return f.last;
+    }
+    run_layer(e, net, i, batch);
+    return i;
+}
+
 static int logical_batch(const b200_engine *e, const network *net)
 {
     if (net->batch > e->cap) {
@@ -745,7 +836,7 @@ static void forward_layers(b200_engine *e, network *net, int start, int end, boo
     for (int i = start; i < end; ++i) {
         if (skip_yolo_forward && net->layers[i].type == YOLO) continue;   // the fused detection path decodes from the raw logits
         if (i == e->tail_guard_layer) B200_CHECK(cudaStreamWaitEvent(e->stream, e->tail_done, 0));   // no-op unless a tail is in flight
-        run_layer(e, net, i, batch);
+        i = run_layer_or_flow(e, net, i, end, batch);
     }
 }
 
@@ -837,6 +928,37 @@ extern "C" void b200_set_conv_backend(network *net, int backend)
     e->conv_backend = backend;
 }
 extern "C" void b200_set_head_sync(network *net, int on) { b200_engine_of(net)->head_sync = on; }
+extern "C" void b200_set_flow(network *net, int on) { b200_engine_of(net)->flow_on = on; }
+// profiling: nanoseconds the flow kernels' TMA producers / residual loaders spent blocked on a dependency and the number of
+// blocking waits, summed over all launches since the last call (reads and clears the device counters of every flow)
+extern "C" void b200_flow_stats(network *net, unsigned long long *out3)
+{
+    b200_engine *e = b200_engine_of(net);
+    for (int i = 0; i < 5; ++i) out3[i] = 0;
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    for (auto &f : e->flows) {
+        unsigned long long v[5];
+        conv_tc_flow_read_stats(f.flow, v);
+        for (int i = 0; i < 3; ++i) out3[i] += v[i];
+        if (f.flow == e->flows[0].flow) { out3[3] = v[3]; out3[4] = v[4]; }
+    }
+}
+extern "C" int b200_flow_trace(network *net, int k, unsigned long long *out, int max_items, int *item0, int max_layers)
+{
+    b200_engine *e = b200_engine_of(net);
+    if (k < 0 || k >= (int)e->flows.size()) return 0;
+    B200_CHECK(cudaStreamSynchronize(e->stream));
+    return conv_tc_flow_trace(e->flows[k].flow, out, max_items, item0, max_layers);
+}
+extern "C" int b200_flow_count(network *net) { return (int)b200_engine_of(net)->flows.size(); }
+extern "C" const char *b200_flow_desc(network *net, int k, int *first, int *last)
+{
+    b200_engine *e = b200_engine_of(net);
+    if (k < 0 || k >= (int)e->flows.size()) return "";
+    if (first) *first = e->flows[k].first;
+    if (last) *last = e->flows[k].last;
+    return conv_tc_flow_desc(e->flows[k].flow);
+}
 
 // ----------------------------------------------------------------------------------------------------
 // inspection hooks
@@ -1002,7 +1124,7 @@ extern "C" void b200_profile_forward(network *net, int iters, float *ms)
         if (it >= 0) B200_CHECK(cudaEventRecord(ev[2 * it + 1], e->stream));
         for (int i = 1; i < net->n; ++i) {
             if (skip_yolo && net->layers[i].type == YOLO) continue;
-            run_layer(e, net, i, batch);
+            i = run_layer_or_flow(e, net, i, net->n, batch);
         }
     };
     one_pass(-1);                                             // warm-up, then the timed passes without a gap

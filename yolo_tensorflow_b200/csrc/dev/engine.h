@@ -49,6 +49,12 @@ struct b200_engine {
     cudaEvent_t tail_done;     // decode + NMS + collect of the current batch finished (d2h_stream waits on it)
     cudaStream_t tail_stream;  // serving loop: decode + NMS + collect of batch k run here, beside the first layers of batch k+1
     cudaEvent_t fwd_done;      // the forward pass of the current batch is complete (tail_stream waits on it)
+    // flows (conv_tc_flow.cu): runs of convolution layers executed by one persistent kernel; flow_at[i] = index of the flow
+    // whose first member is layer i, or -1.  flow_on = 0 runs the members one launch per layer (b200_set_flow).
+    struct FlowRun { int first, last; ConvTcFlow *flow; };
+    std::vector<FlowRun> flows;
+    std::vector<int> flow_at;
+    int flow_on;
     int tail_guard_layer;      // first layer that overwrites something the tail reads (head logits / l.output): it waits for tail_done
     cudaEvent_t lb_uploaded, lb_done;   // b200_letterbox_batch*: raw images are on the device / the resize kernel has consumed them
     int fwd_enqueued;          // the submitted batch's forward pass is already in the compute stream (b200_detect_submitted)

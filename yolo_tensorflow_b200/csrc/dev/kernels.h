@@ -62,6 +62,19 @@ ConvTcPlan *conv_tc_block_plan_create(TView x, TView out, ConvParams p1, ConvPar
 bool conv_tc_shape_supported(int cin, int stride, int act);
 void launch_conv_tc(ConvTcPlan *plan, cudaStream_t s);
 const char *conv_tc_plan_desc(ConvTcPlan *plan);
+// A FLOW: a run of tcgen05 convolution layers executed by ONE persistent CTA-pair kernel.  Tiles of layer n+1 start as soon as the
+// tiles of layer n they read are stored (per-256-pixel completion counters in HBM) instead of at a kernel boundary, so the
+// tensor pipe does not drain between layers.  members[k].dep / res_dep: index (inside the flow) of the layer producing member
+// k's input / fused-shortcut operand, or -1 when that tensor is complete before the flow is launched.
+struct ConvTcFlow;
+struct ConvTcFlowMember { ConvTcPlan *plan; int dep, res_dep; };
+bool conv_tc_plan_flow_ok(const ConvTcPlan *plan);
+ConvTcFlow *conv_tc_flow_create(const ConvTcFlowMember *members, int n);      // nullptr: not worth it / does not fit
+void conv_tc_flow_destroy(ConvTcFlow *flow);
+void launch_conv_tc_flow(ConvTcFlow *flow, cudaStream_t s);
+const char *conv_tc_flow_desc(ConvTcFlow *flow);
+int conv_tc_flow_trace(ConvTcFlow *flow, unsigned long long *out, int max_items, int *item0, int max_layers);
+void conv_tc_flow_read_stats(ConvTcFlow *flow, unsigned long long *out3);     // reads and clears (call with the stream idle)
 // cuTensorMapEncodeTiled through the runtime's driver entry point (dtype 0 = bf16, 1 = fp32; swizzle_bytes 0/32/64/128)
 void tc_encode_tiled(void *map, int dtype, int rank, void *base, const unsigned long long *dims, const unsigned long long *strides_bytes,
                      const unsigned *box, int swizzle_bytes);

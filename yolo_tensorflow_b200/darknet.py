@@ -81,6 +81,11 @@ lib.b200_set_default_fusion.argtypes = [c_int]
 lib.b200_get_precision.argtypes = [c_void_p]; lib.b200_get_precision.restype = c_int
 lib.b200_set_conv_backend.argtypes = [c_void_p, c_int]
 lib.b200_set_head_sync.argtypes = [c_void_p, c_int]
+lib.b200_set_flow.argtypes = [c_void_p, c_int]
+lib.b200_flow_stats.argtypes = [c_void_p, POINTER(c_ulonglong)]
+lib.b200_flow_trace.argtypes = [c_void_p, c_int, c_void_p, c_int, POINTER(c_int), c_int]; lib.b200_flow_trace.restype = c_int
+lib.b200_flow_count.argtypes = [c_void_p]; lib.b200_flow_count.restype = c_int
+lib.b200_flow_desc.argtypes = [c_void_p, c_int, POINTER(c_int), POINTER(c_int)]; lib.b200_flow_desc.restype = c_char_p
 lib.b200_fetch_layer_output.argtypes = [c_void_p, c_int, POINTER(c_float)]
 lib.b200_set_layer_output.argtypes = [c_void_p, c_int, POINTER(c_float)]
 lib.b200_run_layers.argtypes = [c_void_p, c_int, c_int]
@@ -228,6 +233,32 @@ class Network:
 
     def set_head_sync(self, on):
         lib.b200_set_head_sync(self.ptr, int(on))
+
+    def set_flow(self, on):
+        """1 (default): flow-capable runs of convolutions execute as one persistent kernel; 0: one launch per layer"""
+        lib.b200_set_flow(self.ptr, int(on))
+
+    def flow_stats(self):
+        """(ns producers blocked on dependencies, ns residual loaders blocked, blocking waits) since the last call"""
+        v = (c_ulonglong * 5)()
+        lib.b200_flow_stats(self.ptr, v)
+        return int(v[0]), int(v[1]), int(v[2]), int(v[3]), int(v[4])
+
+    def flow_trace(self, k, max_items=1 << 20):
+        """(stamps [items][5] uint64: 4 x ns + pair | position << 16, item0 [layers + 1]) of flow k's last launch; needs B200_FLOW_TRACE=1 when the net was parsed"""
+        buf = np.zeros((max_items, 5), dtype=np.uint64)
+        item0 = (c_int * 64)()
+        n = lib.b200_flow_trace(self.ptr, k, buf.ctypes.data, max_items, item0, 64)
+        return buf[:n], list(item0)
+
+    def flows(self):
+        """[(first layer, last layer, plan text)] of the planned flows"""
+        out = []
+        for k in range(lib.b200_flow_count(self.ptr)):
+            a, b = c_int(0), c_int(0)
+            d = lib.b200_flow_desc(self.ptr, k, byref(a), byref(b)).decode()
+            out.append((a.value, b.value, d))
+        return out
 
     def boxes(self, b, w, h, thresh, relative=1):
         """get_network_boxes_batch -> (dets pointer, count); caller frees with free_detections"""
