@@ -271,8 +271,10 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                         if (leader) { if (bytes) mbar_expect_tx(&full[stage], bytes); else mbar_arrive(&full[stage]); }
                         const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
                         if (!skip_a) {
-                            if (args.im2col) tma2_load_im2col_4d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, ox0, oy0, n0, tap % args.size, tap / args.size);
-                            else if (args.mode == 0) tma2_load_2d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, m_tile * 128);
+                            // bit 2: every CTA loads the SAME A rows (pixel tile 0 / 1): private versus shared lines, same bytes per SM
+                            if (args.im2col) tma2_load_im2col_4d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, (args.exp & 4) ? -args.pad : ox0,
+                                                                 (args.exp & 4) ? -args.pad : oy0, (args.exp & 4) ? (int)rank : n0, tap % args.size, tap / args.size);
+                            else if (args.mode == 0) tma2_load_2d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, ((args.exp & 4) ? (int)rank : m_tile) * 128);
                             else tma2_load_4d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, ox0 + tap % args.size - args.pad, oy0 + tap / args.size - args.pad, n0);
                         }
                         if (!skip_b) tma2_load_2d(bmap, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n + v.col_off + (int)rank * half_w);
