@@ -61,3 +61,14 @@ net.resize(224, 192)
 rec, counts = net.detect_batch(synth.make_images(2, 3, 192, 224, 7), 224, 192, .3, .45)
 print("resized yolov2", len(rec))
 net.close()
+# round 2, second part: the flow kernel (B200_FLOW=1) and the im2col-mode loads at odd sizes / strides
+os.environ["B200_FLOW"] = "1"
+cfg = synth.make_cfg("yolov3", work, batch=3, width=160, height=96)
+net = dn.Network(cfg, os.path.join(work, "yolov3.weights"), precision=dn.PREC_BF16)
+os.environ.pop("B200_FLOW")
+print("flows", [(a, b) for a, b, _ in net.flows()])
+x = synth.make_images(3, 3, 96, 160, 9)
+for _ in range(2):
+    rec, counts = net.detect_batch(x, 160, 96, .3, .45)
+print("flow detect", len(rec), net.flow_stats()[:3])
+net.close()

@@ -270,14 +270,17 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                         const uint32_t bytes = 2u * (uint32_t)((skip_a ? 0 : args.a_rows * BLOCK_K * 2) + (skip_b ? 0 : half_w * BLOCK_K * 2));
                         if (leader) { if (bytes) mbar_expect_tx(&full[stage], bytes); else mbar_arrive(&full[stage]); }
                         const int tap = kb / args.cin_blocks, cb = kb - tap * args.cin_blocks;
+                        // bit 3 (8): A lands in a buffer the tensor core never reads (a ring-epilogue slot); bit 4 (16): B is issued before A
+                        uint8_t *dstA_x = (args.exp & 8) ? sC + 2 * 16384 : sA + (size_t)stage * A_BYTES;
+                        if ((args.exp & 16) && !skip_b) tma2_load_2d(bmap, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n + v.col_off + (int)rank * half_w);
                         if (!skip_a) {
                             // bit 2: every CTA loads the SAME A rows (pixel tile 0 / 1): private versus shared lines, same bytes per SM
-                            if (args.im2col) tma2_load_im2col_4d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, (args.exp & 4) ? -args.pad : ox0,
+                            if (args.im2col) tma2_load_im2col_4d(&maps.a[0], dstA_x, &full[stage], cb * BLOCK_K, (args.exp & 4) ? -args.pad : ox0,
                                                                  (args.exp & 4) ? -args.pad : oy0, (args.exp & 4) ? (int)rank : n0, tap % args.size, tap / args.size);
-                            else if (args.mode == 0) tma2_load_2d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, ((args.exp & 4) ? (int)rank : m_tile) * 128);
+                            else if (args.mode == 0) tma2_load_2d(&maps.a[0], dstA_x, &full[stage], cb * BLOCK_K, ((args.exp & 4) ? (int)rank : m_tile) * 128);
                             else tma2_load_4d(&maps.a[0], sA + (size_t)stage * A_BYTES, &full[stage], cb * BLOCK_K, ox0 + tap % args.size - args.pad, oy0 + tap / args.size - args.pad, n0);
                         }
-                        if (!skip_b) tma2_load_2d(bmap, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n + v.col_off + (int)rank * half_w);
+                        if (!(args.exp & 16) && !skip_b) tma2_load_2d(bmap, sB + (size_t)stage * args.b_stage_bytes, &full[stage], kb * BLOCK_K, n_tile * args.block_n + v.col_off + (int)rank * half_w);
                         if (++stage == stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
