@@ -51,6 +51,10 @@ void b200_flow_stats(network *net, unsigned long long *out5);
 /* profiling (flows planned under B200_FLOW_TRACE=1 only, else returns 0): 5 values per item of flow k's last launch — device-clock
  * stamps (ns) inputs complete, first operands landed, last MMA issued, tile stored, then pair | position in its list << 16 — and the first item number of each member layer */
 int  b200_flow_trace(network *net, int k, unsigned long long *out, int max_items, int *item0, int max_layers);
+/* host-only self-test of the flow scheduler (no device needed): a chain of n layers over a batch x hw x hw map,
+ * spec[4k..4k+3] = {filter size 1|3, stride, input channels, filters}, is scheduled on `pairs` CTA pairs and the item lists are
+ * replayed without the cost model; returns -1 when every item runs exactly once (no deadlock), else the first stuck item */
+int  b200_flow_schedule_selftest(int n, const int *spec, int batch, int hw, int pairs, double *makespan_us, double *work_us);
 
 /* ---- opaque engine, one per network -------------------------------------------------------------- */
 typedef struct b200_engine b200_engine;

@@ -606,6 +606,125 @@ void conv_tc_flow_destroy(ConvTcFlow *f)
     delete f;
 }
 
+// ---- the schedule of a flow: list scheduling of all items on the CTA pairs in simulated time ------------------------------------
+// A free pair takes the oldest item whose inputs are complete (or, if none is, the one that completes first).  Item cost
+// model: tensor time 0.375 us per 256 x 256 x 64 k-block (measured marginal rate of the pair kernel) against the bytes
+// the item moves at 1/74 of the HBM rate, plus 0.5 us.  The model only shapes the lists; correctness never depends on it:
+// any order produced here is a valid execution in simulated time, so the kernel (all pairs co-resident) cannot deadlock.
+static void flow_schedule(const std::vector<FlowLayerArgs> &L, int ctr, int pairs, std::vector<unsigned> &sched, std::vector<int> &sched_off,
+                          double &makespan, double &work)
+{
+    const int n = (int)L.size();
+    int total_items = 0;
+    for (const FlowLayerArgs &a : L) total_items += a.items;
+    sched.clear();
+    sched_off.assign(pairs + 1, 0);
+    makespan = 0; work = 0;
+    std::vector<double> dur(n);
+    for (int k = 0; k < n; ++k) {
+        const FlowLayerArgs &a = L[k];
+        const double t_mma = a.num_kblocks * (a.block_n / 256.0) * 0.375;
+        const double bytes = 256.0 * a.cin_blocks * 64 * 2 + 256.0 * a.block_n * 2 * (1 + a.has_res);
+        const double t_mem = bytes / 88.0e3;
+        dur[k] = (t_mma > t_mem ? t_mma : t_mem) + 0.5;
+        work += dur[k] * a.items;
+    }
+    std::vector<unsigned short> layer_of(total_items);
+    for (int k = 0; k < n; ++k) for (int t = 0; t < L[k].items; ++t) layer_of[L[k].item0 + t] = (unsigned short)k;
+    std::vector<double> ctr_done(ctr, 0.0);
+    std::vector<int> ctr_left(ctr);
+    for (int k = 0; k < n; ++k) for (int mp = 0; mp < L[k].items / L[k].n_tiles; ++mp) ctr_left[L[k].done_off + mp] = L[k].n_tiles;
+    std::vector<char> taken(total_items, 0);
+    std::vector<double> pair_free(pairs, 0.0);
+    std::vector<std::vector<unsigned>> lists(pairs);
+    auto ready = [&](int id, double &rt) {
+        const int k = layer_of[id];
+        const FlowLayerArgs &a = L[k];
+        const int mp = (id - a.item0) / a.n_tiles;
+        rt = 0;
+        if (a.dep >= 0) {
+            int jlo, jhi;
+            flow_dep_range(a, mp, jlo, jhi);
+            for (int j = jlo; j <= jhi; ++j) {
+                if (ctr_left[a.dep_off + j] > 0) return false;
+                if (ctr_done[a.dep_off + j] > rt) rt = ctr_done[a.dep_off + j];
+            }
+        }
+        if (a.res_dep >= 0) {
+            if (ctr_left[a.res_off + mp] > 0) return false;
+            if (ctr_done[a.res_off + mp] > rt) rt = ctr_done[a.res_off + mp];
+        }
+        return true;
+    };
+    int cursor = 0;
+    const int window = 2048;
+    for (int done = 0; done < total_items; ++done) {
+        int p = 0;
+        for (int q = 1; q < pairs; ++q) if (pair_free[q] < pair_free[p]) p = q;
+        const double T = pair_free[p];
+        while (cursor < total_items && taken[cursor]) ++cursor;
+        int best = -1; double best_rt = 1e300;
+        for (int id = cursor; id < total_items && id < cursor + window; ++id) {
+            if (taken[id]) continue;
+            double rt;
+            if (!ready(id, rt)) continue;
+            if (rt <= T) { best = id; best_rt = rt; break; }
+            if (rt < best_rt) { best = id; best_rt = rt; }
+        }
+        if (best < 0) { fprintf(stderr, "b200-darknet: internal error: flow schedule has no runnable item\n"); abort(); }
+        const int k = layer_of[best];
+        const FlowLayerArgs &a = L[k];
+        const double start = T > best_rt ? T : best_rt, fin = start + dur[k];
+        taken[best] = 1;
+        lists[p].push_back(((unsigned)k << 24) | (unsigned)(best - a.item0));
+        pair_free[p] = fin;
+        const int c = a.done_off + (best - a.item0) / a.n_tiles;
+        if (fin > ctr_done[c]) ctr_done[c] = fin;
+        --ctr_left[c];
+        if (fin > makespan) makespan = fin;
+    }
+    for (int q = 0; q < pairs; ++q) {
+        sched_off[q] = (int)sched.size();
+        sched.insert(sched.end(), lists[q].begin(), lists[q].end());
+    }
+    sched_off[pairs] = (int)sched.size();
+}
+
+// Replays per-pair item lists WITHOUT the cost model: a pair may run its next item as soon as the counters that item waits on
+// are complete.  Returns -1 when every item ran exactly once, else the first item that could never run (a deadlock or a hole).
+static int flow_schedule_check(const std::vector<FlowLayerArgs> &L, int ctr, int pairs, const std::vector<unsigned> &sched, const std::vector<int> &sched_off)
+{
+    std::vector<int> left(ctr, 0), pos(pairs);
+    int total = 0;
+    for (const FlowLayerArgs &a : L) { for (int mp = 0; mp < a.items / a.n_tiles; ++mp) left[a.done_off + mp] = a.n_tiles; total += a.items; }
+    if ((int)sched.size() != total) return 0;
+    std::vector<char> ran(total, 0);
+    for (int q = 0; q < pairs; ++q) pos[q] = sched_off[q];
+    int done = 0;
+    for (bool progress = true; progress;) {
+        progress = false;
+        for (int q = 0; q < pairs; ++q) {
+            while (pos[q] < sched_off[q + 1]) {
+                const unsigned ent = sched[pos[q]];
+                const FlowLayerArgs &a = L[ent >> 24];
+                const int t = (int)(ent & 0xffffffu), mp = t / a.n_tiles;
+                bool ok = t < a.items && !ran[a.item0 + t];
+                if (ok && a.dep >= 0) {
+                    int jlo, jhi;
+                    flow_dep_range(a, mp, jlo, jhi);
+                    for (int j = jlo; j <= jhi && ok; ++j) ok = left[a.dep_off + j] == 0;
+                }
+                if (ok && a.res_dep >= 0) ok = left[a.res_off + mp] == 0;
+                if (!ok) break;
+                ran[a.item0 + t] = 1; --left[a.done_off + mp]; ++pos[q]; ++done; progress = true;
+            }
+        }
+    }
+    if (done == total) return -1;
+    for (int q = 0; q < pairs; ++q) if (pos[q] < sched_off[q + 1]) { const unsigned ent = sched[pos[q]]; return L[ent >> 24].item0 + (int)(ent & 0xffffffu); }
+    return 0;
+}
+
 ConvTcFlow *conv_tc_flow_create(const ConvTcFlowMember *members, int n)
 {
     if (n < 2 || n > kFlowMaxLayers) return nullptr;
@@ -656,85 +775,11 @@ ConvTcFlow *conv_tc_flow_create(const ConvTcFlowMember *members, int n)
         if (a.has_res) encode_tile_view(&maps[4 * k + 3], p->res, pa.cout_pad, dense, 64);
         flops += p->flops;
     }
-    // ---- the schedule: list scheduling of all items on the 74 pairs in simulated time ------------------------------------
-    // A free pair takes the oldest item whose inputs are complete (or, if none is, the one that completes first).  Item cost
-    // model: tensor time 0.375 us per 256 x 256 x 64 k-block (measured marginal rate of the pair kernel) against the bytes
-    // the item moves at 1/74 of the HBM rate, plus 0.5 us.  The model only shapes the lists; correctness never depends on it.
     const int pairs = 74;
-    const int total_items = item;
     std::vector<unsigned> sched;
-    std::vector<int> sched_off(pairs + 1, 0);
+    std::vector<int> sched_off;
     double makespan = 0, work = 0;
-    {
-        std::vector<double> dur(n);
-        for (int k = 0; k < n; ++k) {
-            const FlowLayerArgs &a = L[k];
-            const double t_mma = a.num_kblocks * (a.block_n / 256.0) * 0.375;
-            const double bytes = 256.0 * a.cin_blocks * 64 * 2 + 256.0 * a.block_n * 2 * (1 + a.has_res);
-            const double t_mem = bytes / 88.0e3;
-            dur[k] = (t_mma > t_mem ? t_mma : t_mem) + 0.5;
-            work += dur[k] * a.items;
-        }
-        std::vector<unsigned short> layer_of(total_items);
-        for (int k = 0; k < n; ++k) for (int t = 0; t < L[k].items; ++t) layer_of[L[k].item0 + t] = (unsigned short)k;
-        std::vector<double> ctr_done(ctr, 0.0);
-        std::vector<int> ctr_left(ctr);
-        for (int k = 0; k < n; ++k) for (int mp = 0; mp < L[k].items / L[k].n_tiles; ++mp) ctr_left[L[k].done_off + mp] = L[k].n_tiles;
-        std::vector<char> taken(total_items, 0);
-        std::vector<double> pair_free(pairs, 0.0);
-        std::vector<std::vector<unsigned>> lists(pairs);
-        auto ready = [&](int id, double &rt) {
-            const int k = layer_of[id];
-            const FlowLayerArgs &a = L[k];
-            const int mp = (id - a.item0) / a.n_tiles;
-            rt = 0;
-            if (a.dep >= 0) {
-                int jlo, jhi;
-                flow_dep_range(a, mp, jlo, jhi);
-                for (int j = jlo; j <= jhi; ++j) {
-                    if (ctr_left[a.dep_off + j] > 0) return false;
-                    if (ctr_done[a.dep_off + j] > rt) rt = ctr_done[a.dep_off + j];
-                }
-            }
-            if (a.res_dep >= 0) {
-                if (ctr_left[a.res_off + mp] > 0) return false;
-                if (ctr_done[a.res_off + mp] > rt) rt = ctr_done[a.res_off + mp];
-            }
-            return true;
-        };
-        int cursor = 0;
-        const int window = 2048;
-        for (int done = 0; done < total_items; ++done) {
-            int p = 0;
-            for (int q = 1; q < pairs; ++q) if (pair_free[q] < pair_free[p]) p = q;
-            const double T = pair_free[p];
-            while (cursor < total_items && taken[cursor]) ++cursor;
-            int best = -1; double best_rt = 1e300;
-            for (int id = cursor; id < total_items && id < cursor + window; ++id) {
-                if (taken[id]) continue;
-                double rt;
-                if (!ready(id, rt)) continue;
-                if (rt <= T) { best = id; best_rt = rt; break; }
-                if (rt < best_rt) { best = id; best_rt = rt; }
-            }
-            if (best < 0) { fprintf(stderr, "b200-darknet: internal error: flow schedule has no runnable item\n"); abort(); }
-            const int k = layer_of[best];
-            const FlowLayerArgs &a = L[k];
-            const double start = T > best_rt ? T : best_rt, fin = start + dur[k];
-            taken[best] = 1;
-            lists[p].push_back(((unsigned)k << 24) | (unsigned)(best - a.item0));
-            pair_free[p] = fin;
-            const int c = a.done_off + (best - a.item0) / a.n_tiles;
-            if (fin > ctr_done[c]) ctr_done[c] = fin;
-            --ctr_left[c];
-            if (fin > makespan) makespan = fin;
-        }
-        for (int q = 0; q < pairs; ++q) {
-            sched_off[q] = (int)sched.size();
-            sched.insert(sched.end(), lists[q].begin(), lists[q].end());
-        }
-        sched_off[pairs] = (int)sched.size();
-    }
+    flow_schedule(L, ctr, pairs, sched, sched_off, makespan, work);
     for (int k = 0; k < n; ++k) if (L[k].items >= (1 << 24)) return nullptr;
 
     ConvTcFlow *f = new ConvTcFlow();
@@ -770,4 +815,38 @@ ConvTcFlow *conv_tc_flow_create(const ConvTcFlowMember *members, int n)
              n, item, ctr, kFlowStages, f->smem_bytes, makespan, work / pairs);
     f->desc = buf;
     return f;
+}
+
+// Host-only self-test of the flow scheduler (no device needed; tests/test_flow_schedule.py): a chain of `n` layers over a
+// batch x hw x hw map — spec[4k .. 4k+3] = {filter size (1 or 3), stride, input channels, filters}, 3x3 layers with stride 1 from
+// the third layer on take the layer two back as their shortcut operand — is cut into items, scheduled on `pairs` pairs and the
+// lists replayed without the cost model.  Returns -1 when the schedule is complete and deadlock-free, else the stuck item.
+extern "C" int b200_flow_schedule_selftest(int n, const int *spec, int batch, int hw, int pairs, double *makespan_us, double *work_us)
+{
+    std::vector<FlowLayerArgs> L(n);
+    int item = 0, ctr = 0, h = hw;
+    for (int k = 0; k < n; ++k) {
+        const int size = spec[4 * k], stride = spec[4 * k + 1], cin = spec[4 * k + 2], cout = spec[4 * k + 3];
+        FlowLayerArgs &a = L[k];
+        memset(&a, 0, sizeof a);
+        const int pad = size / 2, oh = (h + 2 * pad - size) / stride + 1;
+        a.block_n = cout < 256 ? cout : 256; a.n_tiles = cout / a.block_n;
+        a.npix = batch * oh * oh; a.m_tiles = (a.npix + 127) / 128;
+        const int m_pairs = (a.m_tiles + 1) / 2;
+        a.item0 = item; a.items = m_pairs * a.n_tiles; item += a.items;
+        a.cin_blocks = cin / 64; a.num_kblocks = size * size * a.cin_blocks;
+        a.im2col = size > 1; a.size = size; a.stride = stride; a.pad = pad; a.OW = a.OH = oh; a.in_W = a.in_H = h;
+        a.done_off = ctr; ctr += m_pairs;
+        a.dep = k - 1; a.res_dep = -1;
+        if (k >= 2 && size == 3 && stride == 1 && L[k - 2].npix == a.npix && L[k - 2].n_tiles * L[k - 2].block_n == cout) { a.res_dep = k - 2; a.has_res = 1; }
+        if (a.dep >= 0) { a.dep_off = L[a.dep].done_off; a.dep_unit = 2 * L[a.dep].n_tiles; }
+        if (a.res_dep >= 0) { a.res_off = L[a.res_dep].done_off; a.res_unit = 2 * L[a.res_dep].n_tiles; }
+        h = oh;
+    }
+    std::vector<unsigned> sched; std::vector<int> off;
+    double mk = 0, wk = 0;
+    flow_schedule(L, ctr, pairs, sched, off, mk, wk);
+    if (makespan_us) *makespan_us = mk;
+    if (work_us) *work_us = wk / pairs;
+    return flow_schedule_check(L, ctr, pairs, sched, off);
 }
