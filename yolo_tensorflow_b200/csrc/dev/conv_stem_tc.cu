@@ -316,8 +316,11 @@ conv_stem_tc_tma_kernel(const __grid_constant__ StemTcMaps maps, const StemTcArg
                 if constexpr (POOL) tma_store_4d(&maps.out, sC[cs], 0, t.tx * (kTW / 2), t.ty * (kTH / 2), t.tn);      // 16 x 2 pooled pixels
                 else tma_store_4d(&maps.out, sC[cs], 0, t.tx * kTW / a.pack, t.ty * kTH, t.tn);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                mbar_arrive(&cempty[cs]);
+                // one store stays in flight (two measured the same): waiting for THIS tile's read before issuing the next serialised the warp at the
+                // store engine's read latency (~0.4 us per tile = the kernel's whole tile period).  The previous tile's slot is
+                // free once all groups but the newest have been read.
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (i > 0) mbar_arrive(&cempty[(i - 1) % kOutSlots]);
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
