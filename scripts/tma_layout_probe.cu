@@ -8,6 +8,8 @@
 //   layout 2  NHWC, every SM reads the SAME tiles (the weights' situation)
 //   layout 3  NHWC through a 4-D (C, W, H, N) map, box 64 x 2 x 2 x 32 pixels (the tiled 3x3 A load of round 1)
 //   layout 4  NHWC through an im2col-mode map, 128 consecutive output pixels per load (the 3x3 A load of round 2)
+// and, in rounds of 12 boxes per CTA, clusters of 2 / 4 CTAs that want the same boxes: each loading them itself, or each loading a
+// part and multicasting it to the cluster (does sharing a box cut the time, i.e. is the L2 -> SM fabric what limits the loads?)
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tma_layout_probe tma_layout_probe.cu -lcuda
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -64,6 +66,88 @@ loads_only(const __grid_constant__ CUtensorMap map, int layout, int npix, int ti
     }
 }
 
+
+// rounds of RS loads (all in flight, then a cluster barrier): cluster of CL CTAs that all want the SAME boxes (two CTA pairs computing
+// different filter tiles of the same pixels).  mc = 0: every CTA loads the whole box itself; mc = 1: every CTA loads 128 / CL
+// rows of it and multicasts them to all CTAs of the cluster, so each box crosses the L2 -> SM fabric once per cluster.
+template <int CL>
+__global__ void __launch_bounds__(128, 1)
+loads_rounds(const __grid_constant__ CUtensorMap map_full, const __grid_constant__ CUtensorMap map_part, int mc, int npix, int tiles_per_cluster, int cblocks, unsigned *sink)
+{
+    extern __shared__ uint8_t raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    constexpr int RS = 12;
+    __shared__ uint64_t full[RS];
+    uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RS; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&full[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const int total = tiles_per_cluster * 9 * cblocks;
+    const int tile0 = (blockIdx.x / CL) * tiles_per_cluster;
+    const int part_rows = 128 / CL;
+    for (int base = 0, round = 0; base < total; base += RS, ++round) {
+        if (threadIdx.x == 0) {
+            const int n = total - base < RS ? total - base : RS;
+            for (int j = 0; j < n; ++j) {
+                const int i = base + j;
+                const int tile = tile0 + i / (9 * cblocks), r = i % (9 * cblocks), tap = r / cblocks, cb = r % cblocks;
+                int p = tile * 128 + (tap / 3 - 1) * 26 + (tap % 3 - 1);
+                if (p < 0) p = 0;
+                if (p > npix - 128) p = npix - 128;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&full[j])), "r"(16384) : "memory");
+                if (mc) {
+                    const uint16_t mask = (uint16_t)((1u << CL) - 1u);
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                                 ::"r"(s32(smem + j * 16384 + rank * part_rows * 128)), "l"(&map_part), "r"(s32(&full[j])), "r"(cb * 64), "r"(p + (int)rank * part_rows), "h"(mask) : "memory");
+                } else {
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                 ::"r"(s32(smem + j * 16384)), "l"(&map_full), "r"(s32(&full[j])), "r"(cb * 64), "r"(p) : "memory");
+                }
+            }
+            for (int j = 0; j < n; ++j)
+                asm volatile("{\n\t.reg .pred p;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(s32(&full[j])), "r"((uint32_t)round & 1u) : "memory");
+        }
+        // nobody may send into a slot of a CTA that has not finished the round
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) sink[blockIdx.x] = ((volatile unsigned *)smem)[0];
+}
+
+template <int CL> static void run_rounds(void *d, int C, int npix, int cblocks, unsigned *sink)
+{
+    CUtensorMap full, part;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)npix}, strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, 128}, pbox[2] = {64, (cuuint32_t)(128 / CL)}, ones[2] = {1, 1};
+    cuTensorMapEncodeTiled(&full, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuTensorMapEncodeTiled(&part, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, dims, strides, pbox, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const int smem = 12 * 16384 + 2048;
+    cudaFuncSetAttribute(loads_rounds<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int clusters = 148 / CL, grid = clusters * CL, tiles = npix / 128, per = tiles / clusters;
+    for (int mc = 0; mc < 2; ++mc) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int it = 0; it < 3; ++it) cudaLaunchKernelEx(&cfg, loads_rounds<CL>, full, part, mc, npix, per, cblocks, sink);
+        cudaEventRecord(e0);
+        const int reps = 20;
+        for (int it = 0; it < reps; ++it) cudaLaunchKernelEx(&cfg, loads_rounds<CL>, full, part, mc, npix, per, cblocks, sink);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = (double)grid * per * 9 * cblocks * 16384.0 * reps;     // bytes DELIVERED into shared memory
+        printf("C %d cluster of %d, %s: %s  %.1f us per launch, %.2f TB/s delivered in aggregate, %.1f GB/s per SM\n", C, CL,
+               mc ? "each CTA loads 1/CL of the box and multicasts it" : "every CTA loads the whole box", cudaGetErrorString(e), ms / reps * 1e3,
+               bytes / (ms * 1e-3) / 1e12, bytes / (ms * 1e-3) / grid / 1e9);
+    }
+}
+
 int main(int argc, char **argv)
 {
     const int C = argc > 1 ? atoi(argv[1]) : 256, npix = 64 * 26 * 26, cblocks = C / 64;
@@ -110,5 +194,7 @@ int main(int argc, char **argv)
                layout == 0 ? "NHWC, own tiles" : layout == 1 ? "channel-blocked, own tiles" : layout == 2 ? "NHWC, same tiles for every SM" : layout == 3 ? "4-D tiled box 2x2x32" : "im2col 128 pixels", cudaGetErrorString(e), ms / reps * 1e3,
                bytes / (ms * 1e-3) / 1e12, bytes / (ms * 1e-3) / 148 / 1e9);
     }
+    run_rounds<2>(d, C, npix, cblocks, sink);
+    run_rounds<4>(d, C, npix, cblocks, sink);
     return 0;
 }
