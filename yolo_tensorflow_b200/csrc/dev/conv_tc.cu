@@ -250,7 +250,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
             int stage = 0; uint32_t phase = 0;
             pdl_wait();
             for (int vt = pair_id; vt < num_tiles; vt += num_pairs) {
-                VTile v; v.tile = vt; v.col_off = 0; v.width = args.block_n;
+                VTile v; v.tile = vt; v.col_off = 0; v.width = args.block_n; v.k0 = 0; v.k1 = args.num_kblocks; v.row_off = 0;
                 if (RING) v = vtile_of(args, vt);
                 const int tile = v.tile, half_w = v.width / 2;
                 const uint32_t tx_bytes = 2u * (uint32_t)(args.a_rows * BLOCK_K * 2 + half_w * BLOCK_K * 2);
@@ -261,7 +261,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
                     int tx = m_tile % args.tiles_x, ty = (m_tile / args.tiles_x) % args.tiles_y, tn = m_tile / (args.tiles_x * args.tiles_y);
                     ox0 = tx * args.TW; oy0 = ty * args.TH; n0 = tn * args.TN;      // a phantom last tile lands past the batch: TMA zero-fills
                 } else if (args.im2col) im2col_origin(args, m_tile, ox0, oy0, n0);
-                for (int kb = 0; kb < args.num_kblocks; ++kb) {
+                for (int kb = v.k0; kb < v.k1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
 #ifdef B200_EXPERIMENTS                            // make EXPERIMENTS=1: scripts/operand_traffic_probe.py
                     if (args.exp) {               // timing experiment: skip operand loads once every stage holds something
@@ -318,19 +318,20 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs ar
             const uint64_t adesc0 = make_desc<BLOCK_K>(smem_u32(sA)), bdesc0 = make_desc<BLOCK_K>(smem_u32(sB));
             const uint32_t a_step = (uint32_t)A_BYTES >> 4, b_step = (uint32_t)args.b_stage_bytes >> 4;
             for (int vt = pair_id; vt < num_tiles; vt += num_pairs) {
-                const int width = RING ? vtile_of(args, vt).width : args.block_n;
-                const uint32_t idesc = idesc_base | ((uint32_t)(width >> 3) << 17);
+                VTile v; v.width = args.block_n; v.k0 = 0; v.k1 = args.num_kblocks;
+                if (RING) v = vtile_of(args, vt);
+                const uint32_t idesc = idesc_base | ((uint32_t)(v.width >> 3) << 17);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * args.block_n);
-                for (int kb = 0; kb < args.num_kblocks; ++kb) {
+                for (int kb = v.k0; kb < v.k1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)stage * a_step);
                     const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)stage * b_step);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k)
-                        tc2_mma_bf16_elect(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc2_mma_bf16_elect(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, ((kb - v.k0) | k) != 0 ? 1u : 0u);
                     tc2_commit_both_elect(&empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -372,6 +373,66 @@ template <int BLOCK_K, typename OutT> static void launch_pair_variant(ConvTcPlan
     }
     if (p->args.ring) launch_pdl(conv_tc_pair_kernel<BLOCK_K, bf16, true>, p->grid, kTcRingThreads, p->smem_bytes, s, 2, p->maps, p->args);
     else launch_pdl(conv_tc_pair_kernel<BLOCK_K, OutT, false>, p->grid, kTcThreads, p->smem_bytes, s, 2, p->maps, p->args);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// split-K finalize: out[p][c] = act(scale[c] * sum_s ws[s][p][c] + shift[c]) (+ residual), bf16.  The slabs are summed in a
+// fixed order (s = 0, 1, ...): deterministic, unlike atomics.  One thread per 8 channels of one pixel; the workspace is
+// L2-resident (a few MB).  Replaces the epilogue of convolutional_layer.c:445-485 for launches with too few tiles to fill
+// the chip (small batches), where cutting K shortens the layer's critical path (13x13 3x3 512->1024 at batch 1: 72 k-blocks).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const float *__restrict__ ws, int ksplit, long long slab_elems, long long npix, int cout_pad,
+                       const float *__restrict__ scale, const float *__restrict__ shift, int leaky,
+                       const bf16 *__restrict__ res, int ldr, float alpha, float beta, bf16 *__restrict__ out, int ldo)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const int groups = cout_pad >> 3;
+    const long long total = npix * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / groups;
+        const int c = (int)(i - p * groups) << 3;
+        const float *src = ws + p * cout_pad + c;
+        float4 a = *reinterpret_cast<const float4 *>(src), b = *reinterpret_cast<const float4 *>(src + 4);
+        for (int s = 1; s < ksplit; ++s) {
+            const float4 a2 = *reinterpret_cast<const float4 *>(src + s * slab_elems), b2 = *reinterpret_cast<const float4 *>(src + s * slab_elems + 4);
+            a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+        }
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float4 s0 = *reinterpret_cast<const float4 *>(scale + c), s1 = *reinterpret_cast<const float4 *>(scale + c + 4);
+        const float4 h0 = *reinterpret_cast<const float4 *>(shift + c), h1 = *reinterpret_cast<const float4 *>(shift + c + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            v[q] = fmaf(v[q], sc[q], sh[q]);
+            if (leaky) v[q] = v[q] > 0.f ? v[q] : 0.1f * v[q];
+        }
+        if (res) {
+            float r[8];
+            load_vec<bf16>(res + p * ldr + c, r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaf(alpha, v[q], beta * r[q]);
+        }
+        store_vec<bf16>(out + p * ldo + c, v);
+    }
+}
+
+void conv_tc_launch_splitk_finalize(ConvTcPlan *p, cudaStream_t s)
+{
+    const ConvTcPlan::SplitK &k = p->sk;
+    const long long total = k.npix * (k.cout_pad >> 3);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    static const bool no_pdl = getenv("B200_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    B200_CHECK(cudaLaunchKernelEx(&cfg, splitk_finalize_kernel, (const float *)k.ws, p->args.ksplit, (long long)p->args.slab_rows * k.cout_pad, k.npix, k.cout_pad,
+                                  k.scale, k.shift, k.act == ACT_LEAKY ? 1 : 0, k.res, k.ldr, k.res_alpha, k.res_beta, k.out, k.ldo));
 }
 
 void conv_tc_launch_tap(ConvTcPlan *p, cudaStream_t s)

@@ -51,6 +51,10 @@ struct ConvTcArgs {
     // tail splitting (CTA-pair kernel, ring epilogue): the tiles of the last, partly filled wave are cut into `split` filter
     // slices so that every pair works during it.  Virtual tile v < split_from is tile v at full width; the others are slices.
     int split_from, split, vtiles;
+    // split-K (CTA-pair kernel, ring epilogue): a launch with few pixel tiles (small batches) cuts every tile's K loop into `ksplit`
+    // ranges of `kb_per` k-blocks, one work unit each; unit (tile, s) stores its raw fp32 accumulators into slab s of a workspace
+    // ([ksplit][slab_rows][cout_pad], rows = pixels) and splitk_finalize_kernel sums the slabs in a fixed order.
+    int ksplit, kb_per, slab_rows;
     int local, ss_stride;    // unshared convolution: weight box and shift row of tile's location (m_tile % locations); floats per shift row
     int ring;                // 1: ring epilogue (ring_roles) with 384 threads; c_bufs = ring depth (<= 4)
     int n_split;             // CTAs per pixel tile, each computing block_n of the cout_pad filters
@@ -303,10 +307,18 @@ template <int PENDING> __device__ __forceinline__ void bulk_wait_read()
 // Nothing in a tile's epilogue waits on a DRAM round trip or on another role's bookkeeping; the roles only meet at
 // mbarriers.  With the serial epilogue (run_epilogue) a fused shortcut cost the 52x52 layers 18 % (990 vs 1200 TFLOP/s).
 // ---------------------------------------------------------------------------------------------------
-struct VTile { int tile, col_off, width; };
+struct VTile { int tile, col_off, width, k0, k1, row_off; };
 __device__ __forceinline__ VTile vtile_of(const ConvTcArgs &a, int v)
 {
     VTile t;
+    t.k0 = 0; t.k1 = a.num_kblocks; t.row_off = 0;
+    if (a.ksplit > 1) {
+        const int s = v % a.ksplit;
+        t.tile = v / a.ksplit; t.col_off = 0; t.width = a.block_n;
+        t.k0 = s * a.kb_per; t.k1 = t.k0 + a.kb_per < a.num_kblocks ? t.k0 + a.kb_per : a.num_kblocks;
+        t.row_off = s * a.slab_rows;
+        return t;
+    }
     if (v < a.split_from) { t.tile = v; t.col_off = 0; t.width = a.block_n; return t; }
     const int w = v - a.split_from;
     t.width = a.block_n / a.split;
@@ -316,7 +328,7 @@ __device__ __forceinline__ VTile vtile_of(const ConvTcArgs &a, int v)
 }
 
 struct RingTile {
-    int n_tile, m_tile, col0, tx, ty, tn, rows_here, nsub;
+    int n_tile, m_tile, col0, tx, ty, tn, rows_here, nsub, row_off;
     bool real;
 };
 template <bool PAIR>
@@ -329,6 +341,7 @@ __device__ __forceinline__ RingTile ring_tile(const ConvTcArgs &args, int vt, in
     t.m_tile = PAIR ? 2 * (tile / args.n_tiles) + rank : tile / args.n_tiles;
     t.col0 = t.n_tile * args.block_n + v.col_off;
     t.nsub = v.width / args.sub_cols;
+    t.row_off = v.row_off;
     t.tx = t.ty = t.tn = 0; t.rows_here = 0;
     t.real = t.m_tile < args.m_tiles;                       // an odd tile count leaves the pair's second CTA a phantom tile
     if (args.mode >= 1) { t.tx = t.m_tile % args.tiles_x; t.ty = (t.m_tile / args.tiles_x) % args.tiles_y; t.tn = t.m_tile / (args.tiles_x * args.tiles_y); }
@@ -416,7 +429,7 @@ __device__ __forceinline__ void ring_roles(const ConvTcMaps &maps, const ConvTcA
                     const int slot = j % NBUF;
                     const uint8_t *src = sC + (size_t)slot * 16384;
                     MBAR_WAIT_HERE(&cwritten[slot], (j / NBUF) & 1);
-                    if (args.mode == 0) tma_store_2d(&maps.c, src, t.col0 + SUBC * q, t.m_tile * 128);
+                    if (args.mode == 0) tma_store_2d(&maps.c, src, t.col0 + SUBC * q, t.m_tile * 128 + t.row_off);
                     else if (args.mode == 1) {
                         tma_store_4d(&maps.c, src, t.col0 + SUBC * q, t.tx * args.TW, t.ty * args.TH, t.tn * args.TN);
                         if (args.upsample)                 // upsample_layer.c:72-96 (nearest, stride 2) fused: same tile, three more phases

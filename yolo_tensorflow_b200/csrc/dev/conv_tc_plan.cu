@@ -124,9 +124,18 @@ void launch_conv_tc(ConvTcPlan *p, cudaStream_t s)
     else if (p->args.mode == 2) conv_tc_launch_patch(p, s);
     else conv_tc_launch_tap(p, s);
     B200_LAUNCHED();
+    if (p->args.ksplit > 1) { conv_tc_launch_splitk_finalize(p, s); B200_LAUNCHED(); }
 }
 
-void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
+void conv_tc_plan_destroy(ConvTcPlan *p)
+{
+    if (!p) return;
+    if (p->sk.ws) cudaFree(p->sk.ws);
+    if (p->sk.ones) cudaFree(p->sk.ones);
+    delete p;
+}
+
+static int pair_tiles_for_split(const ConvTcArgs &a) { return ((a.m_tiles + 1) / 2) * a.n_tiles; }
 
 // shape test shared with the planner (engine.cu decides about shortcut fusion before buffers exist)
 bool conv_tc_shape_supported(int cin, int stride, int act)
@@ -444,7 +453,24 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
                  out.ld % 8 == 0 && (!residual || residual->ld % 8 == 0) && a.num_kblocks * (cp.cout_pad < 256 ? cp.cout_pad : 256) >= 4 * 128;
     // MEASURED (YOLOv3-416 b64): the ring epilogue wins on every stageable layer (1x1 layers -10..-20 %, fused shortcuts
     // -8 %) except the stride-2 3x3 layers without a residual, which lose the pipeline stage the ring's slots cost (+3 %).
-    const bool ring_pays = residual || !(cp.size == 3 && cp.stride == 2 && a.block_n == 256);
+    // split-K (small batches): a mode-0 layer whose pixel tiles occupy at most half of the 74 CTA pairs and whose K loop is long
+    // is cut along K so that the idle pairs shorten its critical path; the partial sums go through an fp32 workspace
+    // (ring epilogue with 32-column fp32 sub-tiles) and splitk_finalize_kernel applies batch-norm, activation and shortcut.
+    int want_ksplit = 1;
+    {
+        const long long tiles_pair = (long long)((a.m_tiles + 1) / 2) * a.n_tiles;
+        if (a.mode == 0 && !local && !up_out && !getenv("B200_NO_SPLITK") && stageable64 && out.dtype == DT_BF16 && block_k == 64 &&
+            a.block_n % 64 == 0 && a.block_n >= 64 && a.m_tiles >= 2 && tiles_pair <= 37 && a.num_kblocks >= 18) {
+            // MEASURED (batch 1, forward pass): at most 8 ranges of at least 4 k-blocks — YOLOv3 1.120 -> 0.979 ms, YOLOv3-tiny 0.206 ->
+            // 0.177 ms, YOLOv2 0.542 -> 0.380 ms; up to 32 ranges 1.037 / 0.185 / 0.421 (the finalize pass reads every slab);
+            // splitting layers from 8 k-blocks on loses (1.054 ms): below 18 the second launch costs more than the K loop saves
+            int s_max = (int)(74 / tiles_pair), by_k = a.num_kblocks / 4;
+            int S = s_max < by_k ? s_max : by_k;
+            if (S > 8) S = 8;
+            if (S >= 2) want_ksplit = S;
+        }
+    }
+    const bool ring_pays = want_ksplit > 1 || residual || !(cp.size == 3 && cp.stride == 2 && a.block_n == 256);
     const bool want_staged = stageable && ring_pays;
     const bool use_ring = want_staged && a.mode != 2 && !getenv("B200_NO_RING");
     int ring_slots = 3;                                  // measured: 3 slots beat 2 and 4 (a 4th costs a pipeline stage)
@@ -554,6 +580,35 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
 #ifdef B200_EXPERIMENTS
     if (getenv("B200_EXP") && a.pair && (a.mode == 0 || cp.stride == 1)) a.exp = atoi(getenv("B200_EXP"));
 #endif
+    memset(&p->sk, 0, sizeof p->sk);
+    if (want_ksplit > 1 && a.pair && a.ring && a.split == 1) {
+        const int kb_per = (a.num_kblocks + want_ksplit - 1) / want_ksplit;
+        const int S = (a.num_kblocks + kb_per - 1) / kb_per;
+        const long long slab_rows = (long long)a.m_tiles * 128;
+        const size_t ws_bytes = (size_t)S * slab_rows * cp.cout_pad * sizeof(float);
+        if (S >= 2 && ws_bytes <= (64u << 20)) {
+            ConvTcPlan::SplitK &k = p->sk;
+            B200_CHECK(cudaMalloc(&k.ws, ws_bytes));
+            B200_CHECK(cudaMalloc(&k.ones, 2 * (size_t)cp.cout_pad * sizeof(float)));
+            std::vector<float> host(2 * (size_t)cp.cout_pad, 0.f);
+            for (int i = 0; i < cp.cout_pad; ++i) host[i] = 1.f;
+            B200_CHECK(cudaMemcpy(k.ones, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+            k.scale = cp.scale; k.shift = cp.shift; k.act = cp.act;
+            k.res = a.res; k.ldr = a.ldr; k.res_alpha = a.res_alpha; k.res_beta = a.res_beta;
+            k.out = (bf16 *)out.p; k.ldo = out.ld; k.npix = a.npix; k.cout_pad = cp.cout_pad;
+            // the tile kernel now produces raw fp32 partial sums: identity epilogue, 32-column fp32 sub-tiles, slab-addressed stores
+            a.ksplit = S; a.kb_per = kb_per; a.slab_rows = (int)slab_rows;
+            p->flow_ok = false;                                  // (a flow would read the identity epilogue constants)
+            a.scale = k.ones; a.shift = k.ones + cp.cout_pad; a.act = ACT_LINEAR; a.res = nullptr;
+            a.sub_cols = 32; a.out_f32 = 1;
+            a.vtiles = pair_tiles_for_split(a) * S;
+            p->grid = 2 * (a.vtiles < 74 ? a.vtiles : 74);
+            unsigned long long dims[2] = {(unsigned long long)cp.cout_pad, (unsigned long long)(S * slab_rows)};
+            unsigned long long strides[1] = {(unsigned long long)cp.cout_pad * sizeof(float)};
+            unsigned box[2] = {32, 128};
+            tc_encode_tiled(&p->maps.c, 1, 2, k.ws, dims, strides, box, 128);
+        }
+    }
     p->flops = 2.0 * (double)a.npix * out.c * K;
     char buf[256];
     snprintf(buf, sizeof buf, "conv_tc mode%d k%d n%d tile %dx%dx%d rows %d m_tiles %d n_tiles %d stages %d smem %zu grid %d%s%s",
@@ -566,6 +621,7 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     else if (a.staged) p->desc += " stagedEpilogue";
     if (a.upsample) p->desc += " +upsample2x";
     if (a.local) p->desc += " unshared(local)";
+    if (a.ksplit > 1) p->desc += " splitK(" + std::to_string(a.ksplit) + "x" + std::to_string(a.kb_per) + ")";
     if (a.split > 1) p->desc += " tailSplit(" + std::to_string(a.split) + "x" + std::to_string(a.vtiles - a.split_from) + ")";
     return p;
 }

@@ -16,6 +16,16 @@ struct ConvTcPlan {
     const void *w;           // repacked weights [cout_pad][K]
     int K;
     bool flow_ok;            // the layer can be a member of a flow (see conv_tc_flow_create)
+    // split-K plans (args.ksplit > 1): the tile kernel writes raw fp32 partial sums into `ws`, splitk_finalize_kernel produces the layer's output
+    struct SplitK {
+        float *ws;                       // [ksplit][slab_rows][cout_pad] fp32, owned by the plan
+        float *ones;                     // the tile kernel's epilogue constants: scale 1 (cout_pad floats) followed by shift 0
+        const float *scale, *shift;      // the layer's folded batch-norm, applied by the finalize kernel
+        int act;
+        const bf16 *res; int ldr; float res_alpha, res_beta;
+        bf16 *out; int ldo;
+        long long npix; int cout_pad;
+    } sk;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -113,3 +123,4 @@ template <typename Kernel> static void launch_pdl(Kernel kernel, int grid, int t
 void conv_tc_launch_tap(ConvTcPlan *p, cudaStream_t s);        // conv_tc.cu: conv_tc_kernel / conv_tc_pair_kernel
 void conv_tc_launch_patch(ConvTcPlan *p, cudaStream_t s);      // conv_tc_patch.cu: conv_tc_patch_kernel
 void conv_tc_launch_block(ConvTcPlan *p, cudaStream_t s);      // conv_tc_patch.cu: conv_tc_block_kernel
+void conv_tc_launch_splitk_finalize(ConvTcPlan *p, cudaStream_t s);   // conv_tc.cu: splitk_finalize_kernel (after the tile kernel of a split-K plan)
