@@ -459,7 +459,8 @@ ConvTcPlan *conv_tc_plan_create(TView in, TView out, ConvParams cp, const TView 
     int want_ksplit = 1;
     {
         const long long tiles_pair = (long long)((a.m_tiles + 1) / 2) * a.n_tiles;
-        if (a.mode == 0 && !local && !up_out && !getenv("B200_NO_SPLITK") && stageable64 && out.dtype == DT_BF16 && block_k == 64 &&
+        const bool flows_requested = getenv("B200_FLOW") && atoi(getenv("B200_FLOW")) != 0;     // a flow member keeps its whole K loop
+        if (a.mode == 0 && !local && !up_out && !getenv("B200_NO_SPLITK") && !flows_requested && stageable64 && out.dtype == DT_BF16 && block_k == 64 &&
             a.block_n % 64 == 0 && a.block_n >= 64 && a.m_tiles >= 2 && tiles_pair <= 37 && a.num_kblocks >= 18) {
             // MEASURED (batch 1, forward pass): at most 8 ranges of at least 4 k-blocks — YOLOv3 1.120 -> 0.979 ms, YOLOv3-tiny 0.206 ->
             // 0.177 ms, YOLOv2 0.542 -> 0.380 ms; up to 32 ranges 1.037 / 0.185 / 0.421 (the finalize pass reads every slab);
