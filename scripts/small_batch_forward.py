@@ -1,5 +1,8 @@
+#!/usr/bin/env python3
+"""Forward-pass device time at small batches (YOLOv3 batch 1 and 4, YOLOv3-tiny and YOLOv2 batch 1) and how many layers the
+planner split along K; run it again with B200_NO_SPLITK=1 for the A/B.  Usage: small_batch_forward.py"""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yolo_tensorflow_b200 import synth, darknet as dn
 import numpy as np
 work = "/tmp/b200_bench"
