@@ -495,6 +495,11 @@ def main_engine(args):
                     "conv_ms_per_step": conv_ms, "forward_ms": fwd_ms, "first_layer_ms": first_ms,
                     "timing": "b200_profile_forward: CUDA events around the whole pass as the step enqueues it (no per-layer brackets), minus the first layer",
                     "non_conv_launches_in_pass": others,
+                    "why_not_higher": "DESIGN.md section 5: (1) every launch pays a batch-independent 10-25 us (profiles/r2_launch_anatomy.txt); (2) the "
+                                      "cross-layer persistent kernel that removes the boundaries (B200_FLOW=1, bit-identical) reaches 82 % tensor-issue "
+                                      "occupancy and is 1-3 % slower: the chip clocks down under sustained tensor load (profiles/r2_flow_*.txt); (3) the "
+                                      "tensor pipe alone runs a 3x3 layer at 1709 TFLOP/s, operand delivery holds the mainloop at 0.47 us per k-block "
+                                      "instead of 0.375 (profiles/r2_operand_traffic_probe.txt, r2_ncu_operand_path.txt)",
                     "conv_tflop_per_step": conv_flops / 1e12,
                     "whole_step_tflops_per_gpu": FLOP_PER_IMAGE * BATCH / (ms / args.steps) * 1e-9,
                     "whole_step_frac_burst": FLOP_PER_IMAGE * BATCH / (ms / args.steps) * 1e-9 / pk["burst"]}
