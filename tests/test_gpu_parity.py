@@ -1279,3 +1279,27 @@ def test_split_k_layers_match_the_unsplit_plan(dn, model, size, batch, workdir):
         if L.type in ("yolo", "region"):
             assert_free_running_heads(net.layer_output(i), outs[i].reshape(batch, -1), (model, i))
     net.close(); ref.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,size,batch", [("yolov3", 416, 16), ("yolov2", 288, 5)])
+def test_im2col_mode_loads_are_bit_identical_to_rectangular_tiles(dn, model, size, batch, workdir):
+    """the 3x3 tap kernels fed by TMA im2col-mode loads (any 128 consecutive output pixels per tile) against the same kernels fed by
+    rectangular 4-D pixel boxes and parity-phase views (B200_NO_IM2COL=1): the tiling differs, every output element sums the same
+    products in the same order -> identical bits in every materialised layer"""
+    os.environ["B200_NO_SPLITK"] = "1"                 # (split-K only exists for the dense / im2col tiling)
+    try:
+        net, cfg, wpath = open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
+        os.environ["B200_NO_IM2COL"] = "1"
+        ref, _, _ = open_net(dn, model, batch, size, workdir, dn.PREC_BF16)
+    finally:
+        os.environ.pop("B200_NO_IM2COL", None); os.environ.pop("B200_NO_SPLITK", None)
+    plans = [dn.lib.b200_layer_plan(net.ptr, i).decode() for i in range(net.n)]
+    assert sum("im2colTMA" in p for p in plans) >= 5 and not any("im2colTMA" in dn.lib.b200_layer_plan(ref.ptr, i).decode() for i in range(ref.n))
+    x = synth.make_images(batch, 3, size, size, 4242)
+    net.predict(x); ref.predict(x)
+    for i in range(net.n):
+        if net.kernel(i) in NOT_MATERIALISED or net.layers[i]["type_name"] not in ("CONVOLUTIONAL", "SHORTCUT", "YOLO", "REGION"):
+            continue
+        assert np.array_equal(net.layer_output(i), ref.layer_output(i)), (i, net.kernel(i), plans[i])
+    net.close(); ref.close()
