@@ -384,11 +384,21 @@ def dropin_latency(dn, sampler, iters=30):
             "do_nms_sort_ms": med["nms"], "candidates": int(num.value), "iters": iters, "clocks": sampler.summary(t_begin, t_end) if sampler else None}
 
 
+_T0 = time.time()
+
+
+def note(rank, msg):
+    """progress line on stderr (rank 0): if a run is cut off, the log says in which phase"""
+    if rank == 0:
+        print("[bench %6.1f s] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def main_engine(args):
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    note(rank, "torch imported, world %d" % world)
     torch.cuda.set_device(local)
     if world > 1:
         # torch.distributed is the control plane only (rendezvous, barriers, max over ranks, the 128-byte NCCL id); the data-path
@@ -397,6 +407,7 @@ def main_engine(args):
             dist.init_process_group("gloo")
         else:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    note(rank, "process group up")
     from yolo_tensorflow_b200 import synth, darknet as dn
     dn.set_gpu(local)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -413,6 +424,7 @@ def main_engine(args):
     run = Runner(dn, torch, HEAD, BATCH, rank, world, local, load_weights=(rank == 0))
     if world > 1:
         run.join(dist, image_base=rank * BATCH, gather=True)
+    note(rank, "headline network planned, weights on every rank")
     x_host = run.load_resident(1002 + rank)           # per-rank image shard: a different seeded batch on every rank
     in_bytes = BATCH * 3 * SIZE * SIZE * 4
     net = run.net
@@ -427,6 +439,7 @@ def main_engine(args):
     run.drain()                                       # the forward pass pre-enqueued for a step that will not come
     total_records = int(nrec)                         # on rank 0 with the gather on: the records of ALL ranks for the last step
 
+    note(rank, "headline timed (%.3f ms per step)" % (ms / args.steps))
     # ---- e2e (a): fp32 NCHW host batches, as network_predict takes them ---------------------------------
     x_host2 = torch.from_numpy(synth.make_images(BATCH, 3, SIZE, SIZE, 2002 + rank)).pin_memory()
     host_batches = [x_host, x_host2]
@@ -467,6 +480,7 @@ def main_engine(args):
     dn.lib.b200_detect_submitted(net.ptr, None, 0, 0, THRESH, NMS, 1, run.out, run.max_out, run.counts)           # drain
     e2e_u8 = world * BATCH * args.steps / (ms_u8 / 1000.0)
 
+    note(rank, "e2e loops timed")
     # ---- roofline of the dominant kernel family (rank 0) -------------------------------------------------
     roofline = None
     if rank == 0:
@@ -506,6 +520,7 @@ def main_engine(args):
     head_clocks = sampler.summary(*win) if sampler else None
     run.close()
 
+    note(rank, "roofline record done")
     # ---- C4: 608x608, 256 images per step split over the ranks (strong scaling), records gathered to rank 0 ----------
     c4 = None
     if not args.headline_only:
@@ -530,6 +545,7 @@ def main_engine(args):
                   "records_gathered_on_rank0_per_step": int(nrec4), "gather": "ncclSend/ncclRecv of fixed record slots inside the step (b200_comm_set_gather)" if world > 1 else "single GPU",
                   "clocks": sampler.summary(*win4) if sampler else None}
 
+    note(rank, "C4 done")
     # ---- the other configurations and the drop-in latency (one GPU only) -----------------------------------------
     other, dropin = None, None
     if world == 1 and not args.headline_only:
