@@ -55,6 +55,9 @@ int  b200_flow_trace(network *net, int k, unsigned long long *out, int max_items
  * spec[4k..4k+3] = {filter size 1|3, stride, input channels, filters}, is scheduled on `pairs` CTA pairs and the item lists are
  * replayed without the cost model; returns -1 when every item runs exactly once (no deadlock), else the first stuck item */
 int  b200_flow_schedule_selftest(int n, const int *spec, int batch, int hw, int pairs, double *makespan_us, double *work_us);
+/* host-only: the completion counters a consuming tile waits on (flow_dep_range) cover every input pixel its taps read;
+ * -1 = yes for every tile, else the first offending tile */
+int  b200_flow_dep_selftest(int batch, int in_h, int in_w, int size, int stride);
 
 /* ---- opaque engine, one per network -------------------------------------------------------------- */
 typedef struct b200_engine b200_engine;

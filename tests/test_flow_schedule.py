@@ -57,3 +57,17 @@ def test_odd_sizes_and_single_tile_layers():
     for batch, hw in ((1, 7), (2, 9), (7, 11), (1, 1)):
         rc, _, _ = run([(3, 1, 64, 64), (1, 1, 64, 128), (3, 1, 128, 64), (1, 1, 64, 64), (3, 1, 64, 64)], batch, hw)
         assert rc == -1, (batch, hw, rc)
+
+
+lib.b200_flow_dep_selftest.argtypes = [ctypes.c_int] * 5
+lib.b200_flow_dep_selftest.restype = ctypes.c_int
+
+
+@pytest.mark.parametrize("size,stride", [(1, 1), (3, 1), (3, 2), (5, 1)])
+def test_dependency_ranges_cover_the_taps(size, stride):
+    """the counters a tile waits on before loading its operands cover every input pixel any of its taps reads (brute force over
+    all tiles), for maps that are multiples of the tile, smaller than a tile, odd and non-square"""
+    for batch, h, w in ((64, 13, 13), (8, 26, 26), (3, 52, 52), (2, 19, 19), (1, 7, 5), (5, 1, 1), (2, 40, 56), (1, 104, 104), (3, 76, 38)):
+        if size == 1 and stride != 1:
+            continue
+        assert lib.b200_flow_dep_selftest(batch, h, w, size, stride) == -1, (batch, h, w, size, stride)

@@ -907,3 +907,33 @@ extern "C" int b200_flow_schedule_selftest(int n, const int *spec, int batch, in
     if (work_us) *work_us = wk / pairs;
     return flow_schedule_check(L, ctr, pairs, sched, off);
 }
+
+// Host-only check of flow_dep_range (the counters a consuming tile waits on) against the brute-force footprint of the tile:
+// for every 256-pixel tile of a size x size / stride convolution over a batch x in_h x in_w input, every input pixel that any tap
+// of any output pixel of the tile reads must belong to a counter inside [jlo, jhi].  Returns -1 when that holds for all tiles,
+// else the first tile that would read data it did not wait for.
+extern "C" int b200_flow_dep_selftest(int batch, int in_h, int in_w, int size, int stride)
+{
+    FlowLayerArgs a;
+    memset(&a, 0, sizeof a);
+    a.size = size; a.stride = stride; a.pad = size / 2; a.im2col = size > 1;
+    a.in_H = in_h; a.in_W = in_w;
+    a.OH = (in_h + 2 * a.pad - size) / stride + 1; a.OW = (in_w + 2 * a.pad - size) / stride + 1;
+    a.npix = batch * a.OH * a.OW;
+    const int m_pairs = (a.npix + 255) / 256;
+    for (int mp = 0; mp < m_pairs; ++mp) {
+        int jlo, jhi;
+        flow_dep_range(a, mp, jlo, jhi);
+        for (int p = mp * 256; p < (mp + 1) * 256 && p < a.npix; ++p) {
+            const int n = p / (a.OH * a.OW), r = p % (a.OH * a.OW), oy = r / a.OW, ox = r % a.OW;
+            for (int ky = 0; ky < size; ++ky)
+                for (int kx = 0; kx < size; ++kx) {
+                    const int iy = oy * stride - a.pad + ky, ix = ox * stride - a.pad + kx;
+                    if (iy < 0 || iy >= in_h || ix < 0 || ix >= in_w) continue;            // zero fill: nothing is read
+                    const int q = ((n * in_h + iy) * in_w + ix) >> 8;
+                    if (size == 1 ? q != mp || jlo != mp || jhi != mp : (q < jlo || q > jhi)) return mp;
+                }
+        }
+    }
+    return -1;
+}
